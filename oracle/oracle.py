@@ -1,0 +1,321 @@
+"""ctypes front end of the CPU oracle (oracle/ofdm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (gr-ofdm_tools_b200/) never imports it.
+
+Also holds numpy restatements of the reference's host-side generators:
+  * _make_sync_word1/2      python/ofdm_txrx_modules.py:75-104 (sqrt(2) amplitude)
+  * _make_sync_word1 (1.42) python/ofdm_cr_tools.py:262-279
+  * spectrum_enforcer       python/ofdm_cr_tools.py:348-378
+PARITY: partially pinned (see ofdm_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = [os.path.join(_HERE, f) for f in ("ofdm_oracle.c", "ofdm_oracle.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("fft_len", C.c_int32), ("cp_len", C.c_int32),
+        ("n_occ_sets", C.c_int32), ("occ_sizes", C.c_void_p), ("occ_carriers", C.c_void_p),
+        ("n_pilot_sets", C.c_int32), ("pilot_sizes", C.c_void_p), ("pilot_carriers", C.c_void_p),
+        ("n_pilot_sym_sets", C.c_int32), ("pilot_sym_sizes", C.c_void_p), ("pilot_symbols", C.c_void_p),
+        ("sync_word1", C.c_void_p), ("sync_word2", C.c_void_p),
+        ("bps_header", C.c_int32), ("bps_payload", C.c_int32),
+        ("scramble_header", C.c_int32), ("scramble_seed", C.c_int32),
+        ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
+        ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32),
+    ]
+
+
+FRAME_DTYPE = np.dtype([
+    ("trigger", "<i8"), ("cfo", "<f4"), ("carr_offset", "<i4"), ("flags", "<u4"),
+    ("pkt_len", "<u2"), ("pkt_num", "<u2"), ("frame_syms", "<u4"), ("slot", "<u4"),
+])
+assert FRAME_DTYPE.itemsize == 32
+F_HDR_OK, F_CRC_OK, F_COMPLETE, F_ACCEPTED = 1, 2, 4, 8
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.orc_crc32.restype = C.c_uint32
+        L.orc_crc32.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_crc8.restype = C.c_uint8
+        L.orc_crc8.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_lfsr_bits.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64]
+        L.orc_scramble.argtypes = [C.c_void_p, C.c_int64, C.c_uint32]
+        L.orc_repack.restype = C.c_int64
+        L.orc_repack.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_header_len.argtypes = [C.c_void_p]
+        L.orc_header_format.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_header_parse.argtypes = [C.c_void_p, C.c_void_p] + [C.c_void_p] * 4
+        L.orc_constellation.argtypes = [C.c_int, C.c_void_p]
+        L.orc_decide.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.orc_fft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_tx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                             C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_tx_frame_samples.restype = C.c_int64
+        L.orc_tx_frame_samples.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_sync_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_rx.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                             C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_int64, C.c_void_p]
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side generators (numpy restatements)
+# ---------------------------------------------------------------------------------------------
+def _active_carriers(fft_len, occupied_carriers, pilot_carriers):
+    # python/ofdm_txrx_modules.py:66-73
+    act = []
+    for c in list(occupied_carriers[0]) + list(pilot_carriers[0]):
+        act.append(c + fft_len if c < 0 else c)
+    return act
+
+
+def make_sync_word1(fft_len, occupied_carriers, pilot_carriers, amplitude=None):
+    """python/ofdm_txrx_modules.py:75-91 (amplitude sqrt 2) / python/ofdm_cr_tools.py:262-279 (1.42)."""
+    amp = np.sqrt(2) if amplitude is None else amplitude
+    act = set(_active_carriers(fft_len, occupied_carriers, pilot_carriers))
+    np.random.seed(42)
+    bpsk = {0: amp, 1: -amp}
+    sw1 = [bpsk[np.random.randint(2)] if (x in act and x % 2) else 0 for x in range(fft_len)]
+    return np.fft.fftshift(sw1)
+
+
+def make_sync_word2(fft_len, occupied_carriers, pilot_carriers):
+    """python/ofdm_txrx_modules.py:93-104."""
+    act = set(_active_carriers(fft_len, occupied_carriers, pilot_carriers))
+    np.random.seed(42)
+    bpsk = {0: 1, 1: -1}
+    sw2 = [bpsk[np.random.randint(2)] if x in act else 0 for x in range(fft_len)]
+    sw2[0] = 0j
+    return np.fft.fftshift(sw2)
+
+
+def spectrum_enforcer(fft_len, spectrum_constraint_fft, lobe_len):
+    """python/ofdm_cr_tools.py:348-378 (integer division as in Python 2)."""
+    usable = list(range(-fft_len // 2, fft_len // 2, 1))
+    usable.remove(0)
+    del usable[0:lobe_len]
+    del usable[-lobe_len:]
+    for carr in spectrum_constraint_fft:
+        if carr in usable:
+            usable.remove(carr)
+    space = len(usable) // 8
+    middle = len(usable) // 2
+    pilots = ((usable[middle - 3 * space], usable[middle - space],
+               usable[middle + space], usable[middle + 3 * space]),)
+    for carr in pilots[0]:
+        usable.remove(carr)
+    occ = (usable,)
+    sw1 = make_sync_word1(fft_len, occ, pilots, amplitude=1.42)
+    sw2 = make_sync_word2(fft_len, occ, pilots)
+    return occ, pilots, ((1, 1, 1, -1),), sw1.tolist(), sw2.tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+class Oracle:
+    """One PHY configuration of the CPU oracle (argument names follow ofdm_tx/ofdm_rx,
+    python/ofdm_txrx_modules.py:143-155,278-291)."""
+
+    def __init__(self, fft_len=64, cp_len=16, occupied_carriers=None, pilot_carriers=None,
+                 pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
+                 scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
+                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None):
+        self.fft_len, self.cp_len = int(fft_len), int(cp_len)
+        self.occ = [list(map(int, s)) for s in occupied_carriers]
+        self.pil = [list(map(int, s)) for s in pilot_carriers]
+        self.pls = [list(map(complex, s)) for s in pilot_symbols]
+        if sync_word1 is None:
+            sync_word1 = make_sync_word1(fft_len, self.occ, self.pil)
+        if sync_word2 is None:
+            sync_word2 = make_sync_word2(fft_len, self.occ, self.pil)
+        if len(sync_word1) != fft_len or len(sync_word2) != fft_len:
+            raise ValueError("Length of sync sequence(s) must be FFT length.")
+        self.sw1 = np.asarray(sync_word1, dtype=np.complex64)
+        self.sw2 = np.asarray(sync_word2, dtype=np.complex64)
+        self.bps_header, self.bps_payload = int(bps_header), int(bps_payload)
+        self.crc_mode = int(crc_mode)
+        self._keep = [
+            np.array([len(s) for s in self.occ], np.int32), np.array(sum(self.occ, []), np.int32),
+            np.array([len(s) for s in self.pil], np.int32), np.array(sum(self.pil, []), np.int32),
+            np.array([len(s) for s in self.pls], np.int32),
+            np.array(sum(self.pls, []), np.complex64), self.sw1, self.sw2,
+        ]
+        k = self._keep
+        p = _Params()
+        p.fft_len, p.cp_len = self.fft_len, self.cp_len
+        p.n_occ_sets, p.occ_sizes, p.occ_carriers = len(self.occ), k[0].ctypes.data, k[1].ctypes.data
+        p.n_pilot_sets, p.pilot_sizes, p.pilot_carriers = len(self.pil), k[2].ctypes.data, k[3].ctypes.data
+        p.n_pilot_sym_sets, p.pilot_sym_sizes, p.pilot_symbols = len(self.pls), k[4].ctypes.data, k[5].ctypes.data
+        p.sync_word1, p.sync_word2 = k[6].ctypes.data, k[7].ctypes.data
+        p.bps_header, p.bps_payload = self.bps_header, self.bps_payload
+        p.scramble_header = int(scramble_bits if scramble_header is None else scramble_header)
+        p.scramble_seed = 0x7F if scramble_bits else 0x00
+        p.crc_mode = self.crc_mode
+        p.threshold, p.max_carr_offset, p.alpha, p.tx_scale = threshold, max_carr_offset, alpha, tx_scale
+        p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
+        self.p = p
+        self.L = lib()
+
+    @property
+    def _pp(self):
+        return C.byref(self.p)
+
+    def header_len(self):
+        return self.L.orc_header_len(self._pp)
+
+    def header_format(self, pkt_len, pkt_num):
+        out = np.zeros(self.header_len(), np.uint8)
+        self.L.orc_header_format(self._pp, pkt_len, pkt_num, _ptr(out))
+        return out
+
+    def header_parse(self, items):
+        items = np.ascontiguousarray(items, np.uint8)
+        v = [C.c_int() for _ in range(4)]
+        ok = self.L.orc_header_parse(self._pp, _ptr(items), *[C.byref(x) for x in v])
+        return bool(ok), v[0].value, v[1].value, v[2].value, v[3].value
+
+    def frame_samples(self, payload_bytes):
+        return self.L.orc_tx_frame_samples(self._pp, payload_bytes)
+
+    def tx(self, packets, first_pkt_num=0):
+        """packets: list of bytes/uint8 arrays -> (complex64 samples, int64 offsets[n+1])."""
+        lens = [len(b) for b in packets]
+        off = np.zeros(len(packets) + 1, np.int64)
+        off[1:] = np.cumsum(lens)
+        flat = np.frombuffer(b"".join(bytes(bytearray(b)) for b in packets), np.uint8).copy() \
+            if packets else np.zeros(0, np.uint8)
+        cap = sum(self.frame_samples(n) for n in lens)
+        out = np.zeros(max(cap, 1), np.complex64)
+        soff = np.zeros(len(packets) + 1, np.int64)
+        rc = self.L.orc_tx(self._pp, _ptr(flat), _ptr(off), len(packets), first_pkt_num,
+                           _ptr(out), cap, _ptr(soff))
+        if rc:
+            raise RuntimeError("orc_tx failed: %d" % rc)
+        return out[:cap], soff
+
+    def sync(self, samples, want_detect=False, f32=False, max_trig=None):
+        s = np.ascontiguousarray(samples, np.complex64)
+        n = s.shape[0]
+        max_trig = max_trig or max(16, n // max(1, self.cp_len) + 16)
+        trig = np.zeros(max_trig, np.int64)
+        cfo = np.zeros(max_trig, np.float32)
+        nt = C.c_int64()
+        det = np.zeros(n, np.uint8) if want_detect else None
+        if f32:
+            rc = self.L.orc_sync_f32(self._pp, _ptr(s), n, _ptr(trig), _ptr(cfo), max_trig, C.byref(nt))
+        else:
+            rc = self.L.orc_sync(self._pp, _ptr(s), n, _ptr(det) if want_detect else None,
+                                 _ptr(trig), _ptr(cfo), max_trig, C.byref(nt))
+        if rc:
+            raise RuntimeError("orc_sync failed: %d" % rc)
+        k = min(nt.value, max_trig)
+        return (trig[:k].copy(), cfo[:k].copy(), det) if want_detect else (trig[:k].copy(), cfo[:k].copy())
+
+    def rx(self, samples, max_frames=None, byte_stride=4096, want_z=True, max_pkt_syms=None):
+        s = np.ascontiguousarray(samples, np.complex64)
+        n = s.shape[0]
+        D = self.fft_len + self.cp_len
+        max_frames = max_frames or (n // (3 * D) + 4)
+        max_trig = max(16, n // max(1, self.cp_len) + 16)
+        recs = np.zeros(max_frames, FRAME_DTYPE)
+        by = np.zeros((max_frames, byte_stride), np.uint8)
+        zs = self.header_len() + (max_pkt_syms or (byte_stride * 8 // self.bps_payload + 1))
+        z = np.zeros((max_frames, zs), np.complex64) if want_z else None
+        trig = np.zeros(max_trig, np.int64)
+        cfo = np.zeros(max_trig, np.float32)
+        nf, nt = C.c_int64(), C.c_int64()
+        rc = self.L.orc_rx(self._pp, _ptr(s), n, _ptr(recs), max_frames, _ptr(by), byte_stride,
+                           _ptr(z) if want_z else None, zs, C.byref(nf), _ptr(trig), _ptr(cfo),
+                           max_trig, C.byref(nt))
+        if rc:
+            raise RuntimeError("orc_rx failed: %d" % rc)
+        k = nf.value
+        return {"frames": recs[:k].copy(), "bytes": by[:k], "z": z[:k] if want_z else None,
+                "triggers": trig[:nt.value].copy(), "cfo": cfo[:nt.value].copy()}
+
+    def payloads(self, res):
+        """Byte strings the flowgraph would deliver (CRC-failed packets dropped, CRC stripped
+        when crc_mode, python/ofdm_radio_hier.py:122,222-226)."""
+        out = []
+        for f, b in zip(res["frames"], res["bytes"]):
+            n = int(f["pkt_len"])
+            if self.crc_mode:
+                if not (f["flags"] & F_CRC_OK):
+                    continue
+                n -= 4
+            out.append(bytes(b[:n]))
+        return out
+
+
+def crc32(data):
+    a = np.frombuffer(bytes(data), np.uint8)
+    return lib().orc_crc32(_ptr(a) if len(a) else None, len(a))
+
+
+def crc8(data):
+    a = np.frombuffer(bytes(data), np.uint8)
+    return lib().orc_crc8(_ptr(a) if len(a) else None, len(a))
+
+
+def lfsr_bits(mask, seed, reg_len, n):
+    out = np.zeros(n, np.uint8)
+    lib().orc_lfsr_bits(mask, seed, reg_len, _ptr(out), n)
+    return out
+
+
+def scramble(data, seed):
+    a = np.frombuffer(bytes(data), np.uint8).copy()
+    lib().orc_scramble(_ptr(a), len(a), seed)
+    return a
+
+
+def repack(items, k, l, align_output):
+    a = np.ascontiguousarray(items, np.uint8)
+    out = np.zeros(len(a) * k // l + 2, np.uint8)
+    n = lib().orc_repack(_ptr(a), len(a), k, l, int(align_output), _ptr(out))
+    return out[:n]
+
+
+def constellation(bps):
+    pts = np.zeros(1 << bps, np.complex64)
+    lib().orc_constellation(bps, _ptr(pts))
+    return pts
+
+
+def decide(bps, z):
+    return lib().orc_decide(bps, float(np.real(z)), float(np.imag(z)))
+
+
+def fft(x, forward=True):
+    a = np.ascontiguousarray(x, np.complex128)
+    out = np.zeros_like(a)
+    lib().orc_fft(len(a), int(forward), _ptr(a), _ptr(out))
+    return out

@@ -1,0 +1,613 @@
+// ofdmx_api.cu -- C ABI (include/ofdmx.h) over the sm_100a kernels.  No CPU fallback: every
+// entry point needs a CUDA device and reports OFDMX_ERR_CUDA otherwise.
+#include "ofdmx_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct ofdmx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    ofdmx_params prm{};
+    KP kp{};
+    std::string err;
+    std::vector<void *> tables;     // device allocations owned by the context
+    // derived host copies
+    std::vector<int> occ_sizes;
+    int hl = 0;
+    // workspace
+    DevBuf ws;
+    int64_t launches = 0;
+    // host-buffer path
+    DevBuf h_samples, h_frames, h_bytes, h_counts;
+    cudaStream_t own_stream = nullptr;
+    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0;
+};
+
+namespace {
+
+int fail(ofdmx_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, OFDMX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+template <typename T>
+int upload(ofdmx_ctx *ctx, const std::vector<T> &v, const T **out)
+{
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CUDA_TRY(ctx, cudaMalloc(&d, bytes));
+    ctx->tables.push_back(d);
+    if (!v.empty()) CUDA_TRY(ctx, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T *>(d);
+    return 0;
+}
+
+int grow(ofdmx_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+inline int shifted_bin(int c, int n)
+{
+    if (c < 0) c += n;
+    return (c + n / 2) % n;
+}
+
+// _get_constellation(bps) (python/ofdm_txrx_modules.py:106-118); 6 = 64-QAM by the same qam.py rule
+bool make_constellation(int bps, std::vector<float2> &pts, std::vector<uint8_t> &lut)
+{
+    pts.clear();
+    lut.assign(64, 0);
+    if (bps == 1) {
+        pts = { make_float2(-1.f, 0.f), make_float2(1.f, 0.f) };
+    } else if (bps == 2) {
+        const float a = 0.707107f;
+        pts = { make_float2(-a, -a), make_float2(a, -a), make_float2(-a, a), make_float2(a, a) };
+    } else if (bps == 3) {
+        static const int mult[8] = { 1, 7, 15, 9, 3, 5, 13, 11 };
+        const float ang = (float)(M_PI / 8.0);
+        for (int i = 0; i < 8; i++) pts.push_back(make_float2((float)std::cos(mult[i] * ang), (float)std::sin(mult[i] * ang)));
+    } else if (bps == 4 || bps == 6) {
+        const int m = 1 << bps, q = (bps == 4) ? 2 : 4;
+        const double step = 1.0 / (q - 0.5);
+        for (int i = 0; i < m; i++) {
+            const int y = i % q, x = (i / q) % q, quad = i / (q * q);
+            const double gx = (x + 0.5) * step, gy = (y + 0.5) * step;
+            double re, im;
+            if (quad == 0) { re = gx; im = gy; }
+            else if (quad == 1) { re = -gy; im = gx; }
+            else if (quad == 2) { re = -gx; im = -gy; }
+            else { re = gy; im = -gx; }
+            pts.push_back(make_float2((float)re, (float)im));
+        }
+        // constellation_rect: sector centre -> closest point
+        const int side = 2 * q;
+        const double w = 2.0 / (side - 1);
+        for (int rs = 0; rs < side; rs++)
+            for (int is = 0; is < side; is++) {
+                const double cr = (rs + 0.5 - side / 2.0) * w, ci = (is + 0.5 - side / 2.0) * w;
+                int best = 0;
+                double bd = 1e300;
+                for (int i = 0; i < m; i++) {
+                    const double dr = cr - pts[i].x, di = ci - pts[i].y, d = dr * dr + di * di;
+                    if (d < bd) { bd = d; best = i; }
+                }
+                lut[rs * side + is] = (uint8_t)best;
+            }
+    } else {
+        return false;
+    }
+    return true;
+}
+
+// gnuradio/digital/lfsr.h
+struct Lfsr {
+    uint32_t sr, mask, len;
+    Lfsr(uint32_t m, uint32_t seed, uint32_t l) : sr(seed), mask(m), len(l) {}
+    unsigned next()
+    {
+        unsigned out = sr & 1u;
+        unsigned nb = (unsigned)__builtin_popcount(sr & mask) & 1u;
+        sr = (sr >> 1) | (nb << len);
+        return out;
+    }
+};
+
+uint32_t h_gf2_mul_x(uint32_t b) { return (b & 1u) ? ((b >> 1) ^ 0xEDB88320u) : (b >> 1); }
+
+int payload_ofdm_syms(const ofdmx_ctx *c, int n_syms)
+{
+    int cnt = 0, acc = 0, s = 1 % c->prm.n_occ_sets;
+    while (acc < n_syms) {
+        cnt++;
+        acc += c->occ_sizes[s];
+        s = (s + 1) % c->prm.n_occ_sets;
+    }
+    return cnt;
+}
+
+// workspace carve-up for RX
+struct RxWs {
+    uint32_t *detmask, *trigmask;
+    int *blocksum, *n_trig, *stream_start, *stream_count, *jumpA, *jumpB;
+    long long *trig;
+    int *trig_stream;
+    float *cfo;
+    ofdmx_frame *spec;
+    uint8_t *markA, *markB;
+    size_t total;
+    long long wps, n_words;
+    int nb;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+RxWs carve(void *base, int64_t n_streams, int64_t n_samples, int64_t max_trig)
+{
+    RxWs w{};
+    w.wps = (n_samples + 31) / 32;
+    if (w.wps < 1) w.wps = 1;
+    w.n_words = w.wps * n_streams;
+    w.nb = (int)((w.n_words + OFDMX_THREADS * TRIG_WPT - 1) / (OFDMX_THREADS * TRIG_WPT));
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return base ? static_cast<char *>(base) + o : nullptr;
+    };
+    w.detmask = (uint32_t *)take(sizeof(uint32_t) * (size_t)w.n_words);
+    w.trigmask = (uint32_t *)take(sizeof(uint32_t) * (size_t)w.n_words);
+    w.blocksum = (int *)take(sizeof(int) * (size_t)(w.nb + 1));
+    w.n_trig = (int *)take(sizeof(int) * 4);
+    w.stream_start = (int *)take(sizeof(int) * (size_t)(n_streams + 2));
+    w.stream_count = (int *)take(sizeof(int) * (size_t)(n_streams + 2));
+    w.jumpA = (int *)take(sizeof(int) * (size_t)(max_trig + 1));
+    w.jumpB = (int *)take(sizeof(int) * (size_t)(max_trig + 1));
+    w.trig = (long long *)take(sizeof(long long) * (size_t)(max_trig + 1));
+    w.trig_stream = (int *)take(sizeof(int) * (size_t)(max_trig + 1));
+    w.cfo = (float *)take(sizeof(float) * (size_t)(max_trig + 1));
+    w.spec = (ofdmx_frame *)take(sizeof(ofdmx_frame) * (size_t)(max_trig + 1));
+    w.markA = (uint8_t *)take((size_t)(max_trig + 1));
+    w.markB = (uint8_t *)take((size_t)(max_trig + 1));
+    w.total = off;
+    return w;
+}
+
+int check_device(ofdmx_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return 0;
+}
+
+// sync front end shared by ofdmx_rx and ofdmx_sync: detect bits -> triggers -> cfo
+int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_streams, int64_t n_samples,
+             int64_t stride, int64_t max_trig, ofdmx_counts *counts_dev, cudaStream_t st)
+{
+    const KP &kp = ctx->kp;
+    CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
+    const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
+    dim3 grid((unsigned)tiles, (unsigned)n_streams);
+    sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr,
+                                                                      w.detmask, w.wps);
+    const long long pb = (w.n_words + OFDMX_THREADS - 1) / OFDMX_THREADS;
+    plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp);
+    trig_count_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.blocksum);
+    trig_scan_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nb, (int)max_trig, counts_dev, w.n_trig, w.stream_start, n_streams);
+    trig_scatter_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.wps, w.blocksum, (int)max_trig,
+                                                         w.trig, w.trig_stream, w.stream_start);
+    cfo_kernel<<<ctx->sm_count * 2, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream,
+                                                            w.n_trig, w.cfo);
+    ctx->launches += 6;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int ofdmx_abi_version(void) { return OFDMX_ABI_VERSION; }
+
+const char *ofdmx_last_error(const ofdmx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
+{
+    if (!prm || !out) return fail(nullptr, OFDMX_ERR_PARAM, "null argument");
+    *out = nullptr;
+    const int N = prm->fft_len;
+    if (N < 16 || N > 4096 || (N & (N - 1))) return fail(nullptr, OFDMX_ERR_PARAM, "fft_len must be a power of two in 16..4096");
+    if (prm->cp_len < 0 || prm->cp_len > N) return fail(nullptr, OFDMX_ERR_PARAM, "cp_len out of range");
+    if (prm->n_occ_sets < 1 || !prm->occ_sizes || !prm->occ_carriers) return fail(nullptr, OFDMX_ERR_PARAM, "occupied_carriers missing");
+    if (!prm->sync_word1 || !prm->sync_word2) return fail(nullptr, OFDMX_ERR_PARAM, "Length of sync sequence(s) must be FFT length.");
+    std::vector<float2> hpts, ppts;
+    std::vector<uint8_t> lut_h, lut_p;
+    if (!make_constellation(prm->bps_header, hpts, lut_h) || !make_constellation(prm->bps_payload, ppts, lut_p))
+        return fail(nullptr, OFDMX_ERR_PARAM, "Modulation not supported.");
+    if (prm->max_pkt_bytes < 1 || prm->max_pkt_bytes > 4095) return fail(nullptr, OFDMX_ERR_PARAM, "max_pkt_bytes must be 1..4095");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
+        return fail(nullptr, OFDMX_ERR_CUDA, "no CUDA device %d (this library has no CPU fallback)", device);
+
+    ofdmx_ctx *c = new ofdmx_ctx();
+    c->device = device;
+    c->prm = *prm;
+    if (int rc = check_device(c)) { delete c; return rc; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+
+    KP &kp = c->kp;
+    kp.N = N;
+    kp.logN = 0;
+    while ((1 << kp.logN) < N) kp.logN++;
+    kp.cp = prm->cp_len;
+    kp.D = N + prm->cp_len;
+    kp.n_occ_sets = prm->n_occ_sets;
+    kp.n_pil_sets = prm->n_pilot_sets;
+    kp.n_pil_sym_sets = prm->n_pilot_sym_sets > 0 ? prm->n_pilot_sym_sets : 1;
+    kp.bps_h = prm->bps_header;
+    kp.bps_p = prm->bps_payload;
+    kp.crc_mode = prm->crc_mode ? 1 : 0;
+    kp.holdoff = prm->demux_holdoff;
+    kp.max_pkt_bytes = prm->max_pkt_bytes;
+    kp.max_pkt_syms = (prm->max_pkt_bytes * 8 + prm->bps_payload - 1) / prm->bps_payload;
+    kp.thr = (double)prm->threshold;
+    kp.alpha = prm->alpha;
+    kp.tx_scale = prm->tx_scale;
+
+    int rc = 0;
+    auto bail = [&](int code) { ofdmx_destroy(c); return code; };
+
+    // carrier plan
+    std::vector<int> occ_bins, occ_base, occ_size, occ_u;
+    std::vector<uint8_t> occ_mask(N, 0);
+    for (int s = 0, a = 0; s < prm->n_occ_sets; s++) {
+        occ_base.push_back(a);
+        occ_size.push_back(prm->occ_sizes[s]);
+        if (prm->occ_sizes[s] < 1) return bail(fail(nullptr, OFDMX_ERR_PARAM, "empty occupied carrier set"));
+        for (int k = 0; k < prm->occ_sizes[s]; k++) {
+            const int cn = prm->occ_carriers[a + k];
+            if (cn < -N / 2 || cn >= N) return bail(fail(nullptr, OFDMX_ERR_PARAM, "carrier index out of range"));
+            const int bin = shifted_bin(cn, N);
+            occ_bins.push_back(bin);
+            occ_mask[bin] = 1;
+        }
+        a += prm->occ_sizes[s];
+    }
+    for (int k = 0; k < N; k++) if (occ_mask[k]) occ_u.push_back(k);
+    c->occ_sizes = occ_size;
+    c->hl = occ_size[0];
+    kp.hl = c->hl;
+    kp.n_occ_u = (int)occ_u.size();
+
+    const int nps = std::max(1, prm->n_pilot_sets);
+    std::vector<uint8_t> pil_flag((size_t)nps * N, 0);
+    std::vector<float2> pil_val((size_t)nps * N, make_float2(0.f, 0.f));
+    std::vector<int> pil_bins, pil_base, pil_size, pil_sym_base;
+    std::vector<float2> pil_sym;
+    for (int s = 0, a = 0; s < prm->n_pilot_sym_sets; s++) {
+        pil_sym_base.push_back(a);
+        for (int k = 0; k < prm->pilot_sym_sizes[s]; k++)
+            pil_sym.push_back(make_float2(prm->pilot_symbols[2 * (a + k)], prm->pilot_symbols[2 * (a + k) + 1]));
+        a += prm->pilot_sym_sizes[s];
+    }
+    if (pil_sym_base.empty()) pil_sym_base.push_back(0);
+    for (int s = 0, a = 0; s < prm->n_pilot_sets; s++) {
+        pil_base.push_back(a);
+        pil_size.push_back(prm->pilot_sizes[s]);
+        // ofdm_equalizer_1d_pilots: "pilot carriers and -symbols do not match" -> ValueError
+        if (s >= prm->n_pilot_sym_sets || prm->pilot_sym_sizes[s] != prm->pilot_sizes[s])
+            return bail(fail(nullptr, OFDMX_ERR_PARAM, "pilot carriers and -symbols do not match."));
+        for (int k = 0; k < prm->pilot_sizes[s]; k++) {
+            const int cn = prm->pilot_carriers[a + k];
+            if (cn < -N / 2 || cn >= N) return bail(fail(nullptr, OFDMX_ERR_PARAM, "pilot carrier index out of range"));
+            const int bin = shifted_bin(cn, N);
+            pil_bins.push_back(bin);
+            pil_flag[(size_t)s * N + bin] = 1;
+            pil_val[(size_t)s * N + bin] = pil_sym[pil_sym_base[s] + k];
+        }
+        a += prm->pilot_sizes[s];
+    }
+    // every pilot-symbol set used on TX (i % n_sym_sets) must cover the carrier set it lands on
+    for (int s = 0; s < prm->n_pilot_sym_sets && prm->n_pilot_sets > 0; s++)
+        if (prm->pilot_sym_sizes[s] < *std::max_element(pil_size.begin(), pil_size.end()))
+            return bail(fail(nullptr, OFDMX_ERR_PARAM, "pilot carriers and -symbols do not match."));
+
+    // sync words, chanest tables
+    std::vector<float2> sw1(N), sw2(N), inv_sw2(N), cv_conj;
+    std::vector<int> cv_k;
+    int first = 0, last = N - 1;
+    for (int k = 0; k < N; k++) {
+        sw1[k] = make_float2(prm->sync_word1[2 * k], prm->sync_word1[2 * k + 1]);
+        sw2[k] = make_float2(prm->sync_word2[2 * k], prm->sync_word2[2 * k + 1]);
+    }
+    for (int k = 0; k < N; k++) if (sw2[k].x != 0.f || sw2[k].y != 0.f) { first = k; break; }
+    for (int k = N - 1; k >= 0; k--) if (sw2[k].x != 0.f || sw2[k].y != 0.f) { last = k; break; }
+    for (int k = 0; k < N; k++) {
+        std::complex<double> a(sw1[k].x, sw1[k].y), b(sw2[k].x, sw2[k].y);
+        inv_sw2[k] = make_float2(0.f, 0.f);
+        if (b != 0.0) {
+            std::complex<double> iv = 1.0 / b;
+            inv_sw2[k] = make_float2((float)iv.real(), (float)iv.imag());
+        }
+        if (a != 0.0) {
+            std::complex<double> cv = b / a;
+            if (cv != 0.0) {
+                cv_k.push_back(k);
+                cv_conj.push_back(make_float2((float)cv.real(), (float)-cv.imag()));
+            }
+        }
+    }
+    kp.n_cv = (int)cv_k.size();
+    int gneg = -first, gpos = N - last - 1;
+    if (prm->max_carr_offset != -1) {
+        gneg = std::max(-prm->max_carr_offset, gneg);
+        gpos = std::min(prm->max_carr_offset, gpos);
+    }
+    if (gneg % 2) gneg++;
+    if (gpos % 2) gpos--;
+    kp.gneg = gneg;
+    kp.gpos = gpos;
+    for (int k : cv_k)
+        if (k + gneg < 0 || k + gpos >= N) return bail(fail(nullptr, OFDMX_ERR_PARAM, "sync words inconsistent with carrier offset range"));
+
+    // twiddles
+    std::vector<float2> tw(N);
+    for (int k = 0; k < N; k++) {
+        const double a = -2.0 * M_PI * k / N;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    // header scramble mask (packet_header_ofdm) and payload keystream (additive_scrambler_bb)
+    std::vector<uint8_t> hdr_mask(c->hl, 0), keystream((size_t)prm->max_pkt_bytes + 8, 0);
+    if (prm->scramble_header) {
+        Lfsr l(0x8a, 0x6f, 7);
+        for (int i = 0; i < c->hl; i++)
+            for (int k = 0; k < prm->bps_header; k++) hdr_mask[i] ^= (uint8_t)(l.next() << k);
+    }
+    {
+        Lfsr l(0x8a, (uint32_t)prm->scramble_seed, 7);
+        for (size_t i = 0; i < keystream.size(); i++)
+            for (int k = 0; k < 8; k++) keystream[i] ^= (uint8_t)(l.next() << k);
+    }
+    // CRC tables
+    std::vector<uint32_t> crc_tab(256), crc_pow(256);
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t v = i;
+        for (int k = 0; k < 8; k++) v = (v & 1u) ? ((v >> 1) ^ 0xEDB88320u) : (v >> 1);
+        crc_tab[i] = v;
+    }
+    {
+        uint32_t x = 0x80000000u;   // x^0
+        for (int j = 255; j >= 0; j--) {
+            crc_pow[j] = x;         // x^(128*(255-j))
+            for (int b = 0; b < 128; b++) x = h_gf2_mul_x(x);
+        }
+    }
+
+#define UP(vec, field)                                          \
+    if ((rc = upload(c, vec, &kp.field)) != 0) return bail(rc);
+    UP(tw, tw) UP(occ_bins, occ_bins) UP(occ_base, occ_base) UP(occ_size, occ_size) UP(occ_u, occ_u)
+    UP(pil_flag, pil_flag) UP(pil_val, pil_val) UP(pil_bins, pil_bins) UP(pil_base, pil_base)
+    UP(pil_size, pil_size) UP(pil_sym, pil_sym) UP(pil_sym_base, pil_sym_base) UP(sw1, sw1) UP(sw2, sw2)
+    UP(cv_k, cv_k) UP(cv_conj, cv_conj) UP(inv_sw2, inv_sw2) UP(hdr_mask, hdr_mask) UP(keystream, keystream)
+    UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
+#undef UP
+
+    // shared-memory budgets
+    {
+        const int L = SYNC_T + N, ce = (L + OFDMX_THREADS - 1) / OFDMX_THREADS, Lp = L + L / ce + 2;
+        c->sync_smem = (size_t)Lp * 32;
+        c->frame_smem = (size_t)N * 8 * 4 + 64 + N + align_up(c->hl, 16) + align_up(kp.max_pkt_syms, 16)
+                        + align_up(kp.max_pkt_bytes, 16) + 16;
+        c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16;
+        if (cudaFuncSetAttribute(sync_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_smem) != cudaSuccess
+            || cudaFuncSetAttribute(rx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem) != cudaSuccess
+            || cudaFuncSetAttribute(tx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx_smem) != cudaSuccess)
+            return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s (is this an sm_100 device?)",
+                             cudaGetErrorString(cudaGetLastError())));
+    }
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
+    *out = c;
+    return OFDMX_OK;
+}
+
+void ofdmx_destroy(ofdmx_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (void *p : c->tables) cudaFree(p);
+    for (DevBuf *b : { &c->ws, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
+        if (b->p) cudaFree(b->p);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int ofdmx_header_len(const ofdmx_ctx *c) { return c ? c->hl : 0; }
+int64_t ofdmx_launch_count(const ofdmx_ctx *c) { return c ? c->launches : 0; }
+
+int64_t ofdmx_tx_frame_samples(const ofdmx_ctx *c, int64_t payload_bytes)
+{
+    if (!c || payload_bytes < 0) return -1;
+    const int64_t lp = payload_bytes + (c->kp.crc_mode ? 4 : 0);
+    const int64_t ns = (lp * 8 + c->kp.bps_p - 1) / c->kp.bps_p;
+    return (int64_t)(3 + payload_ofdm_syms(c, (int)ns)) * c->kp.D;
+}
+
+int ofdmx_reserve(ofdmx_ctx *c, int64_t n_streams, int64_t n_samples, int64_t max_frames)
+{
+    if (!c || n_streams < 1 || n_samples < 0 || max_frames < 1) return fail(c, OFDMX_ERR_PARAM, "bad reserve shape");
+    if (int rc = check_device(c)) return rc;
+    RxWs w = carve(nullptr, n_streams, n_samples, max_frames);
+    return grow(c, c->ws, w.total);
+}
+
+int ofdmx_sync(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t n_samples, int64_t stride,
+               int64_t *trig_out, float *cfo_out, int32_t *stream_out, int64_t max_trig,
+               ofdmx_counts *counts_dev, void *stream)
+{
+    if (!c || !samples_dev || !counts_dev || n_streams < 1 || n_samples < 1 || max_trig < 1 || stride < n_samples)
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_sync arguments");
+    if (max_trig > 0x7ffffff0LL || n_samples / 32 * n_streams > 0x7fffffffLL * 512)
+        return fail(c, OFDMX_ERR_PARAM, "problem too large");
+    if (int rc = check_device(c)) return rc;
+    if (int rc = ofdmx_reserve(c, n_streams, n_samples, max_trig)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    RxWs w = carve(c->ws.p, n_streams, n_samples, max_trig);
+    if (int rc = run_sync(c, w, (const float2 *)samples_dev, n_streams, n_samples, stride, max_trig, counts_dev, st)) return rc;
+    // results are bounded by max_trig entries; copy whole arrays (stale tail entries are ignored by n_triggers)
+    if (trig_out) CUDA_TRY(c, cudaMemcpyAsync(trig_out, w.trig, sizeof(long long) * (size_t)max_trig, cudaMemcpyDeviceToDevice, st));
+    if (cfo_out) CUDA_TRY(c, cudaMemcpyAsync(cfo_out, w.cfo, sizeof(float) * (size_t)max_trig, cudaMemcpyDeviceToDevice, st));
+    if (stream_out) CUDA_TRY(c, cudaMemcpyAsync(stream_out, w.trig_stream, sizeof(int) * (size_t)max_trig, cudaMemcpyDeviceToDevice, st));
+    return OFDMX_OK;
+}
+
+int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t n_samples, int64_t stride,
+             ofdmx_frame *frames_out, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+             float *z_out, int64_t z_stride, ofdmx_counts *counts_dev, void *stream)
+{
+    if (!c || !samples_dev || !frames_out || !bytes_out || !counts_dev || n_streams < 1 || n_samples < 1
+        || max_frames < 1 || stride < n_samples)
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_rx arguments");
+    if (byte_stride < c->kp.max_pkt_bytes) return fail(c, OFDMX_ERR_CAPACITY, "byte_stride < max_pkt_bytes");
+    if (z_out && z_stride < c->hl) return fail(c, OFDMX_ERR_CAPACITY, "z_stride < header_len");
+    if (max_frames > 0x7ffffff0LL) return fail(c, OFDMX_ERR_PARAM, "max_frames too large");
+    if (int rc = check_device(c)) return rc;
+    if (int rc = ofdmx_reserve(c, n_streams, n_samples, max_frames)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    RxWs w = carve(c->ws.p, n_streams, n_samples, max_frames);
+    const float2 *smp = (const float2 *)samples_dev;
+    if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
+    rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
+        c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
+        byte_stride, (float2 *)z_out, z_stride);
+    chain_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(c->kp, n_samples, w.trig, w.spec, w.stream_start, w.jumpA, w.jumpB,
+                                                       w.markA, w.markB, w.stream_count);
+    emit_scan_kernel<<<1, 1024, 0, st>>>(w.stream_count, n_streams, counts_dev);
+    emit_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(w.spec, w.markA, w.stream_start, w.stream_count, frames_out);
+    c->launches += 4;
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+int ofdmx_rx_host(ofdmx_ctx *c, const float *samples_host, int64_t n_streams, int64_t n_samples,
+                  ofdmx_frame *frames_host, int64_t max_frames, uint8_t *bytes_host, int64_t byte_stride,
+                  ofdmx_counts *counts_host)
+{
+    if (!c || !samples_host || !frames_host || !bytes_host || !counts_host)
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_rx_host arguments");
+    if (int rc = check_device(c)) return rc;
+    const size_t sbytes = sizeof(float2) * (size_t)n_streams * (size_t)n_samples;
+    if (int rc = grow(c, c->h_samples, sbytes)) return rc;
+    if (int rc = grow(c, c->h_frames, sizeof(ofdmx_frame) * (size_t)max_frames)) return rc;
+    if (int rc = grow(c, c->h_bytes, (size_t)max_frames * (size_t)byte_stride)) return rc;
+    if (int rc = grow(c, c->h_counts, sizeof(ofdmx_counts))) return rc;
+    cudaStream_t st = c->own_stream;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_samples.p, samples_host, sbytes, cudaMemcpyHostToDevice, st));
+    if (int rc = ofdmx_rx(c, (const float *)c->h_samples.p, n_streams, n_samples, n_samples,
+                          (ofdmx_frame *)c->h_frames.p, max_frames, (uint8_t *)c->h_bytes.p, byte_stride, nullptr, 0,
+                          (ofdmx_counts *)c->h_counts.p, st))
+        return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(counts_host, c->h_counts.p, sizeof(ofdmx_counts), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    const int64_t nf = std::min<int64_t>(counts_host->n_frames, max_frames);
+    const int64_t ntr = std::min<int64_t>(counts_host->n_triggers, max_frames);
+    if (nf > 0)
+        CUDA_TRY(c, cudaMemcpyAsync(frames_host, c->h_frames.p, sizeof(ofdmx_frame) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+    if (ntr > 0)
+        CUDA_TRY(c, cudaMemcpyAsync(bytes_host, c->h_bytes.p, (size_t)ntr * (size_t)byte_stride, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return OFDMX_OK;
+}
+
+int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_dev, int64_t n_pkts,
+             int32_t first_pkt_num, float *samples_out, int64_t cap_samples, int64_t *sample_off_dev, void *stream)
+{
+    if (!c || !payload_dev || !pkt_off_dev || !samples_out || !sample_off_dev || n_pkts < 0)
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_tx arguments");
+    if (n_pkts == 0) return OFDMX_OK;
+    if (int rc = check_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    tx_offsets_kernel<<<1, 1024, 0, st>>>(c->kp, (const long long *)pkt_off_dev, n_pkts, (long long *)sample_off_dev);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
+    tx_frame_kernel<<<grid, OFDMX_THREADS, c->tx_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts,
+                                                              first_pkt_num, (float2 *)samples_out, cap_samples,
+                                                              (const long long *)sample_off_dev);
+    c->launches += 2;
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+int ofdmx_fft(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_syms, int forward, void *stream)
+{
+    if (!c || !in_dev || !out_dev || n_syms < 0) return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_fft arguments");
+    if (n_syms == 0) return OFDMX_OK;
+    if (int rc = check_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_syms, (int64_t)c->sm_count * 8);
+    const size_t sm = (size_t)c->kp.N * 8;
+    if (forward)
+        fft_vcc_kernel<false><<<grid, OFDMX_THREADS, sm, st>>>((const float2 *)in_dev, (float2 *)out_dev, n_syms, c->kp.N, c->kp.logN, c->kp.tw);
+    else
+        fft_vcc_kernel<true><<<grid, OFDMX_THREADS, sm, st>>>((const float2 *)in_dev, (float2 *)out_dev, n_syms, c->kp.N, c->kp.logN, c->kp.tw);
+    c->launches += 1;
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+int ofdmx_crc32(ofdmx_ctx *c, const uint8_t *bytes_dev, const int64_t *pkt_off_dev, int64_t n_pkts,
+                uint32_t *crc_out_dev, void *stream)
+{
+    if (!c || !bytes_dev || !pkt_off_dev || !crc_out_dev || n_pkts < 0) return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_crc32 arguments");
+    if (n_pkts == 0) return OFDMX_OK;
+    if (int rc = check_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
+    crc32_kernel<<<grid, OFDMX_THREADS, 0, st>>>(bytes_dev, (const long long *)pkt_off_dev, n_pkts, crc_out_dev,
+                                                 c->kp.crc_tab, c->kp.crc_pow);
+    c->launches += 1;
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""Host-side driver of the B200 OFDM PHY: one `OfdmPhy` = one configured TX/RX chain.
+
+PyTorch is used only as the device-buffer carrier (allocation, streams); all arithmetic happens in
+libofdmx.so (gr-ofdm_tools_b200/csrc).  Argument names follow the reference's hier blocks
+(python/ofdm_txrx_modules.py:143-155,278-291; python/ofdm_radio_hier.py:34-39).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FRAME_DTYPE = np.dtype([
+    ("trigger", "<i8"), ("cfo", "<f4"), ("stream", "<i4"), ("flags", "<u4"),
+    ("pkt_len", "<u2"), ("pkt_num", "<u2"), ("frame_syms", "<u2"), ("carr_offset", "<i2"),
+    ("slot", "<u4"),
+])
+assert FRAME_DTYPE.itemsize == 32
+
+_SEQ_SEED = 42
+
+
+def _get_active_carriers(fft_len, occupied_carriers, pilot_carriers):
+    """python/ofdm_txrx_modules.py:66-73."""
+    active = []
+    for carrier in list(occupied_carriers[0]) + list(pilot_carriers[0]):
+        active.append(carrier + fft_len if carrier < 0 else carrier)
+    return active
+
+
+def _make_sync_word1(fft_len, occupied_carriers, pilot_carriers, amplitude=None):
+    """First Schmidl & Cox preamble symbol: seeded random BPSK on the odd active carriers
+    (python/ofdm_txrx_modules.py:75-91; amplitude 1.42 variant python/ofdm_cr_tools.py:262-279)."""
+    amp = float(np.sqrt(2)) if amplitude is None else float(amplitude)
+    active = set(_get_active_carriers(fft_len, occupied_carriers, pilot_carriers))
+    rs = np.random.RandomState(_SEQ_SEED)
+    vals = []
+    for x in range(fft_len):
+        if x in active and x % 2:
+            vals.append(amp if rs.randint(2) == 0 else -amp)
+        else:
+            vals.append(0.0)
+    return np.fft.fftshift(vals)
+
+
+def _make_sync_word2(fft_len, occupied_carriers, pilot_carriers):
+    """Second preamble symbol: seeded random BPSK on every active carrier, DC forced to zero
+    (python/ofdm_txrx_modules.py:93-104)."""
+    active = set(_get_active_carriers(fft_len, occupied_carriers, pilot_carriers))
+    rs = np.random.RandomState(_SEQ_SEED)
+    vals = []
+    for x in range(fft_len):
+        if x in active:
+            vals.append(1 + 0j if rs.randint(2) == 0 else -1 + 0j)
+        else:
+            vals.append(0j)
+    vals[0] = 0j
+    return np.fft.fftshift(vals)
+
+
+class RxResult(object):
+    """Output of one RX call: frame records (numpy, FRAME_DTYPE), payload slots, counts."""
+
+    def __init__(self, frames, slots, counts, z, crc_mode, n_triggers):
+        self.frames = frames
+        self.slots = slots          # uint8 [max_frames, byte_stride] (torch tensor or numpy)
+        self.counts = counts
+        self.z = z
+        self.crc_mode = crc_mode
+        self.n_triggers = n_triggers
+
+    def slot_bytes(self, f):
+        row = self.slots[int(f["slot"])]
+        row = row.cpu().numpy() if hasattr(row, "cpu") else row
+        return row[: int(f["pkt_len"])]
+
+    def payloads(self):
+        """Packets as the flowgraph delivers them: with crc_mode, failed packets are dropped and the
+        4 CRC bytes stripped (python/ofdm_radio_hier.py:122,222-226)."""
+        slots = self.slots.cpu().numpy() if hasattr(self.slots, "cpu") else self.slots
+        out = []
+        for f in self.frames:
+            n = int(f["pkt_len"])
+            if self.crc_mode:
+                if not (int(f["flags"]) & _lib.F_CRC_OK):
+                    continue
+                n -= 4
+            out.append(bytes(slots[int(f["slot"]), :n]))
+        return out
+
+
+class OfdmPhy(object):
+    def __init__(self, fft_len=64, cp_len=16, occupied_carriers=None, pilot_carriers=None,
+                 pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
+                 scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
+                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None,
+                 max_pkt_bytes=4095, device=0):
+        self.fft_len, self.cp_len = int(fft_len), int(cp_len)
+        self.occupied_carriers = [list(map(int, s)) for s in occupied_carriers]
+        self.pilot_carriers = [list(map(int, s)) for s in pilot_carriers]
+        self.pilot_symbols = [list(map(complex, s)) for s in pilot_symbols]
+        if sync_word1 is None:
+            sync_word1 = _make_sync_word1(fft_len, self.occupied_carriers, self.pilot_carriers)
+        elif len(sync_word1) != self.fft_len:
+            raise ValueError("Length of sync sequence(s) must be FFT length.")
+        if sync_word2 is None:
+            sync_word2 = _make_sync_word2(fft_len, self.occupied_carriers, self.pilot_carriers)
+        elif len(sync_word2) != self.fft_len:
+            # the single-sync-word mode (sync_word2=()) of ofdm_chanest_vcvc is not built
+            raise ValueError("Length of sync sequence(s) must be FFT length.")
+        self.sync_word1 = np.asarray(sync_word1, dtype=np.complex64)
+        self.sync_word2 = np.asarray(sync_word2, dtype=np.complex64)
+        self.bps_header, self.bps_payload = int(bps_header), int(bps_payload)
+        self.crc_mode = int(crc_mode)
+        self.max_pkt_bytes = int(max_pkt_bytes)
+        self.device = int(device)
+        self.byte_stride = (self.max_pkt_bytes + 15) // 16 * 16
+
+        def flat(sets, dt):
+            return np.array([v for s in sets for v in s], dtype=dt)
+
+        self._keep = [
+            np.array([len(s) for s in self.occupied_carriers], np.int32), flat(self.occupied_carriers, np.int32),
+            np.array([len(s) for s in self.pilot_carriers], np.int32), flat(self.pilot_carriers, np.int32),
+            np.array([len(s) for s in self.pilot_symbols], np.int32), flat(self.pilot_symbols, np.complex64),
+            self.sync_word1, self.sync_word2,
+        ]
+        k = self._keep
+        p = _lib.Params()
+        p.fft_len, p.cp_len = self.fft_len, self.cp_len
+        p.n_occ_sets, p.occ_sizes, p.occ_carriers = len(self.occupied_carriers), k[0].ctypes.data, k[1].ctypes.data
+        p.n_pilot_sets, p.pilot_sizes, p.pilot_carriers = len(self.pilot_carriers), k[2].ctypes.data, k[3].ctypes.data
+        p.n_pilot_sym_sets, p.pilot_sym_sizes, p.pilot_symbols = len(self.pilot_symbols), k[4].ctypes.data, k[5].ctypes.data
+        p.sync_word1, p.sync_word2 = k[6].ctypes.data, k[7].ctypes.data
+        p.bps_header, p.bps_payload = self.bps_header, self.bps_payload
+        p.scramble_header = int(scramble_bits if scramble_header is None else scramble_header)
+        p.scramble_seed = 0x7F if scramble_bits else 0x00
+        p.crc_mode = self.crc_mode
+        p.threshold, p.max_carr_offset, p.alpha, p.tx_scale = threshold, max_carr_offset, alpha, tx_scale
+        p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
+        p.max_pkt_bytes = self.max_pkt_bytes
+        self.params = p
+        self._ctx = None
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            L = _lib.load()
+            h = C.c_void_p()
+            _lib.check(L.ofdmx_create(C.byref(self.params), self.device, C.byref(h)))
+            self._ctx = h
+        return self._ctx
+
+    def close(self):
+        if self._ctx is not None:
+            _lib.load().ofdmx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _torch(self):
+        import torch
+        return torch
+
+    def _dev(self):
+        return self._torch().device("cuda", self.device)
+
+    def _stream(self):
+        return C.c_void_p(self._torch().cuda.current_stream(self._dev()).cuda_stream)
+
+    def header_len(self):
+        return _lib.load().ofdmx_header_len(self.ctx)
+
+    def frame_samples(self, payload_bytes):
+        return _lib.load().ofdmx_tx_frame_samples(self.ctx, int(payload_bytes))
+
+    def launch_count(self):
+        return _lib.load().ofdmx_launch_count(self.ctx)
+
+    # ------------------------------------------------------------------ TX
+    def tx(self, packets, first_pkt_num=0):
+        """packets: list of bytes-like (or (uint8 cuda tensor, int64 cuda offsets)).
+        Returns (complex64 cuda tensor of samples, int64 cuda tensor of n+1 frame offsets)."""
+        torch = self._torch()
+        dev = self._dev()
+        if isinstance(packets, tuple):
+            payload, off = packets
+            lens = (off[1:] - off[:-1]).cpu().numpy()
+        else:
+            lens = np.array([len(b) for b in packets], np.int64)
+            flat = np.frombuffer(b"".join(bytes(bytearray(b)) for b in packets), np.uint8)
+            payload = torch.from_numpy(flat.copy() if len(flat) else np.zeros(1, np.uint8)).to(dev)
+            o = np.zeros(len(lens) + 1, np.int64)
+            o[1:] = np.cumsum(lens)
+            off = torch.from_numpy(o).to(dev)
+        n = len(lens)
+        extra = 4 if self.crc_mode else 0
+        if n and int(lens.max()) + extra > self.max_pkt_bytes:
+            raise ValueError("packet longer than max_pkt_bytes")
+        uniq = {int(v): self.frame_samples(int(v)) for v in np.unique(lens)}
+        cap = int(sum(uniq[int(v)] for v in lens))
+        out = torch.empty(max(cap, 1), dtype=torch.complex64, device=dev)
+        soff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        if n:
+            _lib.check(_lib.load().ofdmx_tx(self.ctx, payload.data_ptr(), off.data_ptr(), n, int(first_pkt_num),
+                                            out.data_ptr(), cap, soff.data_ptr(), self._stream()), self.ctx)
+        return out[:cap], soff
+
+    # ------------------------------------------------------------------ RX
+    def rx(self, samples, max_frames=None, want_z=False, max_pkt_syms=None):
+        """samples: complex64 cuda tensor [n] or [n_streams, n].  Returns RxResult (synchronises)."""
+        torch = self._torch()
+        s = samples if samples.dim() == 2 else samples.unsqueeze(0)
+        assert s.dtype == torch.complex64 and s.is_cuda and s.stride(1) == 1
+        n_streams, n = s.shape
+        D = self.fft_len + self.cp_len
+        if max_frames is None:
+            max_frames = int(n_streams * (n // (3 * D) + 4))
+        dev = s.device
+        frames = torch.empty(max_frames * 32, dtype=torch.uint8, device=dev)
+        slots = torch.empty((max_frames, self.byte_stride), dtype=torch.uint8, device=dev)
+        counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        z, zs = None, 0
+        if want_z:
+            zs = self.header_len() + (max_pkt_syms or (self.max_pkt_bytes * 8 // self.bps_payload + 1))
+            z = torch.zeros((max_frames, zs), dtype=torch.complex64, device=dev)
+        _lib.check(_lib.load().ofdmx_rx(
+            self.ctx, s.data_ptr(), n_streams, n, s.stride(0), frames.data_ptr(), max_frames,
+            slots.data_ptr(), self.byte_stride, z.data_ptr() if want_z else None, zs,
+            counts.data_ptr(), self._stream()), self.ctx)
+        c = counts.cpu().numpy()
+        if c[2]:
+            raise BufferError("more triggers (%d) than max_frames (%d)" % (c[0], max_frames))
+        nf = int(c[1])
+        rec = np.frombuffer(frames[: nf * 32].cpu().numpy().tobytes(), FRAME_DTYPE).copy()
+        return RxResult(rec, slots, c, z, self.crc_mode, int(c[0]))
+
+    def rx_host(self, samples, max_frames=None):
+        """Same through ofdmx_rx_host: numpy complex64 in, numpy out (H2D/D2H inside the call)."""
+        s = np.ascontiguousarray(samples, np.complex64)
+        if s.ndim == 1:
+            s = s[None, :]
+        n_streams, n = s.shape
+        D = self.fft_len + self.cp_len
+        if max_frames is None:
+            max_frames = int(n_streams * (n // (3 * D) + 4))
+        frames = np.zeros(max_frames, FRAME_DTYPE)
+        slots = np.zeros((max_frames, self.byte_stride), np.uint8)
+        cnt = _lib.Counts()
+        _lib.check(_lib.load().ofdmx_rx_host(self.ctx, s.ctypes.data, n_streams, n, frames.ctypes.data, max_frames,
+                                             slots.ctypes.data, self.byte_stride, C.byref(cnt)), self.ctx)
+        if cnt.overflow:
+            raise BufferError("more triggers (%d) than max_frames (%d)" % (cnt.n_triggers, max_frames))
+        c = np.array([cnt.n_triggers, cnt.n_frames, cnt.overflow, 0], np.int32)
+        return RxResult(frames[: cnt.n_frames].copy(), slots, c, None, self.crc_mode, cnt.n_triggers)
+
+    def sync(self, samples, max_trig=None):
+        """Schmidl & Cox only: returns (trigger indices int64, cfo float32, stream int32) as numpy."""
+        torch = self._torch()
+        s = samples if samples.dim() == 2 else samples.unsqueeze(0)
+        n_streams, n = s.shape
+        if max_trig is None:
+            max_trig = int(n_streams * (n // max(1, self.cp_len) + 16))
+        dev = s.device
+        trig = torch.zeros(max_trig, dtype=torch.int64, device=dev)
+        cfo = torch.zeros(max_trig, dtype=torch.float32, device=dev)
+        st = torch.zeros(max_trig, dtype=torch.int32, device=dev)
+        counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().ofdmx_sync(self.ctx, s.data_ptr(), n_streams, n, s.stride(0), trig.data_ptr(),
+                                          cfo.data_ptr(), st.data_ptr(), max_trig, counts.data_ptr(),
+                                          self._stream()), self.ctx)
+        c = counts.cpu().numpy()
+        if c[2]:
+            raise BufferError("more triggers (%d) than max_trig (%d)" % (c[0], max_trig))
+        k = int(c[0])
+        return trig[:k].cpu().numpy(), cfo[:k].cpu().numpy(), st[:k].cpu().numpy()
+
+    # ------------------------------------------------------------------ single blocks
+    def fft(self, x, forward=True):
+        """fft.fft_vcc(fft_len, forward, (), True) on a [n_syms, fft_len] complex64 cuda tensor."""
+        torch = self._torch()
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().ofdmx_fft(self.ctx, x.data_ptr(), out.data_ptr(), x.numel() // self.fft_len,
+                                         int(bool(forward)), self._stream()), self.ctx)
+        return out
+
+    def crc32(self, packets):
+        torch = self._torch()
+        dev = self._dev()
+        lens = np.array([len(b) for b in packets], np.int64)
+        flat = np.frombuffer(b"".join(bytes(bytearray(b)) for b in packets), np.uint8)
+        payload = torch.from_numpy(flat.copy() if len(flat) else np.zeros(1, np.uint8)).to(dev)
+        o = np.zeros(len(lens) + 1, np.int64)
+        o[1:] = np.cumsum(lens)
+        off = torch.from_numpy(o).to(dev)
+        out = torch.zeros(max(len(lens), 1), dtype=torch.int64, device=dev).to(torch.int32)
+        _lib.check(_lib.load().ofdmx_crc32(self.ctx, payload.data_ptr(), off.data_ptr(), len(lens), out.data_ptr(),
+                                           self._stream()), self.ctx)
+        return out[: len(lens)].cpu().numpy().astype(np.uint32)

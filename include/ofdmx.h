@@ -1,0 +1,159 @@
+/*
+ * ofdmx.h -- C ABI of the B200-native OFDM physical layer (libofdmx.so).
+ *
+ * This is the drop-in boundary for the sample-path blocks that gr-ofdm_tools' hier blocks wire
+ * together (citations relative to the reference tree):
+ *   python/ofdm_txrx_modules.py:120-254  ofdm_tx   (header gen, scrambler, repack, mapper, mux,
+ *                                                   carrier allocator, IFFT, cyclic prefixer)
+ *   python/ofdm_txrx_modules.py:257-426  ofdm_rx   (S&C sync, delay+NCO+mixer, header/payload
+ *                                                   demux, FFT, chanest, DFE equaliser, serializer,
+ *                                                   decoder, repack, descrambler)
+ *   python/ofdm_radio_hier.py:92-244     the same chain flattened, plus crc32_bb and selectors
+ *   python/ofdm_tx_rx_hier.py:55-87      ofdm_tx -> x0.01 ; ofdm_rx
+ * The reference has no native/FFI layer of its own (lib/CMakeLists.txt:27-34 is empty): its
+ * "FFI" for this path is the GNU Radio block API (io signatures of uint8 / gr_complex items plus
+ * "packet_len" stream tags).  The entry points below are what a gr.basic_block adaptor binds;
+ * INTEGRATION.md shows that adaptor.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (a CUDA stream is passed as void*).
+ *   - every *_dev pointer is device memory owned by the caller; the library owns only the opaque
+ *     context and its internal workspace (grown on demand, never on a steady-state call).
+ *   - complex samples are interleaved float32 (re,im) == gr_complex; frequency-domain vectors are
+ *     in shifted order (DC at fft_len/2) as in the reference (python/ofdm_txrx_modules.py:28-29).
+ *   - packet delimitation: CSR-style int64 offsets replace "packet_len" tags.
+ *   - all calls return 0 on success or a negative ofdmx_status; ofdmx_last_error() gives text.
+ *   - a context is single-owner (not thread-safe); different contexts may run concurrently.
+ *   - there is no CPU fallback: every entry point fails with OFDMX_ERR_CUDA if no sm_100 device.
+ */
+#ifndef OFDMX_H
+#define OFDMX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDMX_ABI_VERSION 1
+
+typedef enum {
+    OFDMX_OK = 0,
+    OFDMX_ERR_PARAM = -1,     /* invalid parameter (e.g. sync word length != fft_len) */
+    OFDMX_ERR_CUDA = -2,      /* CUDA runtime error / no device */
+    OFDMX_ERR_CAPACITY = -3,  /* caller buffer too small */
+    OFDMX_ERR_NOMEM = -4
+} ofdmx_status;
+
+typedef struct ofdmx_ctx ofdmx_ctx;
+
+/* Constructor parameters of ofdm_tx / ofdm_rx (python/ofdm_txrx_modules.py:143-155,278-291) and of
+ * ofdm_radio_hier (python/ofdm_radio_hier.py:34-39), flattened.  All pointers are HOST memory and
+ * are copied by ofdmx_create. */
+typedef struct {
+    int32_t fft_len;                /* power of two, 16..4096 */
+    int32_t cp_len;
+    int32_t n_occ_sets;             /* occupied_carriers: set-major flat list of carrier numbers */
+    const int32_t *occ_sizes;
+    const int32_t *occ_carriers;
+    int32_t n_pilot_sets;           /* pilot_carriers */
+    const int32_t *pilot_sizes;
+    const int32_t *pilot_carriers;
+    int32_t n_pilot_sym_sets;       /* pilot_symbols (re,im interleaved) */
+    const int32_t *pilot_sym_sizes;
+    const float *pilot_symbols;
+    const float *sync_word1;        /* fft_len x (re,im), shifted order */
+    const float *sync_word2;
+    int32_t bps_header;             /* 1 BPSK, 2 QPSK, 3 8PSK, 4 16-QAM, 6 64-QAM (extension) */
+    int32_t bps_payload;
+    int32_t scramble_header;        /* packet_header_ofdm(scramble_header=...) */
+    int32_t scramble_seed;          /* additive_scrambler seed: 0x7f = on, 0x00 = off */
+    int32_t crc_mode;               /* 1: in-graph digital.crc32_bb on TX and RX */
+    float   threshold;              /* ofdm_sync_sc_cfb plateau threshold (0.9) */
+    int32_t max_carr_offset;        /* ofdm_chanest_vcvc max_carr_offset; -1 = unlimited */
+    float   alpha;                  /* ofdm_equalizer_simpledfe alpha (0.1) */
+    float   tx_scale;               /* multiply_const_vcc after the prefixer (0.01 in the hier blocks) */
+    int32_t demux_holdoff;          /* header_payload_demux: items left unconsumed after a payload:
+                                       fft_len+cp_len (GNU Radio < 3.7.10) or 1 (>= 3.7.10) */
+    int32_t max_pkt_bytes;          /* largest header length field the caller sizes slots for (<=4095) */
+} ofdmx_params;
+
+/* Per-frame record (replaces the stream tags / PMT header dict of the reference). 32 bytes. */
+typedef struct {
+    int64_t  trigger;       /* index of the trigger item in the stream (S&C output coordinates) */
+    float    cfo;           /* fine frequency estimate arg(P) at the trigger [rad] */
+    int32_t  stream;        /* stream index */
+    uint32_t flags;         /* OFDMX_F_* */
+    uint16_t pkt_len;       /* header length field: bytes incl. in-graph CRC */
+    uint16_t pkt_num;       /* header packet counter */
+    uint16_t frame_syms;    /* payload OFDM symbols */
+    int16_t  carr_offset;   /* integer carrier offset (ofdm_sync_carr_offset tag) */
+    uint32_t slot;          /* payload bytes are at bytes_out_dev + slot*byte_stride */
+} ofdmx_frame;
+
+#define OFDMX_F_HDR_OK   1u   /* header CRC-8 matched */
+#define OFDMX_F_CRC_OK   2u   /* payload CRC-32 matched (always set when crc_mode == 0) */
+#define OFDMX_F_COMPLETE 4u   /* whole frame lies inside the buffer */
+#define OFDMX_F_ACCEPTED 8u   /* the header/payload demux would have examined this trigger */
+#define OFDMX_F_HDR_SEEN 16u  /* the 3 header-side symbols lie inside the buffer */
+
+typedef struct {
+    int32_t n_triggers;     /* plateau-detector triggers found (all streams) */
+    int32_t n_frames;       /* frame records written */
+    int32_t overflow;       /* nonzero: n_triggers exceeded max_frames, output truncated */
+    int32_t reserved;
+} ofdmx_counts;
+
+/* ---- lifetime ---- */
+int  ofdmx_abi_version(void);
+int  ofdmx_create(const ofdmx_params *params, int device, ofdmx_ctx **ctx_out);
+void ofdmx_destroy(ofdmx_ctx *ctx);
+const char *ofdmx_last_error(const ofdmx_ctx *ctx);   /* ctx may be NULL (creation errors) */
+/* pre-size the internal workspace so that later calls of this shape do not allocate */
+int  ofdmx_reserve(ofdmx_ctx *ctx, int64_t n_streams, int64_t n_samples, int64_t max_frames);
+int  ofdmx_header_len(const ofdmx_ctx *ctx);          /* items in the header = len(occupied_carriers[0]) */
+int64_t ofdmx_tx_frame_samples(const ofdmx_ctx *ctx, int64_t payload_bytes);
+int64_t ofdmx_launch_count(const ofdmx_ctx *ctx);     /* kernels launched by this context so far */
+
+/* ---- TX: replaces ofdm_tx (+ crc32_bb + x tx_scale) ----
+ * payload_dev[pkt_offsets[i] .. pkt_offsets[i+1]) is packet i.  Packet i is written to
+ * samples_out_dev[sample_offsets_dev[i] .. sample_offsets_dev[i+1]) (offsets computed on device). */
+int ofdmx_tx(ofdmx_ctx *ctx, const uint8_t *payload_dev, const int64_t *pkt_offsets_dev,
+             int64_t n_pkts, int32_t first_pkt_num, float *samples_out_dev, int64_t cap_samples,
+             int64_t *sample_offsets_dev /* n_pkts+1 */, void *cuda_stream);
+
+/* ---- RX: replaces ofdm_rx (+ crc32_bb check) ----
+ * samples_dev: n_streams rows of n_samples complex items, row stride stream_stride (items).
+ * frames_out_dev: records of the frames the demux accepts with a valid header, ordered by
+ * (stream, trigger).  bytes_out_dev: max_frames slots of byte_stride bytes.  z_out_dev (optional
+ * debug tap, may be NULL): pre-decision equalised symbols, header_len + payload symbols per slot.
+ * counts_dev: one ofdmx_counts. */
+int ofdmx_rx(ofdmx_ctx *ctx, const float *samples_dev, int64_t n_streams, int64_t n_samples,
+             int64_t stream_stride, ofdmx_frame *frames_out_dev, int64_t max_frames,
+             uint8_t *bytes_out_dev, int64_t byte_stride, float *z_out_dev, int64_t z_stride,
+             ofdmx_counts *counts_dev, void *cuda_stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies in, runs, copies records, counts and
+ * the used payload slots back, and synchronises.  This is the call a GNU Radio work() makes. */
+int ofdmx_rx_host(ofdmx_ctx *ctx, const float *samples_host, int64_t n_streams, int64_t n_samples,
+                  ofdmx_frame *frames_host, int64_t max_frames, uint8_t *bytes_host,
+                  int64_t byte_stride, ofdmx_counts *counts_host);
+
+/* ---- Schmidl & Cox only: replaces digital.ofdm_sync_sc_cfb + plateau detector ----
+ * trig_out_dev / cfo_out_dev / stream_out_dev: up to max_trig triggers ordered by (stream, index). */
+int ofdmx_sync(ofdmx_ctx *ctx, const float *samples_dev, int64_t n_streams, int64_t n_samples,
+               int64_t stream_stride, int64_t *trig_out_dev, float *cfo_out_dev,
+               int32_t *stream_out_dev, int64_t max_trig, ofdmx_counts *counts_dev,
+               void *cuda_stream);
+
+/* ---- single blocks, exported for block-level parity tests and reuse ---- */
+/* fft.fft_vcc(fft_len, forward, (), shift=True): n_syms vectors of fft_len items */
+int ofdmx_fft(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_syms, int forward,
+              void *cuda_stream);
+/* digital.crc32_bb arithmetic: zlib CRC-32 of each packet */
+int ofdmx_crc32(ofdmx_ctx *ctx, const uint8_t *bytes_dev, const int64_t *pkt_offsets_dev,
+                int64_t n_pkts, uint32_t *crc_out_dev, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

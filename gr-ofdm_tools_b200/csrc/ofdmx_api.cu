@@ -22,7 +22,21 @@ struct DevBuf {
 
 }  // namespace
 
+enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN, K_EMIT_SCAN,
+             K_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_NSLOTS };
+static const char *const kSlotNames[K_NSLOTS] = {
+    "sync_metric_kernel", "plateau_kernel", "trig_count_kernel", "trig_scan_kernel", "trig_scatter_kernel",
+    "cfo_kernel", "rx_frame_kernel", "chain_kernel", "emit_scan_kernel", "emit_kernel", "tx_offsets_kernel",
+    "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel" };
+
+struct ProfRec { int slot; cudaEvent_t a, b; };
+
 struct ofdmx_ctx {
+    bool profiling = false;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[K_NSLOTS] = {0};
+    int64_t prof_calls[K_NSLOTS] = {0};
     int device = 0;
     int sm_count = 148;
     ofdmx_params prm{};
@@ -85,6 +99,34 @@ int grow(ofdmx_ctx *ctx, DevBuf &b, size_t bytes)
     b.cap = want;
     return 0;
 }
+
+// records a CUDA event pair around one kernel launch when profiling is on
+struct KTimer {
+    ofdmx_ctx *c;
+    cudaStream_t st;
+    ProfRec r;
+    bool on;
+    KTimer(ofdmx_ctx *ctx, int slot, cudaStream_t s) : c(ctx), st(s), on(ctx->profiling)
+    {
+        ctx->launches++;
+        if (!on) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        r.slot = slot; r.a = get(); r.b = get();
+        cudaEventRecord(r.a, st);
+    }
+    ~KTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(r.b, st);
+        c->prof_pending.push_back(r);
+    }
+};
+#define KT(slot) KTimer kt_(ctx_, slot, st)
 
 inline int shifted_bin(int c, int n)
 {
@@ -223,20 +265,20 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
              int64_t stride, int64_t max_trig, ofdmx_counts *counts_dev, cudaStream_t st)
 {
     const KP &kp = ctx->kp;
+    ofdmx_ctx *ctx_ = ctx;
     CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
     const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
     dim3 grid((unsigned)tiles, (unsigned)n_streams);
-    sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr,
-                                                                      w.detmask, w.wps);
+    { KT(K_SYNC); sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr,
+                                                                                   w.detmask, w.wps); }
     const long long pb = (w.n_words + OFDMX_THREADS - 1) / OFDMX_THREADS;
-    plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp);
-    trig_count_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.blocksum);
-    trig_scan_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nb, (int)max_trig, counts_dev, w.n_trig, w.stream_start, n_streams);
-    trig_scatter_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.wps, w.blocksum, (int)max_trig,
-                                                         w.trig, w.trig_stream, w.stream_start);
-    cfo_kernel<<<ctx->sm_count * 2, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream,
-                                                            w.n_trig, w.cfo);
-    ctx->launches += 6;
+    { KT(K_PLATEAU); plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp); }
+    { KT(K_TRIG_COUNT); trig_count_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.blocksum); }
+    { KT(K_TRIG_SCAN); trig_scan_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nb, (int)max_trig, counts_dev, w.n_trig, w.stream_start, n_streams); }
+    { KT(K_TRIG_SCATTER); trig_scatter_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.wps, w.blocksum, (int)max_trig,
+                                                                             w.trig, w.trig_stream, w.stream_start); }
+    { KT(K_CFO); cfo_kernel<<<ctx->sm_count * 2, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream,
+                                                                          w.n_trig, w.cfo); }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -456,11 +498,42 @@ void ofdmx_destroy(ofdmx_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     for (void *p : c->tables) cudaFree(p);
     for (DevBuf *b : { &c->ws, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
         if (b->p) cudaFree(b->p);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+int ofdmx_profile(ofdmx_ctx *c, int enable)
+{
+    if (!c) return OFDMX_ERR_PARAM;
+    c->profiling = enable != 0;
+    for (auto &r : c->prof_pending) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
+    c->prof_pending.clear();
+    for (int i = 0; i < K_NSLOTS; i++) { c->prof_ms[i] = 0; c->prof_calls[i] = 0; }
+    return OFDMX_OK;
+}
+int ofdmx_profile_slots(void) { return K_NSLOTS; }
+const char *ofdmx_profile_name(int slot) { return (slot >= 0 && slot < K_NSLOTS) ? kSlotNames[slot] : ""; }
+int ofdmx_profile_read(ofdmx_ctx *c, float *ms_total, int64_t *calls)
+{
+    if (!c || !ms_total || !calls) return OFDMX_ERR_PARAM;
+    if (int rc = check_device(c)) return rc;
+    for (auto &r : c->prof_pending) {
+        CUDA_TRY(c, cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CUDA_TRY(c, cudaEventElapsedTime(&ms, r.a, r.b));
+        c->prof_ms[r.slot] += ms;
+        c->prof_calls[r.slot]++;
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_pending.clear();
+    for (int i = 0; i < K_NSLOTS; i++) { ms_total[i] = (float)c->prof_ms[i]; calls[i] = c->prof_calls[i]; }
+    return OFDMX_OK;
 }
 
 int ofdmx_header_len(const ofdmx_ctx *c) { return c ? c->hl : 0; }
@@ -518,14 +591,14 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     RxWs w = carve(c->ws.p, n_streams, n_samples, max_frames);
     const float2 *smp = (const float2 *)samples_dev;
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
-    rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
+    ofdmx_ctx *ctx_ = c;
+    { KT(K_FRAME); rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
         c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
-        byte_stride, (float2 *)z_out, z_stride);
-    chain_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(c->kp, n_samples, w.trig, w.spec, w.stream_start, w.jumpA, w.jumpB,
-                                                       w.markA, w.markB, w.stream_count);
-    emit_scan_kernel<<<1, 1024, 0, st>>>(w.stream_count, n_streams, counts_dev);
-    emit_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(w.spec, w.markA, w.stream_start, w.stream_count, frames_out);
-    c->launches += 4;
+        byte_stride, (float2 *)z_out, z_stride); }
+    { KT(K_CHAIN); chain_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(c->kp, n_samples, w.trig, w.spec, w.stream_start, w.jumpA, w.jumpB,
+                                                       w.markA, w.markB, w.stream_count); }
+    { KT(K_EMIT_SCAN); emit_scan_kernel<<<1, 1024, 0, st>>>(w.stream_count, n_streams, counts_dev); }
+    { KT(K_EMIT); emit_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(w.spec, w.markA, w.stream_start, w.stream_count, frames_out); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }
@@ -568,12 +641,12 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
     if (n_pkts == 0) return OFDMX_OK;
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    tx_offsets_kernel<<<1, 1024, 0, st>>>(c->kp, (const long long *)pkt_off_dev, n_pkts, (long long *)sample_off_dev);
+    ofdmx_ctx *ctx_ = c;
+    { KT(K_TX_OFF); tx_offsets_kernel<<<1, 1024, 0, st>>>(c->kp, (const long long *)pkt_off_dev, n_pkts, (long long *)sample_off_dev); }
     const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
-    tx_frame_kernel<<<grid, OFDMX_THREADS, c->tx_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts,
+    { KT(K_TX); tx_frame_kernel<<<grid, OFDMX_THREADS, c->tx_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts,
                                                               first_pkt_num, (float2 *)samples_out, cap_samples,
-                                                              (const long long *)sample_off_dev);
-    c->launches += 2;
+                                                              (const long long *)sample_off_dev); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }
@@ -586,11 +659,12 @@ int ofdmx_fft(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_syms,
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)std::min<int64_t>(n_syms, (int64_t)c->sm_count * 8);
     const size_t sm = (size_t)c->kp.N * 8;
+    ofdmx_ctx *ctx_ = c;
+    KT(K_FFT);
     if (forward)
         fft_vcc_kernel<false><<<grid, OFDMX_THREADS, sm, st>>>((const float2 *)in_dev, (float2 *)out_dev, n_syms, c->kp.N, c->kp.logN, c->kp.tw);
     else
         fft_vcc_kernel<true><<<grid, OFDMX_THREADS, sm, st>>>((const float2 *)in_dev, (float2 *)out_dev, n_syms, c->kp.N, c->kp.logN, c->kp.tw);
-    c->launches += 1;
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }
@@ -603,9 +677,9 @@ int ofdmx_crc32(ofdmx_ctx *c, const uint8_t *bytes_dev, const int64_t *pkt_off_d
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
-    crc32_kernel<<<grid, OFDMX_THREADS, 0, st>>>(bytes_dev, (const long long *)pkt_off_dev, n_pkts, crc_out_dev,
-                                                 c->kp.crc_tab, c->kp.crc_pow);
-    c->launches += 1;
+    ofdmx_ctx *ctx_ = c;
+    { KT(K_CRC); crc32_kernel<<<grid, OFDMX_THREADS, 0, st>>>(bytes_dev, (const long long *)pkt_off_dev, n_pkts, crc_out_dev,
+                                                 c->kp.crc_tab, c->kp.crc_pow); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }

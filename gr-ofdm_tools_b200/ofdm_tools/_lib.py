@@ -49,6 +49,10 @@ SYMBOLS = {
     "ofdmx_rx": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
     "ofdmx_rx_host": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "ofdmx_sync": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P]),
+    "ofdmx_profile": (C.c_int, [_P, C.c_int]),
+    "ofdmx_profile_slots": (C.c_int, []),
+    "ofdmx_profile_name": (C.c_char_p, [C.c_int]),
+    "ofdmx_profile_read": (C.c_int, [_P, _P, _P]),
     "ofdmx_fft": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P]),
     "ofdmx_crc32": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
 }

@@ -182,6 +182,19 @@ class OfdmPhy(object):
     def launch_count(self):
         return _lib.load().ofdmx_launch_count(self.ctx)
 
+    def profile(self, enable=True):
+        """Start/stop recording CUDA events around every kernel this context launches."""
+        _lib.check(_lib.load().ofdmx_profile(self.ctx, int(bool(enable))), self.ctx)
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since profile(True); synchronises the events."""
+        L = _lib.load()
+        n = L.ofdmx_profile_slots()
+        ms = (C.c_float * n)()
+        calls = (C.c_int64 * n)()
+        _lib.check(L.ofdmx_profile_read(self.ctx, ms, calls), self.ctx)
+        return {L.ofdmx_profile_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n) if calls[i]}
+
     # ------------------------------------------------------------------ TX
     def tx(self, packets, first_pkt_num=0):
         """packets: list of bytes-like (or (uint8 cuda tensor, int64 cuda offsets)).

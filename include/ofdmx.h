@@ -145,6 +145,15 @@ int ofdmx_sync(ofdmx_ctx *ctx, const float *samples_dev, int64_t n_streams, int6
                int32_t *stream_out_dev, int64_t max_trig, ofdmx_counts *counts_dev,
                void *cuda_stream);
 
+/* ---- per-kernel timing (CUDA events recorded on the caller's stream around every kernel) ----
+ * ofdmx_profile(ctx, 1) starts recording and clears the totals; ofdmx_profile_read synchronises the
+ * recorded events and adds them to the totals: ms_total[i] / calls[i] for kernel slot i <
+ * ofdmx_profile_slots(); ofdmx_profile_name(i) names the slot. */
+int ofdmx_profile(ofdmx_ctx *ctx, int enable);
+int ofdmx_profile_slots(void);
+const char *ofdmx_profile_name(int slot);
+int ofdmx_profile_read(ofdmx_ctx *ctx, float *ms_total, int64_t *calls);
+
 /* ---- single blocks, exported for block-level parity tests and reuse ---- */
 /* fft.fft_vcc(fft_len, forward, (), shift=True): n_syms vectors of fft_len items */
 int ofdmx_fft(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_syms, int forward,

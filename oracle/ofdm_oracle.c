@@ -564,7 +564,10 @@ int orc_sync_f32(const orc_params *p, const float *r, int64_t n_samp,
     for (int64_t i = 0; i < n_samp; i++) {
         float sr = 0.f, si = 0.f, se = 0.f;
         const float *a = xr + n + i - h + 1, *b = xi + n + i - h + 1, *c = en + i + 1;
+        /* VOLK evaluates these dot products with SIMD partial sums; allow the same here */
+#pragma omp simd reduction(+ : sr, si)
         for (int k = 0; k < h; k++) { sr += -1.0f * a[k]; si += -1.0f * b[k]; }
+#pragma omp simd reduction(+ : se)
         for (int k = 0; k < n; k++) se += 0.5f * c[k];
         float m = (sr * sr + si * si) / (se * se);
         det[i] = (uint8_t)(m >= p->threshold);
@@ -718,15 +721,16 @@ static void frame_equalize(const rx_ctx *c, cd *frame, int n_sym, int off, cd *H
     for (int k = 0; k < n; k++) H[k] *= pc;
 }
 
-int orc_rx(const orc_params *p, const float *r, int64_t n_samp,
-           orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
-           float *z_out, int64_t z_stride, int64_t *n_frames,
-           int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig)
+static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
+                   orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+                   float *z_out, int64_t z_stride, int64_t *n_frames,
+                   int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig, int f32sync)
 {
     if (check_params(p)) return -1;
     const int n = p->fft_len, D = n + p->cp_len, hl = orc_header_len(p);
     if (n > 4096) return -1;
-    int rc = orc_sync(p, r, n_samp, NULL, trig, cfo, max_trig, n_trig);
+    int rc = f32sync ? orc_sync_f32(p, r, n_samp, trig, cfo, max_trig, n_trig)
+                     : orc_sync(p, r, n_samp, NULL, trig, cfo, max_trig, n_trig);
     if (rc) return rc;
     if (*n_trig > max_trig) return -3;
 
@@ -859,4 +863,23 @@ int orc_rx(const orc_params *p, const float *r, int64_t n_samp,
     free(base); free(c.occ_mask); free(c.occ_base); free(c.pil_mask); free(c.pil_val);
     free(y); free(H); free(zh); free(hbits);
     return rc;
+}
+
+int orc_rx(const orc_params *p, const float *r, int64_t n_samp,
+           orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+           float *z_out, int64_t z_stride, int64_t *n_frames,
+           int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig)
+{
+    return rx_impl(p, r, n_samp, recs, max_frames, bytes_out, byte_stride, z_out, z_stride, n_frames,
+                   trig, cfo, max_trig, n_trig, 0);
+}
+
+/* CPU-baseline variant: the sync stage is the float32 FIR port (what GNU Radio's blocks cost);
+ * everything after the trigger list is the same code as orc_rx. */
+int orc_rx_baseline(const orc_params *p, const float *r, int64_t n_samp,
+                    orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+                    int64_t *n_frames, int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig)
+{
+    return rx_impl(p, r, n_samp, recs, max_frames, bytes_out, byte_stride, NULL, 0, n_frames,
+                   trig, cfo, max_trig, n_trig, 1);
 }

@@ -110,6 +110,11 @@ int orc_rx(const orc_params *p, const float *samples, int64_t n,
            float *z_out, int64_t z_stride, int64_t *n_frames,
            int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig);
 
+/* same chain with the float32 FIR sync port in front: used only to time the CPU baseline */
+int orc_rx_baseline(const orc_params *p, const float *samples, int64_t n,
+                    orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+                    int64_t *n_frames, int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,8 @@ def lib():
         L.orc_rx.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                              C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_int64, C.c_void_p]
+        L.orc_rx_baseline.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     return _LIB
 
 
@@ -260,6 +262,24 @@ class Oracle:
         k = nf.value
         return {"frames": recs[:k].copy(), "bytes": by[:k], "z": z[:k] if want_z else None,
                 "triggers": trig[:nt.value].copy(), "cfo": cfo[:nt.value].copy()}
+
+    def rx_baseline(self, samples, max_frames=None, byte_stride=4096):
+        """RX with the float32 FIR sync port (CPU-baseline timing only). Returns frame records."""
+        s = np.ascontiguousarray(samples, np.complex64)
+        n = s.shape[0]
+        D = self.fft_len + self.cp_len
+        max_frames = max_frames or (n // (3 * D) + 4)
+        max_trig = max(16, n // max(1, self.cp_len) + 16)
+        recs = np.zeros(max_frames, FRAME_DTYPE)
+        by = np.zeros((max_frames, byte_stride), np.uint8)
+        trig = np.zeros(max_trig, np.int64)
+        cfo = np.zeros(max_trig, np.float32)
+        nf, nt = C.c_int64(), C.c_int64()
+        rc = self.L.orc_rx_baseline(self._pp, _ptr(s), n, _ptr(recs), max_frames, _ptr(by), byte_stride,
+                                    C.byref(nf), _ptr(trig), _ptr(cfo), max_trig, C.byref(nt))
+        if rc:
+            raise RuntimeError("orc_rx_baseline failed: %d" % rc)
+        return recs[:nf.value].copy()
 
     def payloads(self, res):
         """Byte strings the flowgraph would deliver (CRC-failed packets dropped, CRC stripped

@@ -1,6 +1,7 @@
 // ofdmx_api.cu -- C ABI (include/ofdmx.h) over the sm_100a kernels.  No CPU fallback: every
 // entry point needs a CUDA device and reports OFDMX_ERR_CUDA otherwise.
 #include "ofdmx_kernels.cuh"
+#include "ofdmx_sync.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -52,7 +53,7 @@ struct ofdmx_ctx {
     // host-buffer path
     DevBuf h_samples, h_frames, h_bytes, h_counts;
     cudaStream_t own_stream = nullptr;
-    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0;
+    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0;
 };
 
 namespace {
@@ -267,10 +268,18 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
     const KP &kp = ctx->kp;
     ofdmx_ctx *ctx_ = ctx;
     CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
-    const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
-    dim3 grid((unsigned)tiles, (unsigned)n_streams);
-    { KT(K_SYNC); sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr,
-                                                                                   w.detmask, w.wps); }
+    if (kp.N >= 32) {
+        const long long tiles = (n_samples + SV_T - 1) / SV_T;
+        dim3 grid((unsigned)tiles, (unsigned)n_streams);
+        KT(K_SYNC);
+        sync_metric_fast_kernel<<<grid, SV_THREADS, ctx->sync_fast_smem, st>>>(samples, n_samples, stride, kp.N, (float)kp.thr,
+                                                                                kp.thr, w.detmask, w.wps);
+    } else {
+        const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
+        dim3 grid((unsigned)tiles, (unsigned)n_streams);
+        KT(K_SYNC);
+        sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr, w.detmask, w.wps);
+    }
     const long long pb = (w.n_words + OFDMX_THREADS - 1) / OFDMX_THREADS;
     { KT(K_PLATEAU); plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp); }
     { KT(K_TRIG_COUNT); trig_count_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.blocksum); }
@@ -482,7 +491,9 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         c->frame_smem = (size_t)N * 8 * 4 + 64 + N + align_up(c->hl, 16) + align_up(kp.max_pkt_syms, 16)
                         + align_up(kp.max_pkt_bytes, 16) + 16;
         c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16;
-        if (cudaFuncSetAttribute(sync_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_smem) != cudaSuccess
+        c->sync_fast_smem = sync_fast_smem_bytes(N);
+        if (cudaFuncSetAttribute(sync_metric_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
+            || cudaFuncSetAttribute(sync_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_smem) != cudaSuccess
             || cudaFuncSetAttribute(rx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem) != cudaSuccess
             || cudaFuncSetAttribute(tx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s (is this an sm_100 device?)",

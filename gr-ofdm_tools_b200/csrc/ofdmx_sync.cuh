@@ -1,0 +1,218 @@
+// ofdmx_sync.cuh -- K2: Schmidl & Cox timing metric, fast kernel (fft_len >= 32).
+//
+// Replaces the per-sample chain of ofdm_sync_sc_cfb (delay, conjugate, multiply, two moving-average
+// FIRs, squares, divide; python/ofdm_txrx_modules.py:324) up to the plateau detector input, producing
+// one detect bit per sample:   detect[n] = R[n]^2 > 0  &&  |P[n]|^2 >= thr * R[n]^2.
+//
+// The decision is defined in exact arithmetic (the oracle evaluates it in float64).  This kernel gets
+// the same bits at float32 speed with a filtered predicate:
+//   * fast path: float32 window sums from a two-level scheme -- per-thread chunk totals (16
+//     consecutive samples), a block scan of the chunk totals gives each chunk's initial window sums,
+//     then a 16-step sliding recurrence inside the chunk;
+//   * every comparison carries a bound `err` on what float32 rounding can have done to it (derived
+//     from the tile's total energy); |lhs - rhs| > err decides immediately;
+//   * the rare samples inside the band (a few per plateau edge) are re-evaluated by the whole warp in
+//     float64 directly from the staged samples -- exactly the oracle's sum.
+//
+// Tile = 4096 samples + fft_len halo per CTA, 256 threads, one 16-sample chunk per thread.  Samples
+// are staged once in shared memory in a 144-byte-per-chunk layout, so that every thread reads its
+// chunk (and the chunks fft_len/2 and fft_len behind it) with conflict-free 16-byte loads.
+#pragma once
+#include "ofdmx_dev.cuh"
+
+#define SV_C 16              // samples per chunk (per thread)
+#define SV_T 4096            // samples per tile
+#define SV_THREADS 256       // = SV_T / SV_C
+
+// float4 index of 16-byte unit q (0..7) of chunk j
+__device__ __forceinline__ int sv_off(int j, int q) { return 9 * j + q; }
+// float2 (sample) index of sample s (relative to the start of the staged region)
+__device__ __forceinline__ int sv_sample(int s) { return (9 * (s >> 4) + ((s >> 1) & 7)) * 2 + (s & 1); }
+
+__device__ __forceinline__ void sv_products(const float4 *__restrict__ r4, int jown, int jdel, float2 *x, float *e)
+{
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 a = r4[sv_off(jown, q)];
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jdel >= 0) b = r4[sv_off(jdel, q)];
+        x[2 * q] = make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+        x[2 * q + 1] = make_float2(fmaf(a.z, b.z, a.w * b.w), fmaf(a.w, b.z, -(a.z * b.w)));
+        e[2 * q] = fmaf(a.x, a.x, a.y * a.y);
+        e[2 * q + 1] = fmaf(a.z, a.z, a.w * a.w);
+    }
+}
+
+__global__ void __launch_bounds__(SV_THREADS, 3)
+sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int N, float thr_f,
+                        double thr_d, uint32_t *__restrict__ detmask, long long wps)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int h = N >> 1;
+    const int nhc = N >> 4;                 // halo chunks
+    const int hc = h >> 4;                  // chunks per half window
+    const int nch = nhc + SV_THREADS;       // chunks staged
+    float4 *r4 = reinterpret_cast<float4 *>(smem_raw);            // 9 * nch float4
+    float *TXr = reinterpret_cast<float *>(r4 + 9 * nch);         // nch + 1 each
+    float *TXi = TXr + nch + 1;
+    float *TE = TXi + nch + 1;
+    __shared__ float wsum[3][SV_THREADS / 32 + 1];
+
+    const long long ts = (long long)blockIdx.x * SV_T;
+    const float2 *r = samples + (long long)blockIdx.y * stride;
+    const bool aligned = ((reinterpret_cast<unsigned long long>(r) & 15ull) == 0);
+
+    // ---- phase 0: stage [ts - N, ts + SV_T) (zeros outside the stream)
+    const int n_units = nch * 8;
+    for (int u = tid; u < n_units; u += SV_THREADS) {
+        const long long m = ts - N + 2LL * u;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= 0 && m + 1 < n) {
+            if (aligned) v = __ldg(reinterpret_cast<const float4 *>(r + m));
+            else { const float2 a = __ldg(&r[m]), b = __ldg(&r[m + 1]); v = make_float4(a.x, a.y, b.x, b.y); }
+        } else if (m >= 0 && m < n) {
+            const float2 a = __ldg(&r[m]);
+            v.x = a.x; v.y = a.y;
+        }
+        r4[u + (u >> 3)] = v;
+    }
+    __syncthreads();
+
+    // ---- phase 1: products and chunk totals
+    const int J = nhc + tid;                // this thread's tile chunk
+    float2 x[SV_C];
+    float e[SV_C];
+    sv_products(r4, J, J - hc, x, e);
+    {
+        float sxr = 0.f, sxi = 0.f, se = 0.f;
+#pragma unroll
+        for (int q = 0; q < SV_C; q++) { sxr += x[q].x; sxi += x[q].y; se += e[q]; }
+        TXr[J] = sxr; TXi[J] = sxi; TE[J] = se;
+    }
+    for (int j = tid; j < nhc; j += SV_THREADS) {      // halo chunks: totals only
+        float2 hx[SV_C];
+        float he[SV_C];
+        sv_products(r4, j, j - hc, hx, he);
+        float sxr = 0.f, sxi = 0.f, se = 0.f;
+#pragma unroll
+        for (int q = 0; q < SV_C; q++) { sxr += hx[q].x; sxi += hx[q].y; se += he[q]; }
+        TXr[j] = sxr; TXi[j] = sxi; TE[j] = se;
+    }
+    __syncthreads();
+
+    // ---- phase 2: exclusive scan of the chunk totals (<= 512 entries, 2 per thread)
+    {
+        const int j0 = 2 * tid, j1 = 2 * tid + 1;
+        const float a0 = (j0 < nch) ? TXr[j0] : 0.f, a1 = (j1 < nch) ? TXr[j1] : 0.f;
+        const float b0 = (j0 < nch) ? TXi[j0] : 0.f, b1 = (j1 < nch) ? TXi[j1] : 0.f;
+        const float c0 = (j0 < nch) ? TE[j0] : 0.f, c1 = (j1 < nch) ? TE[j1] : 0.f;
+        float ia = a0 + a1, ib = b0 + b1, ic = c0 + c1;
+        const float ta = ia, tb = ib, tc = ic;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float pa = __shfl_up_sync(0xffffffffu, ia, o);
+            const float pb = __shfl_up_sync(0xffffffffu, ib, o);
+            const float pc = __shfl_up_sync(0xffffffffu, ic, o);
+            if (lane >= o) { ia += pa; ib += pb; ic += pc; }
+        }
+        if (lane == 31) { wsum[0][wid] = ia; wsum[1][wid] = ib; wsum[2][wid] = ic; }
+        __syncthreads();
+        float oa = 0.f, ob = 0.f, oc = 0.f;
+        for (int w = 0; w < wid; w++) { oa += wsum[0][w]; ob += wsum[1][w]; oc += wsum[2][w]; }
+        const float ea = oa + ia - ta, eb = ob + ib - tb, ec = oc + ic - tc;   // exclusive prefix at j0
+        if (j0 < nch) { TXr[j0] = ea; TXi[j0] = eb; TE[j0] = ec; }
+        if (j1 < nch) { TXr[j1] = ea + a0; TXi[j1] = eb + b0; TE[j1] = ec + c0; }
+        if (tid == ((nch - 1) >> 1)) {               // element nch = grand total (a1/b1/c1 are 0 past the end)
+            TXr[nch] = ea + a0 + a1; TXi[nch] = eb + b0 + b1; TE[nch] = ec + c0 + c1;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: sliding window inside the chunk, filtered comparison
+    const float A = TE[nch];                         // total energy staged: bounds every partial sum
+    const float eps = 1.0e-5f * A;                   // bound on the float32 error of Pr, Pi, E
+    float Pr = TXr[J] - TXr[J - hc];
+    float Pi = TXi[J] - TXi[J - hc];
+    float E = TE[J] - TE[J - nhc];
+    const float thr4 = 0.25f * thr_f;
+    unsigned det = 0, unc = 0;
+    const int jd = J - hc, jn = J - nhc;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float4 b = r4[sv_off(jd, q)];          // r[n - N/2]
+        const float4 c = r4[sv_off(jn, q)];          // r[n - N]
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const float br = s ? b.z : b.x, bi = s ? b.w : b.y, cr = s ? c.z : c.x, ci = s ? c.w : c.y;
+            const float xdr = fmaf(br, cr, bi * ci), xdi = fmaf(bi, cr, -(br * ci));   // x[n - N/2]
+            const float ed = fmaf(cr, cr, ci * ci);                                       // e[n - N]
+            const int k = 2 * q + s;
+            Pr += x[k].x - xdr;
+            Pi += x[k].y - xdi;
+            E += e[k] - ed;
+            const float pm2 = fmaf(Pr, Pr, Pi * Pi);
+            const float rhs = thr4 * E * E;
+            const float d = pm2 - rhs;
+            const float err = fmaf(2.0f * eps, fabsf(Pr) + fabsf(Pi) + fabsf(E), fmaf(3.0f * eps, eps, 1.0e-6f * (pm2 + rhs)));
+            det |= (d > err ? 1u : 0u) << k;
+            unc |= (fabsf(d) <= err ? 1u : 0u) << k;
+        }
+    }
+    if (A == 0.0f) { det = 0; unc = 0; }             // all-zero tile: R^2 > 0 is false everywhere
+    {   // samples beyond the end of the stream never detect
+        const long long first = ts + (long long)tid * SV_C;
+        if (first + SV_C > n) {
+            const int valid = (n > first) ? (int)(n - first) : 0;
+            const unsigned m = (valid >= 16) ? 0xffffu : ((1u << valid) - 1u);
+            det &= m; unc &= m;
+        }
+    }
+
+    // ---- exact re-evaluation (float64, whole warp per sample) of the samples inside the band
+    unsigned pending = __ballot_sync(0xffffffffu, unc != 0);
+    const float2 *r2 = reinterpret_cast<const float2 *>(r4);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        unsigned m = __shfl_sync(0xffffffffu, unc, src);
+        const int jsrc = nhc + (wid << 5) + src;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int i = (jsrc << 4) + k;           // sample position in the staged region
+            double sr = 0.0, si = 0.0, se = 0.0;
+            for (int t = lane; t < h; t += 32) {
+                const float2 a = r2[sv_sample(i - t)], b = r2[sv_sample(i - t - h)];
+                sr += (double)a.x * b.x + (double)a.y * b.y;
+                si += (double)a.y * b.x - (double)a.x * b.y;
+            }
+            for (int t = lane; t < N; t += 32) {
+                const float2 a = r2[sv_sample(i - t)];
+                se += (double)a.x * a.x + (double)a.y * a.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                si += __shfl_xor_sync(0xffffffffu, si, o);
+                se += __shfl_xor_sync(0xffffffffu, se, o);
+            }
+            const double R = 0.5 * se, R2 = R * R, pm2 = sr * sr + si * si;
+            const bool dd = (R2 > 0.0) && (pm2 >= thr_d * R2);
+            if (lane == src) det = dd ? (det | (1u << k)) : (det & ~(1u << k));
+        }
+    }
+
+    // ---- 16 bits per thread -> 32-bit words
+    const unsigned hi = __shfl_down_sync(0xffffffffu, det, 1);
+    if (!(tid & 1)) {
+        const long long w = (ts >> 5) + (tid >> 1);
+        if (w < wps) detmask[(long long)blockIdx.y * wps + w] = (det & 0xffffu) | (hi << 16);
+    }
+}
+
+static inline size_t sync_fast_smem_bytes(int N)
+{
+    const int nch = (N >> 4) + SV_THREADS;
+    return (size_t)nch * 9 * 16 + 3 * (size_t)(nch + 1) * 4 + 16;
+}

@@ -2,6 +2,7 @@
 // entry point needs a CUDA device and reports OFDMX_ERR_CUDA otherwise.
 #include "ofdmx_kernels.cuh"
 #include "ofdmx_sync.cuh"
+#include "ofdmx_frame1024.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -9,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -53,7 +55,9 @@ struct ofdmx_ctx {
     // host-buffer path
     DevBuf h_samples, h_frames, h_bytes, h_counts;
     cudaStream_t own_stream = nullptr;
-    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0;
+    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0, frame1k_smem = 0;
+    bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
+    int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
 };
 
 namespace {
@@ -475,6 +479,19 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         }
     }
 
+    // reciprocals of the constellation points, position of each union carrier in each set's list
+    std::vector<float2> inv_hpts, inv_ppts;
+    for (auto &v : hpts) { std::complex<double> z = 1.0 / std::complex<double>(v.x, v.y); inv_hpts.push_back(make_float2((float)z.real(), (float)z.imag())); }
+    for (auto &v : ppts) { std::complex<double> z = 1.0 / std::complex<double>(v.x, v.y); inv_ppts.push_back(make_float2((float)z.real(), (float)z.imag())); }
+    std::vector<int> pos_su((size_t)prm->n_occ_sets * occ_u.size(), -1);
+    for (int s = 0; s < prm->n_occ_sets; s++)
+        for (int q = 0; q < occ_size[s]; q++) {
+            const int bin = occ_bins[occ_base[s] + q];
+            const int u = (int)(std::lower_bound(occ_u.begin(), occ_u.end(), bin) - occ_u.begin());
+            if (pos_su[(size_t)s * occ_u.size() + u] < 0) pos_su[(size_t)s * occ_u.size() + u] = q;
+        }
+    kp.max_frame_syms = payload_ofdm_syms(c, kp.max_pkt_syms);
+
 #define UP(vec, field)                                          \
     if ((rc = upload(c, vec, &kp.field)) != 0) return bail(rc);
     UP(tw, tw) UP(occ_bins, occ_bins) UP(occ_base, occ_base) UP(occ_size, occ_size) UP(occ_u, occ_u)
@@ -482,6 +499,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(pil_size, pil_size) UP(pil_sym, pil_sym) UP(pil_sym_base, pil_sym_base) UP(sw1, sw1) UP(sw2, sw2)
     UP(cv_k, cv_k) UP(cv_conj, cv_conj) UP(inv_sw2, inv_sw2) UP(hdr_mask, hdr_mask) UP(keystream, keystream)
     UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
+    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su)
 #undef UP
 
     // shared-memory budgets
@@ -491,6 +509,12 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         c->frame_smem = (size_t)N * 8 * 4 + 64 + N + align_up(c->hl, 16) + align_up(kp.max_pkt_syms, 16)
                         + align_up(kp.max_pkt_bytes, 16) + 16;
         c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16;
+        if (N == 1024) {
+            c->frame1k_warps = std::max(4, std::min(F1K_MAXW, 3 + kp.max_frame_syms));
+            c->frame1k_smem = frame1024_smem_bytes(c->frame1k_warps, kp.n_occ_u, c->hl, kp.max_pkt_syms, kp.max_pkt_bytes);
+            if (cudaFuncSetAttribute(rx_frame1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem) != cudaSuccess)
+                return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
+        }
         c->sync_fast_smem = sync_fast_smem_bytes(N);
         if (cudaFuncSetAttribute(sync_metric_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
             || cudaFuncSetAttribute(sync_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_smem) != cudaSuccess
@@ -499,6 +523,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s (is this an sm_100 device?)",
                              cudaGetErrorString(cudaGetLastError())));
     }
+    if (const char *fg = getenv("OFDMX_FORCE_GENERIC")) c->force_generic = (fg[0] == '1');
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
     *out = c;
@@ -603,9 +628,17 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     const float2 *smp = (const float2 *)samples_dev;
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
     ofdmx_ctx *ctx_ = c;
-    { KT(K_FRAME); rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
-        c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
-        byte_stride, (float2 *)z_out, z_stride); }
+    if (c->frame1k_warps > 0 && !c->force_generic) {
+        KT(K_FRAME);
+        rx_frame1024_kernel<<<c->sm_count * 2, c->frame1k_warps * 32, c->frame1k_smem, st>>>(
+            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
+            byte_stride, (float2 *)z_out, z_stride);
+    } else {
+        KT(K_FRAME);
+        rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
+            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
+            byte_stride, (float2 *)z_out, z_stride);
+    }
     { KT(K_CHAIN); chain_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(c->kp, n_samples, w.trig, w.spec, w.stream_start, w.jumpA, w.jumpB,
                                                        w.markA, w.markB, w.stream_count); }
     { KT(K_EMIT_SCAN); emit_scan_kernel<<<1, 1024, 0, st>>>(w.stream_count, n_streams, counts_dev); }

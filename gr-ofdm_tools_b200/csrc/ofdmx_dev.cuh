@@ -42,6 +42,10 @@ struct KP {
     const float2 *ppts;          // [2^bps_p] payload constellation points
     const uint8_t *lut_h;        // constellation_rect sector LUTs (QAM only)
     const uint8_t *lut_p;
+    const float2 *inv_hpts;      // 1 / constellation point
+    const float2 *inv_ppts;
+    const int *pos_su;           // [n_occ_sets][n_occ_u] position of union carrier u in set's list, or -1
+    int max_frame_syms;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -141,7 +145,7 @@ __device__ __forceinline__ uint32_t gf2_mul(uint32_t a, uint32_t b)
 }
 
 // CRC-32 of msg[0..len) held in shared (or global) memory; all threads of a 256-thread block call
-// it, the result is returned to every thread.  scratch: >= 9 uint32 in shared memory.
+// it (256..480 threads), the result is returned to every thread.  scratch: 16 uint32 in shared memory.
 // Method: the message is viewed as the tail of a 4096-byte zero-padded buffer cut into 256
 // 16-byte chunks; each thread computes the raw (zero-init) CRC register of its chunk and shifts it
 // by x^(8*bytes that follow); the XOR of all terms is the raw CRC.  The 0xFFFFFFFF initial value is
@@ -166,7 +170,7 @@ __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__r
         const int pad = 4096 - clen;                 // leading virtual zeros
         // thread's 16 bytes: virtual positions [tid*16, tid*16+16)
         uint32_t reg = 0;
-        for (int q = 0; q < 16; q++) {
+        for (int q = 0; q < 16 && tid < 256; q++) {
             int vp = tid * 16 + q - pad;
             if (vp < 0) continue;
             int gi = done + vp;
@@ -174,7 +178,7 @@ __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__r
             if (gi < 4) byte ^= 0xFF;                // init = 0xFFFFFFFF
             reg = __ldg(&tab[(reg ^ byte) & 0xFF]) ^ (reg >> 8);
         }
-        uint32_t term = reg ? gf2_mul(reg, __ldg(&powtab[tid])) : 0u;
+        uint32_t term = reg ? gf2_mul(reg, __ldg(&powtab[tid & 255])) : 0u;
         // XOR-reduce over the block
         for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
         __syncthreads();
@@ -190,10 +194,10 @@ __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__r
                 for (int i = 0; i < 128; i++) sh = gf2_mul_x(sh);
                 prev = gf2_mul(prev, sh);
             }
-            scratch[8] = prev ^ t;
+            scratch[15] = prev ^ t;
         }
         __syncthreads();
-        reg_total = scratch[8];
+        reg_total = scratch[15];
         done += clen;
     }
     return reg_total ^ 0xFFFFFFFFu;

@@ -1,0 +1,371 @@
+// ofdmx_frame1024.cuh -- K1+K3+K4 fast path for fft_len = 1024: one CTA per trigger, one WARP per
+// OFDM symbol.
+//
+//   * each warp pulls its symbol's 1024 samples straight from HBM into registers (32 per lane,
+//     coalesced 256-byte rows), derotates them with a phasor recurrence (the NCO of
+//     frequency_modulator_fc), and runs the 1024-point forward FFT entirely in registers as
+//     32 x 32: a generated straight-line 32-point FFT per lane, twiddles from a lane-contiguous
+//     shared table, one conflict-free shared-memory transpose, a second 32-point FFT;
+//   * all symbols of a frame are transformed concurrently by different warps (no barriers inside the
+//     FFT, only __syncwarp);
+//   * channel estimation, the decision-directed equaliser, demapping and serialisation then run
+//     carrier-parallel: a thread walks its carriers through every symbol of the round without any
+//     block barrier (carriers are independent in ofdm_equalizer_simpledfe);
+//   * bit packing, descrambling and the CRC-32 check finish the frame; only payload bytes and the
+//     32-byte record go back to HBM.
+#pragma once
+#include "ofdmx_kernels.cuh"
+#include "fft32_gen.cuh"
+
+#define F1K_MAXW 9
+#define F1K_ROW 34                      // float2 per transpose row (272 B: 16-byte aligned, conflict-free)
+#define F1K_SLOT (32 * F1K_ROW)         // float2 per warp buffer (>= 1024)
+
+// One symbol: load + derotate + 1024-point FFT.  Result: Tw[k] = X[k], natural order, k < 1024.
+__device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict__ r, long long n, long long i0,
+                                           long long t, double kappa, bool slow, int j, int jend,
+                                           const long long *__restrict__ trig, const float *__restrict__ cfo,
+                                           float2 *__restrict__ Tw, const float2 *__restrict__ tws, int lane)
+{
+    float2 v[32];
+    const long long sbase = i0 - p.D + lane;          // stream index of this lane's first sample
+    if (sbase - lane >= 0 && sbase - lane + 1024 <= n) {
+#pragma unroll
+        for (int a = 0; a < 32; a++) v[a] = __ldg(&r[sbase + 32 * a]);
+    } else {
+#pragma unroll
+        for (int a = 0; a < 32; a++) {
+            const long long s = sbase + 32 * a;
+            v[a] = (s >= 0 && s < n) ? __ldg(&r[s]) : make_float2(0.f, 0.f);
+        }
+    }
+    if (!slow) {
+        // phase(i) = 2 pi kappa (i - t + 1); phasor recurrence over a (step = 32 samples)
+        double tb = kappa * (double)(i0 + lane - t + 1);
+        tb -= rint(tb);
+        double tsd = kappa * 32.0;
+        tsd -= rint(tsd);
+        float sn, cs, ssn, scs;
+        sincospif(2.0f * (float)tb, &sn, &cs);
+        sincospif(2.0f * (float)tsd, &ssn, &scs);
+        float2 ph = make_float2(cs, sn);
+        const float2 st = make_float2(scs, ssn);
+#pragma unroll
+        for (int a = 0; a < 32; a++) {
+            v[a] = cmul(v[a], ph);
+            ph = cmul(ph, st);
+        }
+    } else {
+        // another raw trigger falls inside this symbol: the sample-and-hold value changes mid-symbol
+#pragma unroll
+        for (int a = 0; a < 32; a++) {
+            double turns = nco_turns(i0 + lane + 32 * a, j, jend, trig, cfo, 1024);
+            turns -= rint(turns);
+            float sn, cs;
+            sincospif(2.0f * (float)turns, &sn, &cs);
+            v[a] = cmul(v[a], make_float2(cs, sn));
+        }
+    }
+    // n = 32 a + b (b = lane):  y_b[k1] = sum_a x[32 a + b] W32^(a k1)
+    fft32_fwd(v);
+    // z_b[k1] = y_b[k1] W1024^(b k1), stored transposed: row k1, column b
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const int k1 = brev5(q);
+        Tw[k1 * F1K_ROW + lane] = cmul(v[q], tws[k1 * 32 + lane]);
+    }
+    __syncwarp();
+    // lane = k1 now owns row k1:  X[k1 + 32 k2] = sum_b z_b[k1] W32^(b k2)
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const float4 t4 = *reinterpret_cast<const float4 *>(&Tw[lane * F1K_ROW + 2 * q]);
+        v[2 * q] = make_float2(t4.x, t4.y);
+        v[2 * q + 1] = make_float2(t4.z, t4.w);
+    }
+    __syncwarp();
+    fft32_fwd(v);
+#pragma unroll
+    for (int q = 0; q < 32; q++) Tw[lane + 32 * brev5(q)] = v[q];
+}
+
+__global__ void __launch_bounds__(F1K_MAXW * 32, 2)
+rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
+                    const long long *__restrict__ trig, const int *__restrict__ trig_stream,
+                    const float *__restrict__ cfo, const int *__restrict__ stream_start,
+                    const int *__restrict__ n_trig_dev, ofdmx_frame *__restrict__ spec,
+                    uint8_t *__restrict__ bytes_out, long long byte_stride, float2 *__restrict__ z_out,
+                    long long z_stride)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, W = blockDim.x >> 5, NT = blockDim.x;
+    float2 *T = reinterpret_cast<float2 *>(smem_raw);          // W warp buffers
+    float2 *tws = T + W * F1K_SLOT;                            // [k1*32 + b]
+    float2 *Hs = tws + 1024;                                   // [n_occ_u]
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(Hs + p.n_occ_u);
+    uint8_t *hb = reinterpret_cast<uint8_t *>(scratch + 16);
+    uint8_t *syms = hb + ((p.hl + 15) & ~15);
+    uint8_t *pk = syms + ((p.max_pkt_syms + 15) & ~15);
+    __shared__ float wbest[F1K_MAXW];
+    __shared__ int wbestg[F1K_MAXW];
+    __shared__ int s_off, s_ok, s_plen, s_pnum, s_psyms, s_fsyms;
+    __shared__ float2 pcs[F1K_MAXW];
+
+    for (int i = tid; i < 1024; i += NT) {
+        const int k1 = i >> 5, b = i & 31;
+        float sn, cs;
+        sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
+        tws[i] = make_float2(cs, sn);
+    }
+    const int nt = *n_trig_dev;
+    const int N = 1024, D = p.D;
+    const bool want_z = (z_out != nullptr);
+    const float al = p.alpha, oma = 1.0f - p.alpha;
+
+    for (int j = blockIdx.x; j < nt; j += gridDim.x) {
+        __syncthreads();
+        const int st = trig_stream[j];
+        const long long t = trig[j];
+        const float2 *r = samples + (long long)st * stride;
+        const int jend = stream_start[st + 1];
+        ofdmx_frame rec;
+        rec.trigger = t; rec.cfo = cfo[j]; rec.stream = st; rec.flags = 0; rec.pkt_len = 0; rec.pkt_num = 0;
+        rec.frame_syms = 0; rec.carr_offset = 0; rec.slot = (uint32_t)j;
+        if (t + 3LL * D > n) {
+            if (tid == 0) spec[j] = rec;
+            continue;
+        }
+        const long long tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
+        const double kappa = (double)rec.cfo * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+        const long long fit = (n - t) / D;                       // whole symbols available from the trigger
+        // ---- round 0: symbols 0 .. min(W, fit) - 1, one per warp
+        if (wid < fit) {
+            const long long i0 = t + (long long)wid * D + p.cp;
+            f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
+        }
+        __syncthreads();
+        const float2 *Y1 = T, *Y2 = T + F1K_SLOT, *Y3 = T + 2 * F1K_SLOT;
+        // ---- ofdm_chanest_vcvc: integer carrier offset
+        {
+            float best = 0.f;
+            int bestg = 0;
+            const int ng = (p.gpos - p.gneg) / 2 + 1;
+            for (int gi = wid; gi < ng; gi += W) {
+                const int g = p.gneg + 2 * gi;
+                float2 acc = make_float2(0.f, 0.f);
+                for (int c = lane; c < p.n_cv; c += 32) {
+                    const int k = p.cv_k[c] + g;
+                    const float2 t1 = cmul_conj(ysh(Y2, k, N), ysh(Y1, k, N));
+                    acc = cadd(acc, cmul(t1, p.cv_conj[c]));
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                }
+                const float v = acc.x * acc.x + acc.y * acc.y;
+                if (v > best) { best = v; bestg = g; }
+            }
+            if (lane == 0) { wbest[wid] = best; wbestg[wid] = bestg; }
+            __syncthreads();
+            if (tid == 0) {
+                float b = 0.f;
+                int g = 0;
+                for (int w = 0; w < W; w++) {
+                    const float v = wbest[w];
+                    if (v > b || (v == b && v > 0.f && wbestg[w] < g)) { b = v; g = wbestg[w]; }
+                }
+                s_off = g;
+            }
+            __syncthreads();
+        }
+        const int off = s_off;
+        // ---- taps + header symbol (ofdm_frame_equalizer_vcvc + simpledfe, BPSK header, symbol 0)
+        {
+            float2 pc = make_float2(1.f, 0.f);
+            if (off != 0) {
+                float sn, cs;
+                sincosf((float)(-TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                pc = make_float2(cs, sn);
+            }
+            float2 rot = make_float2(1.f, 0.f);       // channel state handed to the payload equaliser
+            if (off != 0) {
+                float sn, cs;
+                sincosf((float)(TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                rot = make_float2(cs, sn);
+            }
+            const int b0 = 0;                          // header uses carrier set 0
+            for (int u = tid; u < p.n_occ_u; u += NT) {
+                const int k = p.occ_u[u];
+                const int src = k + off;
+                float2 Hk = make_float2(0.f, 0.f), y = make_float2(0.f, 0.f);
+                if (src >= 0 && src < N) {
+                    Hk = cmul(ysh(Y2, src, N), p.inv_sw2[k]);
+                    y = cmul(ysh(Y3, src, N), pc);
+                }
+                int d;
+                float2 z = make_float2(0.f, 0.f);
+                if (p.n_pil_sets && p.pil_flag[k]) {
+                    const float2 pv = p.pil_val[k];
+                    const float2 q = cdivf(y, pv);
+                    Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
+                    d = ofdm_decide(p.bps_h, pv.x, pv.y, p.lut_h);
+                } else {
+                    z = cdivf(y, Hk);
+                    d = ofdm_decide(p.bps_h, z.x, z.y, p.lut_h);
+                    const float2 q = cmul(y, p.inv_hpts[d]);
+                    Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
+                }
+                const int pos = p.pos_su[b0 * p.n_occ_u + u];
+                if (pos >= 0) {
+                    hb[pos] = (uint8_t)d ^ p.hdr_mask[pos];
+                    if (want_z) z_out[(long long)j * z_stride + pos] = z;
+                }
+                Hs[u] = cmul(Hk, rot);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int bpb = p.bps_h, msk = (1 << bpb) - 1;
+            unsigned len = 0, num = 0;
+            int k = 0, ok = 1;
+            for (int i = 0; i < 12 && k < p.hl; i += bpb, k++) len |= ((unsigned)(hb[k] & msk)) << i;
+            if (k < p.hl) {
+                for (int i = 0; i < 12 && k < p.hl; i += bpb, k++) num |= ((unsigned)(hb[k] & msk)) << i;
+                if (k < p.hl) {
+                    const uint8_t crc = crc8_hdr(len, num);
+                    for (int i = 0; i < 8 && k < p.hl; i += bpb, k++)
+                        if ((hb[k] & msk) != ((crc >> i) & msk)) ok = 0;
+                }
+            }
+            int ps = (int)len * 8 / p.bps_p;
+            if (((int)len * 8) % p.bps_p) ps++;
+            int fl = 0, acc = 0, s = 0;
+            while (acc < ps) { fl++; acc += p.occ_size[s]; s = (s + 1) % p.n_occ_sets; }
+            s_ok = ok; s_plen = (int)len; s_pnum = (int)num; s_psyms = ps; s_fsyms = fl;
+        }
+        __syncthreads();
+        rec.flags = OFDMX_F_HDR_SEEN;
+        rec.carr_offset = (int16_t)off;
+        rec.pkt_len = (uint16_t)s_plen;
+        rec.pkt_num = (uint16_t)s_pnum;
+        const int fsyms = s_fsyms, psyms = s_psyms;
+        rec.frame_syms = (uint16_t)fsyms;
+        if (!s_ok) {
+            if (tid == 0) spec[j] = rec;
+            continue;
+        }
+        rec.flags |= OFDMX_F_HDR_OK;
+        if (t + (long long)(3 + fsyms) * D > n || s_plen > p.max_pkt_bytes) {
+            if (tid == 0) spec[j] = rec;
+            continue;
+        }
+        rec.flags |= OFDMX_F_COMPLETE;
+
+        // ---- payload: rounds of up to W symbols; round 0 already holds payload symbols 0 .. W-4
+        int cbase = 0;                                // serialised symbols before payload symbol `first`
+        int first = 0;                                // first payload symbol of this round
+        int slot0 = 3;                                // warp buffer holding payload symbol `first`
+        int in_round = min(fsyms, W - 3);
+        for (;;) {
+            if (off != 0) {   // per-symbol phase fix exp(-j 2 pi off cp / N (i+1)) of ofdm_frame_equalizer_vcvc
+                if (tid < in_round) {
+                    float sn, cs;
+                    sincosf((float)(-TWO_PI_D * off * p.cp / N * (first + tid + 1)), &sn, &cs);
+                    pcs[tid] = make_float2(cs, sn);
+                }
+                __syncthreads();
+            }
+            // carrier-parallel DFE over the symbols of this round (no barriers: carriers are independent)
+            for (int u = tid; u < p.n_occ_u; u += NT) {
+                const int k = p.occ_u[u];
+                const int src = k + off;
+                float2 Hk = Hs[u];
+                int cb = cbase;
+                for (int ii = 0; ii < in_round; ii++) {
+                    const int i = first + ii;
+                    const float2 *Y = T + (slot0 + ii) * F1K_SLOT;
+                    const int set = (1 + i) % p.n_occ_sets;
+                    const int pset = p.n_pil_sets ? (1 + i) % p.n_pil_sets : 0;
+                    float2 y = make_float2(0.f, 0.f);
+                    if (src >= 0 && src < N) {
+                        y = ysh(Y, src, N);
+                        if (off != 0) y = cmul(y, pcs[ii]);
+                    }
+                    int d;
+                    float2 z = make_float2(0.f, 0.f);
+                    if (p.n_pil_sets && p.pil_flag[pset * N + k]) {
+                        const float2 pv = p.pil_val[pset * N + k];
+                        const float2 q = cdivf(y, pv);
+                        Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
+                        d = ofdm_decide(p.bps_p, pv.x, pv.y, p.lut_p);
+                    } else {
+                        z = cdivf(y, Hk);
+                        d = ofdm_decide(p.bps_p, z.x, z.y, p.lut_p);
+                        const float2 q = cmul(y, p.inv_ppts[d]);
+                        Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
+                    }
+                    const int pos = p.pos_su[set * p.n_occ_u + u];
+                    if (pos >= 0) {
+                        const int idx = cb + pos;
+                        if (idx < psyms) {
+                            syms[idx] = (uint8_t)d;
+                            if (want_z && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
+                        }
+                    }
+                    cb += p.occ_size[set];
+                }
+                Hs[u] = Hk;
+            }
+            for (int ii = 0; ii < in_round; ii++) cbase += p.occ_size[(1 + first + ii) % p.n_occ_sets];
+            first += in_round;
+            if (first >= fsyms) break;
+            // next round: transform the next W payload symbols
+            __syncthreads();
+            in_round = min(fsyms - first, W);
+            slot0 = 0;
+            if (wid < in_round) {
+                const long long i0 = t + (long long)(3 + first + wid) * D + p.cp;
+                f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        const int cnt = min(cbase, psyms);
+        // ---- repack_bits_bb(bps, 8, key, True) + additive_scrambler_bb
+        const int nbytes = min(cnt * p.bps_p / 8, p.max_pkt_bytes);
+        for (int mb = tid; mb < nbytes; mb += NT) {
+            unsigned v = 0;
+            if (p.bps_p == 4) {
+                v = (unsigned)syms[2 * mb] | ((unsigned)syms[2 * mb + 1] << 4);
+            } else {
+                for (int b = 0; b < 8; b++) {
+                    const int bi = mb * 8 + b;
+                    const int si = bi / p.bps_p, sb = bi - si * p.bps_p;
+                    v |= ((unsigned)(syms[si] >> sb) & 1u) << b;
+                }
+            }
+            const uint8_t o = (uint8_t)v ^ p.keystream[mb];
+            pk[mb] = o;
+            bytes_out[(long long)j * byte_stride + mb] = o;
+        }
+        __syncthreads();
+        bool crc_ok = true;
+        if (p.crc_mode) {
+            if (nbytes < 4) crc_ok = false;
+            else {
+                const uint32_t c = crc32_block(pk, nbytes - 4, p.crc_tab, p.crc_pow, scratch);
+                const uint32_t got = (uint32_t)pk[nbytes - 4] | ((uint32_t)pk[nbytes - 3] << 8)
+                                     | ((uint32_t)pk[nbytes - 2] << 16) | ((uint32_t)pk[nbytes - 1] << 24);
+                crc_ok = (c == got);
+            }
+        }
+        if (crc_ok) rec.flags |= OFDMX_F_CRC_OK;
+        if (tid == 0) spec[j] = rec;
+    }
+}
+
+static inline size_t frame1024_smem_bytes(int W, int n_occ_u, int hl, int max_pkt_syms, int max_pkt_bytes)
+{
+    auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    return (size_t)W * F1K_SLOT * 8 + 1024 * 8 + al16((size_t)n_occ_u * 8) + 64 + al16(hl) + al16(max_pkt_syms)
+           + al16(max_pkt_bytes) + 32;
+}

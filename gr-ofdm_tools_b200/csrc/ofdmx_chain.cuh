@@ -1,0 +1,177 @@
+// ofdmx_chain.cuh -- header_payload_demux acceptance chain over the speculative per-trigger records.
+//
+// The demux is a sequential state machine: after examining trigger i it resumes its
+// search at an item index that depends on i's header (failed: t+1; decoded: after the payload), and
+// ignores every trigger before that.  With next[i] = first trigger at or after the resume point
+// (or the first trigger of the next stream when the demux stalls / the stream ends), the examined
+// triggers of ALL streams are the orbit of trigger 0 under next.  next[i] > i, so the orbit is found
+// block-wise:
+//   chain_next_kernel   per block of 4096 triggers: next[] and, by in-shared pointer jumping,
+//                       exit[i] = first node >= block end on i's path
+//   chain_entry_kernel  walk exit[] from trigger 0: <= one entry node per block (short serial walk)
+//   chain_mark_kernel   per block: exact pointer doubling in shared memory from the entry node ->
+//                       examined marks; emit flag = examined && header ok && frame complete
+//   chain_scan_kernel / chain_emit_kernel   ordered compaction of the emitted records
+#pragma once
+#include "ofdmx_dev.cuh"
+#include "ofdmx.h"
+
+#define CH_B 4096
+#define CH_T 1024
+
+__global__ void __launch_bounds__(CH_T)
+chain_next_kernel(const KP p, const long long *__restrict__ trig, const int *__restrict__ trig_stream,
+                  const ofdmx_frame *__restrict__ spec, const int *__restrict__ stream_start,
+                  const int *__restrict__ n_trig_dev, int *__restrict__ nxt, int *__restrict__ exitp)
+{
+    __shared__ int e[CH_B];
+    const int nt = *n_trig_dev;
+    const int base = blockIdx.x * CH_B;
+    if (base >= nt) return;
+    const int end = min(base + CH_B, nt), cnt = end - base;
+    for (int li = threadIdx.x; li < cnt; li += CH_T) {
+        const int i = base + li;
+        const ofdmx_frame f = spec[i];
+        const int b = stream_start[trig_stream[i] + 1];          // first trigger of the next stream
+        long long resume = 0;
+        int nx = -1;
+        if (!(f.flags & OFDMX_F_HDR_SEEN)) nx = b;                // demux stalls waiting for the header
+        else if (!(f.flags & OFDMX_F_HDR_OK)) resume = f.trigger + 1;   // header CRC failed
+        else if (!(f.flags & OFDMX_F_COMPLETE)) nx = b;           // demux stalls waiting for the payload
+        else
+            resume = (f.frame_syms > 0) ? f.trigger + (long long)(3 + f.frame_syms) * p.D - p.holdoff
+                                        : f.trigger + 3LL * p.D;
+        if (nx < 0) {
+            int lo = i + 1, hi = b;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (trig[mid] < resume) lo = mid + 1; else hi = mid;
+            }
+            nx = lo;
+        }
+        nxt[i] = nx;
+        e[li] = nx;
+    }
+    __syncthreads();
+    for (int round = 0; round < 12; round++) {                    // 2^12 = CH_B
+        int moved = 0;
+        for (int li = threadIdx.x; li < cnt; li += CH_T) {
+            const int v = e[li];
+            if (v < end) { e[li] = e[v - base]; moved = 1; }
+        }
+        if (!__syncthreads_or(moved)) break;
+    }
+    for (int li = threadIdx.x; li < cnt; li += CH_T) exitp[base + li] = e[li];
+}
+
+__global__ void chain_entry_kernel(const int *__restrict__ n_trig_dev, const int *__restrict__ exitp,
+                                   int *__restrict__ entry, int nblk)
+{
+    for (int g = threadIdx.x; g < nblk; g += blockDim.x) entry[g] = -1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nt = *n_trig_dev;
+        int cur = 0;
+        while (cur < nt) {
+            entry[cur / CH_B] = cur;
+            cur = exitp[cur];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CH_T)
+chain_mark_kernel(const ofdmx_frame *__restrict__ spec, const int *__restrict__ n_trig_dev,
+                  const int *__restrict__ nxt, const int *__restrict__ entry, uint8_t *__restrict__ emitflag,
+                  int *__restrict__ blockcount)
+{
+    __shared__ int jA[CH_B], jB[CH_B];
+    __shared__ uint8_t mA[CH_B], mB[CH_B];
+    __shared__ int wt[33];
+    const int nt = *n_trig_dev;
+    const int base = blockIdx.x * CH_B;
+    if (base >= nt) {
+        if (threadIdx.x == 0) blockcount[blockIdx.x] = 0;
+        return;
+    }
+    const int end = min(base + CH_B, nt), cnt = end - base;
+    const int ent = entry[blockIdx.x];
+    for (int li = threadIdx.x; li < cnt; li += CH_T) {
+        const int nx = nxt[base + li];
+        jA[li] = (nx < end) ? nx - base : CH_B;
+        mA[li] = (base + li == ent) ? 1 : 0;
+    }
+    __syncthreads();
+    int *jc = jA, *jn = jB;
+    uint8_t *mc = mA, *mn = mB;
+    if (ent >= 0) {
+        for (int span = 1; span < cnt; span <<= 1) {
+            for (int li = threadIdx.x; li < cnt; li += CH_T) mn[li] = mc[li];
+            __syncthreads();
+            for (int li = threadIdx.x; li < cnt; li += CH_T) {
+                const int jx = jc[li];
+                if (jx < cnt) {
+                    if (mc[li]) mn[jx] = 1;
+                    jn[li] = jc[jx];
+                } else {
+                    jn[li] = CH_B;
+                }
+            }
+            __syncthreads();
+            int *tj = jc; jc = jn; jn = tj;
+            uint8_t *tm = mc; mc = mn; mn = tm;
+        }
+    }
+    int local = 0;
+    for (int li = threadIdx.x; li < cnt; li += CH_T) {
+        const unsigned fl = spec[base + li].flags;
+        const uint8_t em = (mc[li] && (fl & OFDMX_F_HDR_OK) && (fl & OFDMX_F_COMPLETE)) ? 1 : 0;
+        emitflag[base + li] = em;
+        local += em;
+    }
+    int total;
+    block_excl_scan(local, wt, total);
+    if (threadIdx.x == 0) blockcount[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+chain_scan_kernel(int *__restrict__ blockcount, int nblk, ofdmx_counts *__restrict__ counts)
+{
+    __shared__ int wt[33];
+    int carry = 0;
+    for (int b0 = 0; b0 < nblk; b0 += 1024) {
+        const int idx = b0 + threadIdx.x;
+        const int v = (idx < nblk) ? blockcount[idx] : 0;
+        int total;
+        const int ex = block_excl_scan(v, wt, total);
+        if (idx < nblk) blockcount[idx] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts->n_frames = carry;
+}
+
+__global__ void __launch_bounds__(CH_T)
+chain_emit_kernel(const ofdmx_frame *__restrict__ spec, const int *__restrict__ n_trig_dev,
+                  const uint8_t *__restrict__ emitflag, const int *__restrict__ blockbase,
+                  ofdmx_frame *__restrict__ frames_out)
+{
+    __shared__ int wt[33];
+    const int nt = *n_trig_dev;
+    const int base = blockIdx.x * CH_B;
+    if (base >= nt) return;
+    const int end = min(base + CH_B, nt);
+    int carry = blockbase[blockIdx.x];
+    for (int i0 = base; i0 < end; i0 += CH_T) {
+        const int i = i0 + threadIdx.x;
+        const int em = (i < end) ? emitflag[i] : 0;
+        int total;
+        const int ex = block_excl_scan(em, wt, total);
+        if (em) {
+            ofdmx_frame f = spec[i];
+            f.flags |= OFDMX_F_ACCEPTED;
+            frames_out[carry + ex] = f;
+        }
+        carry += total;
+        __syncthreads();
+    }
+}

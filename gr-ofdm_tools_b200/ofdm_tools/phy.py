@@ -225,33 +225,51 @@ class OfdmPhy(object):
         return out[:cap], soff
 
     # ------------------------------------------------------------------ RX
-    def rx(self, samples, max_frames=None, want_z=False, max_pkt_syms=None):
-        """samples: complex64 cuda tensor [n] or [n_streams, n].  Returns RxResult (synchronises)."""
+    def default_max_frames(self, n_streams, n):
+        return int(n_streams * (n // (3 * (self.fft_len + self.cp_len)) + 4))
+
+    def rx_buffers(self, max_frames, device, want_z=False, max_pkt_syms=None):
+        """Pre-allocated output buffers for rx_enqueue (reusable across calls)."""
+        torch = self._torch()
+        b = {"max_frames": int(max_frames),
+             "frames": torch.empty(max_frames * 32, dtype=torch.uint8, device=device),
+             "slots": torch.empty((max_frames, self.byte_stride), dtype=torch.uint8, device=device),
+             "counts": torch.zeros(4, dtype=torch.int32, device=device), "z": None, "zs": 0}
+        if want_z:
+            b["zs"] = self.header_len() + (max_pkt_syms or (self.max_pkt_bytes * 8 // self.bps_payload + 1))
+            b["z"] = torch.zeros((max_frames, b["zs"]), dtype=torch.complex64, device=device)
+        return b
+
+    def rx_enqueue(self, samples, bufs):
+        """Launch the RX chain on the current stream; no host synchronisation."""
         torch = self._torch()
         s = samples if samples.dim() == 2 else samples.unsqueeze(0)
         assert s.dtype == torch.complex64 and s.is_cuda and s.stride(1) == 1
         n_streams, n = s.shape
-        D = self.fft_len + self.cp_len
-        if max_frames is None:
-            max_frames = int(n_streams * (n // (3 * D) + 4))
-        dev = s.device
-        frames = torch.empty(max_frames * 32, dtype=torch.uint8, device=dev)
-        slots = torch.empty((max_frames, self.byte_stride), dtype=torch.uint8, device=dev)
-        counts = torch.zeros(4, dtype=torch.int32, device=dev)
-        z, zs = None, 0
-        if want_z:
-            zs = self.header_len() + (max_pkt_syms or (self.max_pkt_bytes * 8 // self.bps_payload + 1))
-            z = torch.zeros((max_frames, zs), dtype=torch.complex64, device=dev)
+        z = bufs["z"]
         _lib.check(_lib.load().ofdmx_rx(
-            self.ctx, s.data_ptr(), n_streams, n, s.stride(0), frames.data_ptr(), max_frames,
-            slots.data_ptr(), self.byte_stride, z.data_ptr() if want_z else None, zs,
-            counts.data_ptr(), self._stream()), self.ctx)
-        c = counts.cpu().numpy()
+            self.ctx, s.data_ptr(), n_streams, n, s.stride(0), bufs["frames"].data_ptr(), bufs["max_frames"],
+            bufs["slots"].data_ptr(), self.byte_stride, z.data_ptr() if z is not None else None, bufs["zs"],
+            bufs["counts"].data_ptr(), self._stream()), self.ctx)
+
+    def rx_collect(self, bufs):
+        """Synchronise and read the records of the last rx_enqueue on these buffers."""
+        c = bufs["counts"].cpu().numpy()
         if c[2]:
-            raise BufferError("more triggers (%d) than max_frames (%d)" % (c[0], max_frames))
+            raise BufferError("more triggers (%d) than max_frames (%d)" % (c[0], bufs["max_frames"]))
         nf = int(c[1])
-        rec = np.frombuffer(frames[: nf * 32].cpu().numpy().tobytes(), FRAME_DTYPE).copy()
-        return RxResult(rec, slots, c, z, self.crc_mode, int(c[0]))
+        rec = np.frombuffer(bufs["frames"][: nf * 32].cpu().numpy().tobytes(), FRAME_DTYPE).copy()
+        return RxResult(rec, bufs["slots"], c, bufs["z"], self.crc_mode, int(c[0]))
+
+    def rx(self, samples, max_frames=None, want_z=False, max_pkt_syms=None):
+        """samples: complex64 cuda tensor [n] or [n_streams, n].  Returns RxResult (synchronises)."""
+        s = samples if samples.dim() == 2 else samples.unsqueeze(0)
+        n_streams, n = s.shape
+        if max_frames is None:
+            max_frames = self.default_max_frames(n_streams, n)
+        bufs = self.rx_buffers(max_frames, s.device, want_z, max_pkt_syms)
+        self.rx_enqueue(s, bufs)
+        return self.rx_collect(bufs)
 
     def rx_host(self, samples, max_frames=None):
         """Same through ofdmx_rx_host: numpy complex64 in, numpy out (H2D/D2H inside the call)."""

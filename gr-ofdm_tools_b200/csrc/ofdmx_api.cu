@@ -496,6 +496,10 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             if (pos_su[(size_t)s * occ_u.size() + u] < 0) pos_su[(size_t)s * occ_u.size() + u] = q;
         }
     kp.max_frame_syms = payload_ofdm_syms(c, kp.max_pkt_syms);
+    kp.pil_in_occ = 0;
+    for (int ps = 0; ps < prm->n_pilot_sets; ps++)
+        for (int k = 0; k < N; k++)
+            if (pil_flag[(size_t)ps * N + k] && occ_mask[k]) kp.pil_in_occ = 1;
 
 #define UP(vec, field)                                          \
     if ((rc = upload(c, vec, &kp.field)) != 0) return bail(rc);
@@ -517,8 +521,16 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         if (N == 1024) {
             c->frame1k_warps = std::max(4, std::min(F1K_MAXW, 3 + kp.max_frame_syms));
             c->frame1k_smem = frame1024_smem_bytes(c->frame1k_warps, kp.n_occ_u, c->hl, kp.max_pkt_syms, kp.max_pkt_bytes);
-            if (cudaFuncSetAttribute(rx_frame1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem) != cudaSuccess)
-                return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
+            cudaError_t e1 = cudaSuccess;
+            switch (kp.bps_p) {
+            case 1: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
+            case 2: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
+            case 3: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
+            case 4: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
+            default: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
+            }
+            if (e1 != cudaSuccess)
+                return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(e1)));
         }
         c->sync_fast_smem = sync_fast_smem_bytes(N);
         if (cudaFuncSetAttribute(sync_metric_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
@@ -635,9 +647,18 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     ofdmx_ctx *ctx_ = c;
     if (c->frame1k_warps > 0 && !c->force_generic) {
         KT(K_FRAME);
-        rx_frame1024_kernel<<<c->sm_count * 2, c->frame1k_warps * 32, c->frame1k_smem, st>>>(
-            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
-            byte_stride, (float2 *)z_out, z_stride);
+#define F1K_LAUNCH(B)                                                                                              \
+    rx_frame1024_kernel<B><<<c->sm_count * 2, F1K_THREADS, c->frame1k_smem, st>>>(                                 \
+        c->kp, c->frame1k_warps, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig,   \
+        w.spec, bytes_out, byte_stride, (float2 *)z_out, z_stride)
+        switch (c->kp.bps_p) {
+        case 1: F1K_LAUNCH(1); break;
+        case 2: F1K_LAUNCH(2); break;
+        case 3: F1K_LAUNCH(3); break;
+        case 4: F1K_LAUNCH(4); break;
+        default: F1K_LAUNCH(6); break;
+        }
+#undef F1K_LAUNCH
     } else {
         KT(K_FRAME);
         rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(

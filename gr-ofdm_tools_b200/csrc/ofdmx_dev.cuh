@@ -46,6 +46,7 @@ struct KP {
     const float2 *inv_ppts;
     const int *pos_su;           // [n_occ_sets][n_occ_u] position of union carrier u in set's list, or -1
     int max_frame_syms;
+    int pil_in_occ;              // some pilot carrier is also in occupied_carriers (equaliser pilot branch reachable)
 };
 
 // ---------------------------------------------------------------------------------------------

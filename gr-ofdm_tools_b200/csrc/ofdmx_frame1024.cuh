@@ -88,8 +88,39 @@ __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict
     for (int q = 0; q < 32; q++) Tw[lane + 32 * brev5(q)] = v[q];
 }
 
-__global__ void __launch_bounds__(F1K_MAXW * 32, 2)
-rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
+// decision_maker with the modulation known at compile time
+template <int BPS>
+__device__ __forceinline__ int f1k_decide(float re, float im, const uint8_t *__restrict__ lut)
+{
+    if (BPS == 1) return re > 0.f;
+    if (BPS == 2) return 2 * (im > 0.f) + (re > 0.f);
+    if (BPS == 3) {
+        int r = (fabsf(re) <= fabsf(im)) ? 4 : 0;
+        if (re <= 0.f) r |= 1;
+        if (im <= 0.f) r |= 2;
+        return r;
+    }
+    constexpr int side = (BPS == 4) ? 4 : 8;
+    constexpr float inv_w = 0.5f * (float)(side - 1), half = 0.5f * (float)side;
+    int rs = __float2int_rz(fmaf(re, inv_w, half));
+    int is = __float2int_rz(fmaf(im, inv_w, half));
+    rs = min(max(rs, 0), side - 1);
+    is = min(max(is, 0), side - 1);
+    return lut[rs * side + is];
+}
+
+__device__ __forceinline__ float f1k_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+#define F1K_THREADS 320
+
+template <int BPS_P>
+__global__ void __launch_bounds__(F1K_THREADS, 2)
+rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples, long long n, long long stride,
                     const long long *__restrict__ trig, const int *__restrict__ trig_stream,
                     const float *__restrict__ cfo, const int *__restrict__ stream_start,
                     const int *__restrict__ n_trig_dev, ofdmx_frame *__restrict__ spec,
@@ -97,16 +128,19 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
                     long long z_stride)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, W = blockDim.x >> 5, NT = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = blockDim.x, NW = blockDim.x >> 5;
     float2 *T = reinterpret_cast<float2 *>(smem_raw);          // W warp buffers
     float2 *tws = T + W * F1K_SLOT;                            // [k1*32 + b]
     float2 *Hs = tws + 1024;                                   // [n_occ_u]
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(Hs + p.n_occ_u);
-    uint8_t *hb = reinterpret_cast<uint8_t *>(scratch + 16);
+    float2 *ipts = Hs + p.n_occ_u;                             // [64] 1 / payload constellation point
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(ipts + 64);
+    uint8_t *lut = reinterpret_cast<uint8_t *>(scratch + 16);  // [64] payload sector LUT
+    uint8_t *hb = lut + 64;
     uint8_t *syms = hb + ((p.hl + 15) & ~15);
     uint8_t *pk = syms + ((p.max_pkt_syms + 15) & ~15);
-    __shared__ float wbest[F1K_MAXW];
-    __shared__ int wbestg[F1K_MAXW];
+    __shared__ float2 wacc[F1K_THREADS / 32][4];
+    __shared__ float wbest[F1K_THREADS / 32];
+    __shared__ int wbestg[F1K_THREADS / 32];
     __shared__ int s_off, s_ok, s_plen, s_pnum, s_psyms, s_fsyms;
     __shared__ float2 pcs[F1K_MAXW];
 
@@ -116,10 +150,17 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
         sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
         tws[i] = make_float2(cs, sn);
     }
+    if (tid < 64) {
+        lut[tid] = p.lut_p[tid];
+        ipts[tid] = (tid < (1 << BPS_P)) ? p.inv_ppts[tid] : make_float2(0.f, 0.f);
+    }
     const int nt = *n_trig_dev;
     const int N = 1024, D = p.D;
     const bool want_z = (z_out != nullptr);
     const float al = p.alpha, oma = 1.0f - p.alpha;
+    const bool one_set = (p.n_occ_sets == 1);
+    const bool pil_occ = (p.pil_in_occ != 0);
+    const int size0 = p.occ_size[0];
 
     for (int j = blockIdx.x; j < nt; j += gridDim.x) {
         __syncthreads();
@@ -136,20 +177,58 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
         }
         const long long tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
         const double kappa = (double)rec.cfo * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
-        const long long fit = (n - t) / D;                       // whole symbols available from the trigger
-        // ---- round 0: symbols 0 .. min(W, fit) - 1, one per warp
-        if (wid < fit) {
+        const long long rem = n - t;
+        // ---- round 0: symbols 0 .. W-1 (those that fit in the buffer), one per warp
+        if (wid < W && (long long)(wid + 1) * D <= rem) {
             const long long i0 = t + (long long)wid * D + p.cp;
             f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
         }
         __syncthreads();
         const float2 *Y1 = T, *Y2 = T + F1K_SLOT, *Y3 = T + 2 * F1K_SLOT;
-        // ---- ofdm_chanest_vcvc: integer carrier offset
-        {
+        // ---- ofdm_chanest_vcvc: integer carrier offset, B(g) = |sum_k conj(Y1[k+g]) conj(cv[k]) Y2[k+g]|
+        const int ng = (p.gpos - p.gneg) / 2 + 1;
+        if (ng <= 4) {
+            // few candidates (max_carr_offset given): every thread takes one cv term for all candidates
+            float2 acc[4];
+#pragma unroll
+            for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
+            for (int c = tid; c < p.n_cv; c += NT) {
+                const int kc = p.cv_k[c];
+                const float2 cvc = p.cv_conj[c];
+#pragma unroll
+                for (int gi = 0; gi < 4; gi++)
+                    if (gi < ng) {
+                        const int k = kc + p.gneg + 2 * gi;
+                        acc[gi] = cadd(acc[gi], cmul(cmul_conj(ysh(Y2, k, N), ysh(Y1, k, N)), cvc));
+                    }
+            }
+#pragma unroll
+            for (int gi = 0; gi < 4; gi++)
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc[gi].x += __shfl_xor_sync(0xffffffffu, acc[gi].x, o);
+                    acc[gi].y += __shfl_xor_sync(0xffffffffu, acc[gi].y, o);
+                }
+            if (lane == 0) {
+#pragma unroll
+                for (int gi = 0; gi < 4; gi++) wacc[wid][gi] = acc[gi];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float b = 0.f;
+                int g = 0;
+                for (int gi = 0; gi < ng; gi++) {
+                    float2 sacc = make_float2(0.f, 0.f);
+                    for (int w = 0; w < NW; w++) sacc = cadd(sacc, wacc[w][gi]);
+                    const float v = sacc.x * sacc.x + sacc.y * sacc.y;
+                    if (v > b) { b = v; g = p.gneg + 2 * gi; }
+                }
+                s_off = g;
+            }
+            __syncthreads();
+        } else {
             float best = 0.f;
             int bestg = 0;
-            const int ng = (p.gpos - p.gneg) / 2 + 1;
-            for (int gi = wid; gi < ng; gi += W) {
+            for (int gi = wid; gi < ng; gi += NW) {
                 const int g = p.gneg + 2 * gi;
                 float2 acc = make_float2(0.f, 0.f);
                 for (int c = lane; c < p.n_cv; c += 32) {
@@ -169,7 +248,7 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
             if (tid == 0) {
                 float b = 0.f;
                 int g = 0;
-                for (int w = 0; w < W; w++) {
+                for (int w = 0; w < NW; w++) {
                     const float v = wbest[w];
                     if (v > b || (v == b && v > 0.f && wbestg[w] < g)) { b = v; g = wbestg[w]; }
                 }
@@ -178,21 +257,16 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
             __syncthreads();
         }
         const int off = s_off;
-        // ---- taps + header symbol (ofdm_frame_equalizer_vcvc + simpledfe, BPSK header, symbol 0)
+        // ---- taps + header symbol (ofdm_frame_equalizer_vcvc + simpledfe, header constellation, symbol 0)
         {
-            float2 pc = make_float2(1.f, 0.f);
+            float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);
             if (off != 0) {
                 float sn, cs;
                 sincosf((float)(-TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
                 pc = make_float2(cs, sn);
-            }
-            float2 rot = make_float2(1.f, 0.f);       // channel state handed to the payload equaliser
-            if (off != 0) {
-                float sn, cs;
                 sincosf((float)(TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
-                rot = make_float2(cs, sn);
+                rot = make_float2(cs, sn);               // channel state handed to the payload equaliser
             }
-            const int b0 = 0;                          // header uses carrier set 0
             for (int u = tid; u < p.n_occ_u; u += NT) {
                 const int k = p.occ_u[u];
                 const int src = k + off;
@@ -203,7 +277,7 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
                 }
                 int d;
                 float2 z = make_float2(0.f, 0.f);
-                if (p.n_pil_sets && p.pil_flag[k]) {
+                if (pil_occ && p.pil_flag[k]) {
                     const float2 pv = p.pil_val[k];
                     const float2 q = cdivf(y, pv);
                     Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
@@ -214,7 +288,7 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
                     const float2 q = cmul(y, p.inv_hpts[d]);
                     Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
                 }
-                const int pos = p.pos_su[b0 * p.n_occ_u + u];
+                const int pos = p.pos_su[u];                 // carrier set 0
                 if (pos >= 0) {
                     hb[pos] = (uint8_t)d ^ p.hdr_mask[pos];
                     if (want_z) z_out[(long long)j * z_stride + pos] = z;
@@ -236,10 +310,12 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
                         if ((hb[k] & msk) != ((crc >> i) & msk)) ok = 0;
                 }
             }
-            int ps = (int)len * 8 / p.bps_p;
-            if (((int)len * 8) % p.bps_p) ps++;
+            int ps = (int)len * 8 / BPS_P;
+            if (((int)len * 8) % BPS_P) ps++;
             int fl = 0, acc = 0, s = 0;
-            while (acc < ps) { fl++; acc += p.occ_size[s]; s = (s + 1) % p.n_occ_sets; }
+            if (one_set) fl = (ps + size0 - 1) / size0;
+            else
+                while (acc < ps) { fl++; acc += p.occ_size[s]; s = (s + 1 == p.n_occ_sets) ? 0 : s + 1; }
             s_ok = ok; s_plen = (int)len; s_pnum = (int)num; s_psyms = ps; s_fsyms = fl;
         }
         __syncthreads();
@@ -254,7 +330,7 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
             continue;
         }
         rec.flags |= OFDMX_F_HDR_OK;
-        if (t + (long long)(3 + fsyms) * D > n || s_plen > p.max_pkt_bytes) {
+        if ((long long)(3 + fsyms) * D > rem || s_plen > p.max_pkt_bytes) {
             if (tid == 0) spec[j] = rec;
             continue;
         }
@@ -265,6 +341,8 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
         int first = 0;                                // first payload symbol of this round
         int slot0 = 3;                                // warp buffer holding payload symbol `first`
         int in_round = min(fsyms, W - 3);
+        int set_first = (p.n_occ_sets > 1) ? 1 : 0;   // carrier set / pilot set of payload symbol `first`
+        int pset_first = (p.n_pil_sets > 1) ? 1 : 0;
         for (;;) {
             if (off != 0) {   // per-symbol phase fix exp(-j 2 pi off cp / N (i+1)) of ofdm_frame_equalizer_vcvc
                 if (tid < in_round) {
@@ -278,32 +356,34 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
             for (int u = tid; u < p.n_occ_u; u += NT) {
                 const int k = p.occ_u[u];
                 const int src = k + off;
+                const bool inr = (src >= 0 && src < N);
+                const int ysrc = (src & (N - 1)) ^ (N >> 1);
                 float2 Hk = Hs[u];
-                int cb = cbase;
-                for (int ii = 0; ii < in_round; ii++) {
-                    const int i = first + ii;
-                    const float2 *Y = T + (slot0 + ii) * F1K_SLOT;
-                    const int set = (1 + i) % p.n_occ_sets;
-                    const int pset = p.n_pil_sets ? (1 + i) % p.n_pil_sets : 0;
+                int cb = cbase, set = set_first, pset = pset_first;
+                const float2 *Y = T + slot0 * F1K_SLOT;
+                int pos = one_set ? p.pos_su[u] : 0;
+                for (int ii = 0; ii < in_round; ii++, Y += F1K_SLOT) {
                     float2 y = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) {
-                        y = ysh(Y, src, N);
+                    if (inr) {
+                        y = Y[ysrc];
                         if (off != 0) y = cmul(y, pcs[ii]);
                     }
                     int d;
                     float2 z = make_float2(0.f, 0.f);
-                    if (p.n_pil_sets && p.pil_flag[pset * N + k]) {
+                    if (pil_occ && p.pil_flag[pset * N + k]) {
                         const float2 pv = p.pil_val[pset * N + k];
                         const float2 q = cdivf(y, pv);
                         Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
-                        d = ofdm_decide(p.bps_p, pv.x, pv.y, p.lut_p);
+                        d = f1k_decide<BPS_P>(pv.x, pv.y, lut);
                     } else {
-                        z = cdivf(y, Hk);
-                        d = ofdm_decide(p.bps_p, z.x, z.y, p.lut_p);
-                        const float2 q = cmul(y, p.inv_ppts[d]);
-                        Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
+                        const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
+                        const float2 nn = cmul_conj(y, Hk);
+                        z = make_float2(nn.x * rinv, nn.y * rinv);
+                        d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                        const float2 q = cmul(y, ipts[d]);
+                        Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                     }
-                    const int pos = p.pos_su[set * p.n_occ_u + u];
+                    if (!one_set) pos = p.pos_su[set * p.n_occ_u + u];
                     if (pos >= 0) {
                         const int idx = cb + pos;
                         if (idx < psyms) {
@@ -311,11 +391,20 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
                             if (want_z && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
                         }
                     }
-                    cb += p.occ_size[set];
+                    if (one_set) cb += size0;
+                    else {
+                        cb += p.occ_size[set];
+                        set = (set + 1 == p.n_occ_sets) ? 0 : set + 1;
+                    }
+                    if (p.n_pil_sets > 1) pset = (pset + 1 == p.n_pil_sets) ? 0 : pset + 1;
                 }
                 Hs[u] = Hk;
             }
-            for (int ii = 0; ii < in_round; ii++) cbase += p.occ_size[(1 + first + ii) % p.n_occ_sets];
+            for (int ii = 0; ii < in_round; ii++) {
+                cbase += p.occ_size[set_first];
+                set_first = (set_first + 1 >= p.n_occ_sets) ? 0 : set_first + 1;
+                if (p.n_pil_sets > 1) pset_first = (pset_first + 1 == p.n_pil_sets) ? 0 : pset_first + 1;
+            }
             first += in_round;
             if (first >= fsyms) break;
             // next round: transform the next W payload symbols
@@ -331,15 +420,18 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
         __syncthreads();
         const int cnt = min(cbase, psyms);
         // ---- repack_bits_bb(bps, 8, key, True) + additive_scrambler_bb
-        const int nbytes = min(cnt * p.bps_p / 8, p.max_pkt_bytes);
+        const int nbytes = min(cnt * BPS_P / 8, p.max_pkt_bytes);
         for (int mb = tid; mb < nbytes; mb += NT) {
             unsigned v = 0;
-            if (p.bps_p == 4) {
+            if (BPS_P == 4) {
                 v = (unsigned)syms[2 * mb] | ((unsigned)syms[2 * mb + 1] << 4);
+            } else if (BPS_P == 2) {
+                v = (unsigned)syms[4 * mb] | ((unsigned)syms[4 * mb + 1] << 2) | ((unsigned)syms[4 * mb + 2] << 4)
+                    | ((unsigned)syms[4 * mb + 3] << 6);
             } else {
                 for (int b = 0; b < 8; b++) {
                     const int bi = mb * 8 + b;
-                    const int si = bi / p.bps_p, sb = bi - si * p.bps_p;
+                    const int si = bi / BPS_P, sb = bi - si * BPS_P;
                     v |= ((unsigned)(syms[si] >> sb) & 1u) << b;
                 }
             }
@@ -366,6 +458,6 @@ rx_frame1024_kernel(const KP p, const float2 *__restrict__ samples, long long n,
 static inline size_t frame1024_smem_bytes(int W, int n_occ_u, int hl, int max_pkt_syms, int max_pkt_bytes)
 {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    return (size_t)W * F1K_SLOT * 8 + 1024 * 8 + al16((size_t)n_occ_u * 8) + 64 + al16(hl) + al16(max_pkt_syms)
+    return (size_t)W * F1K_SLOT * 8 + 1024 * 8 + (size_t)n_occ_u * 8 + 64 * 8 + 64 + 64 + al16(hl) + al16(max_pkt_syms)
            + al16(max_pkt_bytes) + 32;
 }

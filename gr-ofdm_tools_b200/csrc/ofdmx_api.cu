@@ -2,6 +2,7 @@
 // entry point needs a CUDA device and reports OFDMX_ERR_CUDA otherwise.
 #include "ofdmx_kernels.cuh"
 #include "ofdmx_sync.cuh"
+#include "ofdmx_sync_tma.cuh"
 #include "ofdmx_frame1024.cuh"
 #include "ofdmx_chain.cuh"
 
@@ -56,7 +57,9 @@ struct ofdmx_ctx {
     // host-buffer path
     DevBuf h_samples, h_frames, h_bytes, h_counts;
     cudaStream_t own_stream = nullptr;
-    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0, frame1k_smem = 0;
+    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0, frame1k_smem = 0, sync_tma_smem = 0;
+    int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
+    bool no_tma = false;            // OFDMX_NO_TMA=1: use the plain-load sync kernel
     bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
     int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
 };
@@ -270,6 +273,43 @@ int check_device(ofdmx_ctx *ctx)
     return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// sample streams as a 3-D tensor {32 floats (16 samples), rows, streams}; false if TMA cannot describe the buffer
+bool make_sample_map(CUtensorMap *tmap, const float2 *samples, int64_t n_streams, int64_t n_samples, int64_t stride)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<uintptr_t>(samples) & 15) != 0) return false;
+    if (n_streams > 1 && (stride & 1)) return false;                 // stream stride must be a multiple of 16 bytes
+    const int64_t rows = n_samples / 16;
+    if (rows < 1 || rows > 0x7fffffffLL - 4096) return false;
+    cuuint64_t dims[3] = { 32, (cuuint64_t)rows, (cuuint64_t)n_streams };
+    cuuint64_t strides[2] = { 128, (cuuint64_t)stride * 8 };
+    if (n_streams == 1) strides[1] = (cuuint64_t)((rows * 128 + 15) / 16 * 16);
+    cuuint32_t box[3] = { 32, ST_BOX_ROWS, 1 };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    return fn(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2 *>(samples), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // sync front end shared by ofdmx_rx and ofdmx_sync: detect bits -> triggers -> cfo
 int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_streams, int64_t n_samples,
              int64_t stride, int64_t max_trig, ofdmx_counts *counts_dev, cudaStream_t st)
@@ -277,12 +317,29 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
     const KP &kp = ctx->kp;
     ofdmx_ctx *ctx_ = ctx;
     CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
-    if (kp.N >= 32) {
+    CUtensorMap tmap;
+    if (kp.N >= 32 && !ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
+        // TMA path: 3-D map {32 floats, rows of 16 samples, streams}; whole rows only (the kernel patches the tail)
+        const long long tiles = (n_samples + SV_T - 1) / SV_T;
+        const long long spans = (tiles + ST_SPAN_TILES - 1) / ST_SPAN_TILES;
+        const long long total = spans * n_streams;
+        const unsigned grid = (unsigned)std::min<long long>(total, (long long)ctx->sm_count * ctx->sync_tma_occ);
+        KT(K_SYNC);
+        sync_metric_tma_kernel<<<grid, SV_THREADS, ctx->sync_tma_smem, st>>>(tmap, samples, n_samples, stride, kp.N, (float)kp.thr,
+                                                                              kp.thr, w.detmask, w.wps, tiles, spans, total);
+    } else if (kp.N >= 32) {
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
         dim3 grid((unsigned)tiles, (unsigned)n_streams);
         KT(K_SYNC);
-        sync_metric_fast_kernel<<<grid, SV_THREADS, ctx->sync_fast_smem, st>>>(samples, n_samples, stride, kp.N, (float)kp.thr,
-                                                                                kp.thr, w.detmask, w.wps);
+#define SVF(NN) sync_metric_fast_kernel<NN><<<grid, SV_THREADS, ctx->sync_fast_smem, st>>>(samples, n_samples, stride, kp.N, (float)kp.thr, kp.thr, w.detmask, w.wps)
+        switch (kp.N) {
+        case 64: SVF(64); break;
+        case 128: SVF(128); break;
+        case 1024: SVF(1024); break;
+        case 2048: SVF(2048); break;
+        default: SVF(0); break;
+        }
+#undef SVF
     } else {
         const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
         dim3 grid((unsigned)tiles, (unsigned)n_streams);
@@ -532,8 +589,20 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             if (e1 != cudaSuccess)
                 return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(e1)));
         }
+        c->sync_tma_smem = sync_tma_smem_bytes(N);
+        if (N >= 32 && cudaFuncSetAttribute(sync_metric_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_tma_smem) != cudaSuccess)
+            return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
+        if (N >= 32) {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sync_metric_tma_kernel, SV_THREADS, c->sync_tma_smem) == cudaSuccess && occ > 0)
+                c->sync_tma_occ = occ;
+        }
         c->sync_fast_smem = sync_fast_smem_bytes(N);
-        if (cudaFuncSetAttribute(sync_metric_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
+        if (cudaFuncSetAttribute(sync_metric_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
+            || cudaFuncSetAttribute(sync_metric_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
+            || cudaFuncSetAttribute(sync_metric_fast_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
+            || cudaFuncSetAttribute(sync_metric_fast_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
+            || cudaFuncSetAttribute(sync_metric_fast_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
             || cudaFuncSetAttribute(sync_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_smem) != cudaSuccess
             || cudaFuncSetAttribute(rx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem) != cudaSuccess
             || cudaFuncSetAttribute(tx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx_smem) != cudaSuccess)
@@ -541,6 +610,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                              cudaGetErrorString(cudaGetLastError())));
     }
     if (const char *fg = getenv("OFDMX_FORCE_GENERIC")) c->force_generic = (fg[0] == '1');
+    c->no_tma = true;   // the plain-load kernel is currently the faster one; OFDMX_USE_TMA=1 selects the TMA ring kernel
+    if (const char *ut = getenv("OFDMX_USE_TMA")) c->no_tma = (ut[0] != '1');
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
     *out = c;

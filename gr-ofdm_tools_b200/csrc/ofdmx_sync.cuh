@@ -43,12 +43,14 @@ __device__ __forceinline__ void sv_products(const float4 *__restrict__ r4, int j
     }
 }
 
+template <int NT>   // NT = fft_len at compile time, or 0 to use the runtime value
 __global__ void __launch_bounds__(SV_THREADS, 3)
-sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int N, float thr_f,
+sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int Nrt, float thr_f,
                         double thr_d, uint32_t *__restrict__ detmask, long long wps)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = NT ? NT : Nrt;
     const int h = N >> 1;
     const int nhc = N >> 4;                 // halo chunks
     const int hc = h >> 4;                  // chunks per half window
@@ -136,6 +138,7 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     float Pi = TXi[J] - TXi[J - hc];
     float E = TE[J] - TE[J - nhc];
     const float thr4 = 0.25f * thr_f;
+    const float e3 = 3.5f * eps, e33 = 3.0f * eps * eps;
     unsigned det = 0, unc = 0;
     const int jd = J - hc, jn = J - nhc;
 #pragma unroll
@@ -151,12 +154,12 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
             Pr += x[k].x - xdr;
             Pi += x[k].y - xdi;
             E += e[k] - ed;
-            const float pm2 = fmaf(Pr, Pr, Pi * Pi);
-            const float rhs = thr4 * E * E;
-            const float d = pm2 - rhs;
-            const float err = fmaf(2.0f * eps, fabsf(Pr) + fabsf(Pi) + fabsf(E), fmaf(3.0f * eps, eps, 1.0e-6f * (pm2 + rhs)));
-            det |= (d > err ? 1u : 0u) << k;
-            unc |= (fabsf(d) <= err ? 1u : 0u) << k;
+            const float d = fmaf(Pr, Pr, Pi * Pi) - thr4 * E * E;
+            // |Pr| + |Pi| <= 0.71 E (Cauchy-Schwarz on the two half windows), pm2 + rhs <= 0.5 E^2
+            const float aE = fabsf(E);
+            const float err = fmaf(aE, fmaf(5.0e-7f, aE, e3), e33);
+            if (d > err) det |= 1u << k;
+            if (fabsf(d) <= err) unc |= 1u << k;
         }
     }
     if (A == 0.0f) { det = 0; unc = 0; }             // all-zero tile: R^2 > 0 is false everywhere

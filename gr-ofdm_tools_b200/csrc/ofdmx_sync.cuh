@@ -44,7 +44,7 @@ __device__ __forceinline__ void sv_products(const float4 *__restrict__ r4, int j
 }
 
 template <int NT>   // NT = fft_len at compile time, or 0 to use the runtime value
-__global__ void __launch_bounds__(SV_THREADS, 3)
+__global__ void __launch_bounds__(SV_THREADS, 4)
 sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int Nrt, float thr_f,
                         double thr_d, uint32_t *__restrict__ detmask, long long wps)
 {
@@ -141,6 +141,18 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     const float e3 = 3.5f * eps, e33 = 3.0f * eps * eps;
     unsigned det = 0, unc = 0;
     const int jd = J - hc, jn = J - nhc;
+    // Chunk-level rejection: inside the chunk |P| can grow by at most the energy entering and leaving
+    // the two half windows, and R can shrink by at most the energy leaving.  If even those extremes stay
+    // below the threshold, no sample of the chunk detects (or is uncertain) and the sliding pass is
+    // skipped -- decided per warp, so noise and payload regions cost no phase-3 work.
+    bool skip;
+    {
+        const float cJ = TE[J + 1] - TE[J], cD = TE[jd + 1] - TE[jd], cN = TE[jn + 1] - TE[jn];
+        const float pmax = fabsf(Pr) + fabsf(Pi) + 0.5f * (cJ + 2.0f * cD + cN) + 4.0f * eps;
+        const float emin = E - cN - 4.0f * eps;
+        skip = (emin > 0.0f) && (pmax * pmax < 0.999f * thr4 * emin * emin);
+    }
+    if (!__all_sync(0xffffffffu, skip)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const float4 b = r4[sv_off(jd, q)];          // r[n - N/2]
@@ -161,6 +173,7 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
             if (d > err) det |= 1u << k;
             if (fabsf(d) <= err) unc |= 1u << k;
         }
+    }
     }
     if (A == 0.0f) { det = 0; unc = 0; }             // all-zero tile: R^2 > 0 is false everywhere
     {   // samples beyond the end of the stream never detect

@@ -216,7 +216,14 @@ sync_metric_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float2 *_
             float E = TE[J] - TE[J - nhc];
             const float e3 = 3.5f * eps, e33 = 3.0f * eps * eps;
             unsigned det = 0, unc = 0;
-            {
+            bool skip;
+            {   // chunk-level rejection (see ofdmx_sync.cuh)
+                const float cJ = TE[J + 1] - TE[J], cD = TE[J - hc + 1] - TE[J - hc], cN = TE[J - nhc + 1] - TE[J - nhc];
+                const float pmax = fabsf(Pr) + fabsf(Pi) + 0.5f * (cJ + 2.0f * cD + cN) + 4.0f * eps;
+                const float emin = E - cN - 4.0f * eps;
+                skip = (emin > 0.0f) && (pmax * pmax < 0.999f * thr4 * emin * emin);
+            }
+            if (!__all_sync(0xffffffffu, skip)) {
                 const int sd = (rdel & 7) << 4, sn = (rdn & 7) << 4;
                 const unsigned char *pd = ring + (rdel << 7), *pn = ring + (rdn << 7);
 #pragma unroll

@@ -579,13 +579,17 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             c->frame1k_warps = std::max(4, std::min(F1K_MAXW, 3 + kp.max_frame_syms));
             c->frame1k_smem = frame1024_smem_bytes(c->frame1k_warps, kp.n_occ_u, c->hl, kp.max_pkt_syms, kp.max_pkt_bytes);
             cudaError_t e1 = cudaSuccess;
+#define F1K_ATTR(B, S, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_frame1024_kernel<B, S, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); if (e2 != cudaSuccess) e1 = e2; }
+#define F1K_ATTR4(B) F1K_ATTR(B, true, false) F1K_ATTR(B, true, true) F1K_ATTR(B, false, false) F1K_ATTR(B, false, true)
             switch (kp.bps_p) {
-            case 1: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
-            case 2: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
-            case 3: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
-            case 4: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
-            default: e1 = cudaFuncSetAttribute(rx_frame1024_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); break;
+            case 1: F1K_ATTR4(1) break;
+            case 2: F1K_ATTR4(2) break;
+            case 3: F1K_ATTR4(3) break;
+            case 4: F1K_ATTR4(4) break;
+            default: F1K_ATTR4(6) break;
             }
+#undef F1K_ATTR4
+#undef F1K_ATTR
             if (e1 != cudaSuccess)
                 return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(e1)));
         }
@@ -718,10 +722,16 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     ofdmx_ctx *ctx_ = c;
     if (c->frame1k_warps > 0 && !c->force_generic) {
         KT(K_FRAME);
-#define F1K_LAUNCH(B)                                                                                              \
-    rx_frame1024_kernel<B><<<c->sm_count * 2, F1K_THREADS, c->frame1k_smem, st>>>(                                 \
+#define F1K_LAUNCH3(B, S, Z)                                                                                       \
+    rx_frame1024_kernel<B, S, Z><<<c->sm_count * 2, F1K_THREADS, c->frame1k_smem, st>>>(                           \
         c->kp, c->frame1k_warps, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig,   \
         w.spec, bytes_out, byte_stride, (float2 *)z_out, z_stride)
+#define F1K_LAUNCH(B)                                                                                              \
+    do {                                                                                                           \
+        if (simple) { if (z_out) F1K_LAUNCH3(B, true, true); else F1K_LAUNCH3(B, true, false); }                   \
+        else { if (z_out) F1K_LAUNCH3(B, false, true); else F1K_LAUNCH3(B, false, false); }                        \
+    } while (0)
+        const bool simple = (c->kp.n_occ_sets == 1 && c->kp.n_pil_sets <= 1 && !c->kp.pil_in_occ);
         switch (c->kp.bps_p) {
         case 1: F1K_LAUNCH(1); break;
         case 2: F1K_LAUNCH(2); break;
@@ -729,6 +739,7 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
         case 4: F1K_LAUNCH(4); break;
         default: F1K_LAUNCH(6); break;
         }
+#undef F1K_LAUNCH3
 #undef F1K_LAUNCH
     } else {
         KT(K_FRAME);

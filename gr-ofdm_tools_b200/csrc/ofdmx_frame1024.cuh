@@ -118,7 +118,9 @@ __device__ __forceinline__ float f1k_rcp(float x)
 
 #define F1K_THREADS 320
 
-template <int BPS_P>
+// SIMPLE: one occupied-carrier set, at most one pilot set, no pilot inside the occupied set (every
+// reference surface); WANT_Z: the pre-decision symbols are tapped to z_out (debug / parity tests).
+template <int BPS_P, bool SIMPLE, bool WANT_Z>
 __global__ void __launch_bounds__(F1K_THREADS, 2)
 rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples, long long n, long long stride,
                     const long long *__restrict__ trig, const int *__restrict__ trig_stream,
@@ -156,10 +158,10 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
     }
     const int nt = *n_trig_dev;
     const int N = 1024, D = p.D;
-    const bool want_z = (z_out != nullptr);
+    constexpr bool want_z = WANT_Z;
     const float al = p.alpha, oma = 1.0f - p.alpha;
-    const bool one_set = (p.n_occ_sets == 1);
-    const bool pil_occ = (p.pil_in_occ != 0);
+    const bool one_set = SIMPLE || (p.n_occ_sets == 1);
+    const bool pil_occ = !SIMPLE && (p.pil_in_occ != 0);
     const int size0 = p.occ_size[0];
 
     for (int j = blockIdx.x; j < nt; j += gridDim.x) {
@@ -383,7 +385,7 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                         const float2 q = cmul(y, ipts[d]);
                         Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                     }
-                    if (!one_set) pos = p.pos_su[set * p.n_occ_u + u];
+                    if (!SIMPLE && !one_set) pos = p.pos_su[set * p.n_occ_u + u];
                     if (pos >= 0) {
                         const int idx = cb + pos;
                         if (idx < psyms) {
@@ -391,12 +393,12 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                             if (want_z && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
                         }
                     }
-                    if (one_set) cb += size0;
+                    if (SIMPLE || one_set) cb += size0;
                     else {
                         cb += p.occ_size[set];
                         set = (set + 1 == p.n_occ_sets) ? 0 : set + 1;
                     }
-                    if (p.n_pil_sets > 1) pset = (pset + 1 == p.n_pil_sets) ? 0 : pset + 1;
+                    if (!SIMPLE && p.n_pil_sets > 1) pset = (pset + 1 == p.n_pil_sets) ? 0 : pset + 1;
                 }
                 Hs[u] = Hk;
             }

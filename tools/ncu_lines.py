@@ -33,7 +33,10 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
-mangled = re.search(r"(_Z\w*" + re.escape(kname.split("(")[0]) + r"\w*)", dis).group(1)
+kbase = re.match(r"(?:void )?(\w+)", kname).group(1)
+targ = re.search(r"<\(int\)(\d+)>", kname)
+pat = r"(_Z\d*" + re.escape(kbase) + (r"ILi%sE\w*" % targ.group(1) if targ else r"\w*") + ")"
+mangled = re.search(pat, dis).group(1)
 sec = dis[dis.index(".section\t.text." + mangled):]
 sec = sec[: sec.index(".section", 20)] if ".section" in sec[20:] else sec
 cur, off2line = ("?", 0), {}
@@ -53,7 +56,7 @@ for a, s, n, w in data:
     by[k] += n
     st[k] += w
     tot += n
-print("kernel", kname.split("(")[0], "total warp-instr", tot, "stall samples", sum(st.values()))
+print("kernel", kbase, "total warp-instr", tot, "stall samples", sum(st.values()))
 srcs = {}
 for (f, l), n in by.most_common(top):
     if f not in srcs:

@@ -60,6 +60,7 @@ struct ofdmx_ctx {
     size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0, frame1k_smem = 0, sync_tma_smem = 0;
     int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
     bool no_tma = false;            // OFDMX_NO_TMA=1: use the plain-load sync kernel
+    bool emit_all = false;          // ofdmx_set_emit_all: frames_out receives every trigger's record
     bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
     int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
 };
@@ -664,6 +665,13 @@ int ofdmx_profile_read(ofdmx_ctx *c, float *ms_total, int64_t *calls)
     return OFDMX_OK;
 }
 
+int ofdmx_set_emit_all(ofdmx_ctx *c, int enable)
+{
+    if (!c) return OFDMX_ERR_PARAM;
+    c->emit_all = enable != 0;
+    return OFDMX_OK;
+}
+
 int ofdmx_header_len(const ofdmx_ctx *c) { return c ? c->hl : 0; }
 int64_t ofdmx_launch_count(const ofdmx_ctx *c) { return c ? c->launches : 0; }
 
@@ -750,7 +758,7 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     { KT(K_CHAIN_NEXT); chain_next_kernel<<<w.nblk, CH_T, 0, st>>>(c->kp, w.trig, w.trig_stream, w.spec, w.stream_start, w.n_trig,
                                                                  w.jumpA, w.jumpB); }
     { KT(K_CHAIN_ENTRY); chain_entry_kernel<<<1, 256, 0, st>>>(w.n_trig, w.jumpB, w.entry, w.nblk); }
-    { KT(K_CHAIN_MARK); chain_mark_kernel<<<w.nblk, CH_T, 0, st>>>(w.spec, w.n_trig, w.jumpA, w.entry, w.markA, w.blockcount); }
+    { KT(K_CHAIN_MARK); chain_mark_kernel<<<w.nblk, CH_T, 0, st>>>(w.spec, w.n_trig, w.jumpA, w.entry, w.markA, w.blockcount, c->emit_all ? 1 : 0); }
     { KT(K_CHAIN_SCAN); chain_scan_kernel<<<1, 1024, 0, st>>>(w.blockcount, w.nblk, counts_dev); }
     { KT(K_CHAIN_EMIT); chain_emit_kernel<<<w.nblk, CH_T, 0, st>>>(w.spec, w.n_trig, w.markA, w.blockcount, frames_out); }
     CUDA_TRY(c, cudaGetLastError());

@@ -82,7 +82,7 @@ __global__ void chain_entry_kernel(const int *__restrict__ n_trig_dev, const int
 __global__ void __launch_bounds__(CH_T)
 chain_mark_kernel(const ofdmx_frame *__restrict__ spec, const int *__restrict__ n_trig_dev,
                   const int *__restrict__ nxt, const int *__restrict__ entry, uint8_t *__restrict__ emitflag,
-                  int *__restrict__ blockcount)
+                  int *__restrict__ blockcount, int emit_all)
 {
     __shared__ int jA[CH_B], jB[CH_B];
     __shared__ uint8_t mA[CH_B], mB[CH_B];
@@ -124,8 +124,9 @@ chain_mark_kernel(const ofdmx_frame *__restrict__ spec, const int *__restrict__ 
     int local = 0;
     for (int li = threadIdx.x; li < cnt; li += CH_T) {
         const unsigned fl = spec[base + li].flags;
-        const uint8_t em = (mc[li] && (fl & OFDMX_F_HDR_OK) && (fl & OFDMX_F_COMPLETE)) ? 1 : 0;
-        emitflag[base + li] = em;
+        // bit 0: record is emitted; bit 1: the demux examined this trigger
+        const uint8_t em = (emit_all || (mc[li] && (fl & OFDMX_F_HDR_OK) && (fl & OFDMX_F_COMPLETE))) ? 1 : 0;
+        emitflag[base + li] = em | (mc[li] ? 2 : 0);
         local += em;
     }
     int total;
@@ -163,12 +164,13 @@ chain_emit_kernel(const ofdmx_frame *__restrict__ spec, const int *__restrict__ 
     int carry = blockbase[blockIdx.x];
     for (int i0 = base; i0 < end; i0 += CH_T) {
         const int i = i0 + threadIdx.x;
-        const int em = (i < end) ? emitflag[i] : 0;
+        const int ef = (i < end) ? emitflag[i] : 0;
+        const int em = ef & 1;
         int total;
         const int ex = block_excl_scan(em, wt, total);
         if (em) {
             ofdmx_frame f = spec[i];
-            f.flags |= OFDMX_F_ACCEPTED;
+            if (ef & 2) f.flags |= OFDMX_F_ACCEPTED;
             frames_out[carry + ex] = f;
         }
         carry += total;

@@ -36,6 +36,76 @@ def plan_segments(n_samples, world, fft_len, cp_len, max_frame_samples):
     return out
 
 
+def demux_chain(records, fft_len, cp_len, holdoff, n_samples):
+    """The header_payload_demux acceptance rule over per-trigger records of ONE stream,
+    sorted by trigger: returns the boolean mask of the frames the flowgraph emits.  Same rule as the
+    device chain kernels (csrc/ofdmx_chain.cuh); used on the host to stitch segments."""
+    D = fft_len + cp_len
+    emit = np.zeros(len(records), bool)
+    pos = 0
+    for i, f in enumerate(records):
+        t = int(f["trigger"])
+        if t < pos:
+            continue
+        fl = int(f["flags"])
+        if t + 3 * D > n_samples or not (fl & _lib.F_HDR_SEEN):
+            break                                   # demux waits for header samples that never come
+        if not (fl & _lib.F_HDR_OK):
+            pos = t + 1
+            continue
+        L = int(f["frame_syms"])
+        if t + (3 + L) * D > n_samples or not (fl & _lib.F_COMPLETE):
+            break                                   # demux waits for payload samples that never come
+        emit[i] = True
+        pos = t + (3 + L) * D - holdoff if L > 0 else t + 3 * D
+    return emit
+
+
+def merge_segments(seg_records, plan, fft_len, cp_len, holdoff, n_samples):
+    """Stitch per-segment emit-all records (triggers relative to each segment's load_start) into the
+    frame list of the unsplit stream.  seg_records[r]: FRAME_DTYPE array from rank r (every trigger);
+    plan: plan_segments(...).  Returns (records with absolute triggers, owner rank per record)."""
+    owned, owner = [], []
+    for r, (rec, (l0, a, b, l1)) in enumerate(zip(seg_records, plan)):
+        rec = rec.copy()
+        rec["trigger"] += l0
+        keep = (rec["trigger"] >= a) & (rec["trigger"] < b)
+        owned.append(rec[keep])
+        owner.append(np.full(int(keep.sum()), r, np.int32))
+    allrec = np.concatenate(owned) if owned else np.zeros(0)
+    allown = np.concatenate(owner) if owner else np.zeros(0, np.int32)
+    emit = demux_chain(allrec, fft_len, cp_len, holdoff, n_samples)
+    out = allrec[emit].copy()
+    out["flags"] |= _lib.F_ACCEPTED
+    return out, allown[emit]
+
+
+def rx_segmented(phy, samples, n_segments, max_pkt_bytes=None):
+    """Run one long stream as n_segments independent RX calls (what n_segments GPUs would each do) and
+    stitch the results; returns (records, list of payload bytes).  `samples`: 1-D cuda complex64."""
+    n = samples.numel()
+    D = phy.fft_len + phy.cp_len
+    max_frame = int(phy.frame_samples((max_pkt_bytes or phy.max_pkt_bytes) - (4 if phy.crc_mode else 0)))
+    plan = plan_segments(n, n_segments, phy.fft_len, phy.cp_len, max_frame)
+    phy.set_emit_all(True)
+    try:
+        segs = [phy.rx(samples[l0:l1]) for (l0, a, b, l1) in plan]
+    finally:
+        phy.set_emit_all(False)
+    recs, own = merge_segments([s.frames for s in segs], plan, phy.fft_len, phy.cp_len,
+                               phy.params.demux_holdoff, n)
+    payloads = []
+    for f, r in zip(recs, own):
+        nb = int(f["pkt_len"])
+        row = segs[r].slots[int(f["slot"])].cpu().numpy()
+        if phy.crc_mode:
+            if not (int(f["flags"]) & _lib.F_CRC_OK):
+                continue
+            nb -= 4
+        payloads.append(bytes(row[:nb]))
+    return recs, payloads
+
+
 def summarize(res, n_samples):
     """Fixed-size per-rank summary of one RX call (RxResult)."""
     f = res.frames

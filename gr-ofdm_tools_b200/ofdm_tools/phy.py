@@ -182,6 +182,10 @@ class OfdmPhy(object):
     def launch_count(self):
         return _lib.load().ofdmx_launch_count(self.ctx)
 
+    def set_emit_all(self, enable=True):
+        """RX then returns one record per plateau trigger (see ofdmx_set_emit_all)."""
+        _lib.check(_lib.load().ofdmx_set_emit_all(self.ctx, int(bool(enable))), self.ctx)
+
     def profile(self, enable=True):
         """Start/stop recording CUDA events around every kernel this context launches."""
         _lib.check(_lib.load().ofdmx_profile(self.ctx, int(bool(enable))), self.ctx)

@@ -132,6 +132,11 @@ int ofdmx_rx(ofdmx_ctx *ctx, const float *samples_dev, int64_t n_streams, int64_
              uint8_t *bytes_out_dev, int64_t byte_stride, float *z_out_dev, int64_t z_stride,
              ofdmx_counts *counts_dev, void *cuda_stream);
 
+/* enable != 0: ofdmx_rx writes a record for EVERY plateau trigger (header fields and flags as decoded
+ * speculatively; OFDMX_F_ACCEPTED marks the triggers the demux examined) instead of only the accepted
+ * frames.  Used to resolve the demux state exactly across the seams of a stream split over several GPUs. */
+int ofdmx_set_emit_all(ofdmx_ctx *ctx, int enable);
+
 /* Same call with HOST buffers (pinned or pageable): copies in, runs, copies records, counts and
  * the used payload slots back, and synchronises.  This is the call a GNU Radio work() makes. */
 int ofdmx_rx_host(ofdmx_ctx *ctx, const float *samples_host, int64_t n_streams, int64_t n_samples,

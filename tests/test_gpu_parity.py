@@ -262,3 +262,56 @@ def test_large_roundtrip_properties():
     assert res.payloads() == pk
     d = np.diff(res.frames["trigger"])
     assert np.all(np.abs(d - 9864) <= 72)
+
+
+@pytest.mark.parametrize("n_seg", [2, 5])
+def test_segmented_stream_equals_unsplit(n_seg):
+    """one long stream cut into segments (one per GPU) with halos, every trigger's record
+    returned (emit-all), demux chain re-run over the owned triggers on the host == unsplit result."""
+    from ofdm_tools import dist
+    cfg = cm.cfg_c1(2, True, 1)
+    rng = np.random.default_rng(123)
+    pk, fr = _frames(cfg, rng, 60, 96)
+    x = cm.channel(fr, rng, gaps=(0, 300), snr_db=28.0, cfo=0.11, tail=400)
+    phy = cm.make_phy(cfg, max_pkt_bytes=128)
+    whole = phy.rx(_to_dev(x))
+    recs, payloads = dist.rx_segmented(phy, _to_dev(x), n_seg)
+    assert np.array_equal(recs["trigger"], whole.frames["trigger"])
+    assert np.array_equal(recs["pkt_num"], whole.frames["pkt_num"])
+    assert np.array_equal(recs["flags"], whole.frames["flags"])
+    assert payloads == whole.payloads() == pk
+
+
+def test_emit_all_returns_every_trigger():
+    cfg = cm.cfg_c1(2, True, 1)
+    rng = np.random.default_rng(8)
+    pk, fr = _frames(cfg, rng, 8, 40)
+    fr[3] = fr[3].copy()
+    fr[3][2 * 80 + 16:3 * 80] *= -1.0
+    x = cm.channel(fr, rng, snr_db=30.0)
+    phy = cm.make_phy(cfg)
+    normal = phy.rx(_to_dev(x))
+    phy.set_emit_all(True)
+    every = phy.rx(_to_dev(x))
+    phy.set_emit_all(False)
+    assert len(every.frames) == every.n_triggers >= 8 and len(normal.frames) == 7
+    acc = every.frames[(every.frames["flags"] & 8) != 0]
+    ok = acc[(acc["flags"] & 5) == 5]
+    assert np.array_equal(ok["trigger"], normal.frames["trigger"])
+
+
+def test_generic_kernel_at_1024_matches_fast_path(monkeypatch):
+    """The any-fft_len frame kernel and the fft_len-1024 fast path give identical records and bytes."""
+    cfg = cm.cfg_c3()
+    rng = np.random.default_rng(55)
+    pk, fr = _frames(cfg, rng, 5, 700)
+    x = cm.channel(fr, rng, gaps=(0, 50), lead=300, tail=3000, snr_db=40.0, cfo=-0.2, fft_len=1024, taps=cm.MULTIPATH)
+    fast = cm.make_phy(cfg).rx(_to_dev(x), want_z=True)
+    monkeypatch.setenv("OFDMX_FORCE_GENERIC", "1")
+    gen = cm.make_phy(cfg).rx(_to_dev(x), want_z=True)
+    monkeypatch.setenv("OFDMX_FORCE_GENERIC", "0")
+    monkeypatch.setenv("OFDMX_USE_TMA", "1")
+    tma = cm.make_phy(cfg).rx(_to_dev(x))
+    assert np.array_equal(fast.frames, gen.frames) and fast.payloads() == gen.payloads() == pk
+    assert np.array_equal(fast.frames, tma.frames) and tma.payloads() == pk
+    assert cm.rel_evm(fast.z.cpu().numpy()[:5, :3000], gen.z.cpu().numpy()[:5, :3000]) < 1e-5

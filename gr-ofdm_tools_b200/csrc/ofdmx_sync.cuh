@@ -65,19 +65,38 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     const float2 *r = samples + (long long)blockIdx.y * stride;
     const bool aligned = ((reinterpret_cast<unsigned long long>(r) & 15ull) == 0);
 
-    // ---- phase 0: stage [ts - N, ts + SV_T) (zeros outside the stream)
+    // ---- phase 0: stage [ts - N, ts + SV_T) (zeros outside the stream).  Loads are issued in batches
+    // of 8 per thread before any store, so one HBM latency covers the whole batch.
     const int n_units = nch * 8;
-    for (int u = tid; u < n_units; u += SV_THREADS) {
-        const long long m = ts - N + 2LL * u;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m >= 0 && m + 1 < n) {
-            if (aligned) v = __ldg(reinterpret_cast<const float4 *>(r + m));
-            else { const float2 a = __ldg(&r[m]), b = __ldg(&r[m + 1]); v = make_float4(a.x, a.y, b.x, b.y); }
-        } else if (m >= 0 && m < n) {
-            const float2 a = __ldg(&r[m]);
-            v.x = a.x; v.y = a.y;
+    const bool interior = aligned && (ts - N >= 0) && (ts + SV_T <= n);
+    for (int u0 = 0; u0 < n_units; u0 += 8 * SV_THREADS) {
+        float4 v[8];
+        if (interior) {
+            const float4 *src = reinterpret_cast<const float4 *>(r + (ts - N)) + u0 + tid;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                v[i] = (u0 + i * SV_THREADS + tid < n_units) ? __ldg(src + i * SV_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int u = u0 + i * SV_THREADS + tid;
+                const long long m = ts - N + 2LL * u;
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (u < n_units && m >= 0 && m + 1 < n) {
+                    if (aligned) t4 = __ldg(reinterpret_cast<const float4 *>(r + m));
+                    else { const float2 a = __ldg(&r[m]), b = __ldg(&r[m + 1]); t4 = make_float4(a.x, a.y, b.x, b.y); }
+                } else if (u < n_units && m >= 0 && m < n) {
+                    const float2 a = __ldg(&r[m]);
+                    t4.x = a.x; t4.y = a.y;
+                }
+                v[i] = t4;
+            }
         }
-        r4[u + (u >> 3)] = v;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int u = u0 + i * SV_THREADS + tid;
+            if (u < n_units) r4[u + (u >> 3)] = v[i];
+        }
     }
     __syncthreads();
 

@@ -44,7 +44,7 @@ __device__ __forceinline__ void sv_products(const float4 *__restrict__ r4, int j
 }
 
 template <int NT>   // NT = fft_len at compile time, or 0 to use the runtime value
-__global__ void __launch_bounds__(SV_THREADS, 4)
+__global__ void __launch_bounds__(SV_THREADS, 3)
 sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int Nrt, float thr_f,
                         double thr_d, uint32_t *__restrict__ detmask, long long wps)
 {

@@ -559,6 +559,21 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         for (int k = 0; k < N; k++)
             if (pil_flag[(size_t)ps * N + k] && occ_mask[k]) kp.pil_in_occ = 1;
 
+    // CRC-8 (poly 0x07, init 0xFF) is affine in the message bits: crc(m) = crc(0) ^ XOR of per-bit terms
+    auto crc8_bytes = [](unsigned len, unsigned num) {
+        uint8_t b[4] = { (uint8_t)(len & 0xFF), (uint8_t)(len >> 8), (uint8_t)(num & 0xFF), (uint8_t)(num >> 8) };
+        uint8_t crc = 0xFF;
+        for (int i = 0; i < 4; i++) {
+            crc ^= b[i];
+            for (int k = 0; k < 8; k++) crc = (crc & 0x80) ? (uint8_t)((crc << 1) ^ 0x07) : (uint8_t)(crc << 1);
+        }
+        return crc;
+    };
+    std::vector<uint8_t> crc8_bit(24);
+    kp.crc8_zero = crc8_bytes(0, 0);
+    for (int l = 0; l < 24; l++)
+        crc8_bit[l] = (uint8_t)(crc8_bytes(l < 12 ? (1u << l) : 0u, l < 12 ? 0u : (1u << (l - 12))) ^ kp.crc8_zero);
+
 #define UP(vec, field)                                          \
     if ((rc = upload(c, vec, &kp.field)) != 0) return bail(rc);
     UP(tw, tw) UP(occ_bins, occ_bins) UP(occ_base, occ_base) UP(occ_size, occ_size) UP(occ_u, occ_u)
@@ -566,7 +581,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(pil_size, pil_size) UP(pil_sym, pil_sym) UP(pil_sym_base, pil_sym_base) UP(sw1, sw1) UP(sw2, sw2)
     UP(cv_k, cv_k) UP(cv_conj, cv_conj) UP(inv_sw2, inv_sw2) UP(hdr_mask, hdr_mask) UP(keystream, keystream)
     UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
-    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su)
+    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit)
 #undef UP
 
     // shared-memory budgets

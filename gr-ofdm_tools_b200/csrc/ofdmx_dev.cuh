@@ -46,6 +46,8 @@ struct KP {
     const float2 *inv_ppts;
     const int *pos_su;           // [n_occ_sets][n_occ_u] position of union carrier u in set's list, or -1
     int max_frame_syms;
+    const uint8_t *crc8_bit;     // [24] CRC-8 contribution of header bit l (len bits 0..11, counter bits 12..23)
+    unsigned crc8_zero;          // CRC-8 of the all-zero header fields
     int pil_in_occ;              // some pilot carrier is also in occupied_carriers (equaliser pilot branch reachable)
 };
 
@@ -159,7 +161,7 @@ __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__r
     if (len < 4) {
         // init folding needs >= 4 message bytes; tiny messages are done serially
         uint32_t c = 0xFFFFFFFFu;
-        for (int i = 0; i < len; i++) c = __ldg(&tab[(c ^ msg[i]) & 0xFF]) ^ (c >> 8);
+        for (int i = 0; i < len; i++) c = tab[(c ^ msg[i]) & 0xFF] ^ (c >> 8);
         return c ^ 0xFFFFFFFFu;
     }
     uint32_t reg_total = 0;   // raw register so far (same value on every thread)
@@ -177,9 +179,9 @@ __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__r
             int gi = done + vp;
             uint8_t byte = msg[gi];
             if (gi < 4) byte ^= 0xFF;                // init = 0xFFFFFFFF
-            reg = __ldg(&tab[(reg ^ byte) & 0xFF]) ^ (reg >> 8);
+            reg = tab[(reg ^ byte) & 0xFF] ^ (reg >> 8);
         }
-        uint32_t term = reg ? gf2_mul(reg, __ldg(&powtab[tid & 255])) : 0u;
+        uint32_t term = reg ? gf2_mul(reg, powtab[tid & 255]) : 0u;
         // XOR-reduce over the block
         for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
         __syncthreads();
@@ -191,7 +193,7 @@ __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__r
             // previous register shifted by the 4096 bytes just processed: x^(8*4096) = powtab[0]*x^128
             uint32_t prev = reg_total;
             if (prev) {
-                uint32_t sh = __ldg(&powtab[0]);
+                uint32_t sh = powtab[0];
                 for (int i = 0; i < 128; i++) sh = gf2_mul_x(sh);
                 prev = gf2_mul(prev, sh);
             }

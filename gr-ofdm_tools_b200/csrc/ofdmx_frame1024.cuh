@@ -140,6 +140,8 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
     uint8_t *hb = lut + 64;
     uint8_t *syms = hb + ((p.hl + 15) & ~15);
     uint8_t *pk = syms + ((p.max_pkt_syms + 15) & ~15);
+    uint8_t *ks = pk + ((p.max_pkt_bytes + 15) & ~15);         // scrambler keystream
+    __shared__ uint32_t s_crc_tab[256], s_crc_pow[256];
     __shared__ float2 wacc[F1K_THREADS / 32][4];
     __shared__ float wbest[F1K_THREADS / 32];
     __shared__ int wbestg[F1K_THREADS / 32];
@@ -152,6 +154,8 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
         sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
         tws[i] = make_float2(cs, sn);
     }
+    for (int i = tid; i < p.max_pkt_bytes; i += NT) ks[i] = p.keystream[i];
+    if (tid < 256) { s_crc_tab[tid] = p.crc_tab[tid]; s_crc_pow[tid] = p.crc_pow[tid]; }
     if (tid < 64) {
         lut[tid] = p.lut_p[tid];
         ipts[tid] = (tid < (1 << BPS_P)) ? p.inv_ppts[tid] : make_float2(0.f, 0.f);
@@ -189,6 +193,7 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
         const float2 *Y1 = T, *Y2 = T + F1K_SLOT, *Y3 = T + 2 * F1K_SLOT;
         // ---- ofdm_chanest_vcvc: integer carrier offset, B(g) = |sum_k conj(Y1[k+g]) conj(cv[k]) Y2[k+g]|
         const int ng = (p.gpos - p.gneg) / 2 + 1;
+        int off_local = 0;
         if (ng <= 4) {
             // few candidates (max_carr_offset given): every thread takes one cv term for all candidates
             float2 acc[4];
@@ -215,18 +220,24 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                 for (int gi = 0; gi < 4; gi++) wacc[wid][gi] = acc[gi];
             }
             __syncthreads();
-            if (tid == 0) {
+            if (wid == 0) {
+                // warp 0 folds the per-warp partial sums (lane = source warp) and picks the first maximum
                 float b = 0.f;
                 int g = 0;
-                for (int gi = 0; gi < ng; gi++) {
-                    float2 sacc = make_float2(0.f, 0.f);
-                    for (int w = 0; w < NW; w++) sacc = cadd(sacc, wacc[w][gi]);
+#pragma unroll
+                for (int gi = 0; gi < 4; gi++) {
+                    float2 sacc = (gi < ng && lane < NW) ? wacc[lane][gi] : make_float2(0.f, 0.f);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sacc.x += __shfl_xor_sync(0xffffffffu, sacc.x, o);
+                        sacc.y += __shfl_xor_sync(0xffffffffu, sacc.y, o);
+                    }
                     const float v = sacc.x * sacc.x + sacc.y * sacc.y;
-                    if (v > b) { b = v; g = p.gneg + 2 * gi; }
+                    if (gi < ng && v > b) { b = v; g = p.gneg + 2 * gi; }
                 }
-                s_off = g;
+                if (lane == 0) s_off = g;
             }
             __syncthreads();
+            off_local = s_off;
         } else {
             float best = 0.f;
             int bestg = 0;
@@ -257,8 +268,9 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                 s_off = g;
             }
             __syncthreads();
+            off_local = s_off;
         }
-        const int off = s_off;
+        const int off = off_local;
         // ---- taps + header symbol (ofdm_frame_equalizer_vcvc + simpledfe, header constellation, symbol 0)
         {
             float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);
@@ -299,7 +311,26 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (p.bps_h == 1 && p.hl >= 32) {
+            // BPSK header (every reference surface): one bit per item; warp 0 gathers the 32 header bits
+            // with a ballot and checks the CRC-8 by linearity (per-bit contributions XOR-reduced)
+            if (wid == 0) {
+                const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1);
+                const unsigned len = bits & 0xFFFu, num = (bits >> 12) & 0xFFFu, crc_rx = bits >> 24;
+                unsigned c8 = (lane < 24 && ((bits >> lane) & 1u)) ? (unsigned)p.crc8_bit[lane] : 0u;
+                for (int o = 16; o > 0; o >>= 1) c8 ^= __shfl_xor_sync(0xffffffffu, c8, o);
+                c8 ^= p.crc8_zero;
+                if (lane == 0) {
+                    int ps = (int)len * 8 / BPS_P;
+                    if (((int)len * 8) % BPS_P) ps++;
+                    int fl = 0, acc = 0, s2 = 0;
+                    if (one_set) fl = (ps + size0 - 1) / size0;
+                    else
+                        while (acc < ps) { fl++; acc += p.occ_size[s2]; s2 = (s2 + 1 == p.n_occ_sets) ? 0 : s2 + 1; }
+                    s_ok = (c8 == crc_rx); s_plen = (int)len; s_pnum = (int)num; s_psyms = ps; s_fsyms = fl;
+                }
+            }
+        } else if (tid == 0) {
             const int bpb = p.bps_h, msk = (1 << bpb) - 1;
             unsigned len = 0, num = 0;
             int k = 0, ok = 1;
@@ -337,6 +368,14 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
             continue;
         }
         rec.flags |= OFDMX_F_COMPLETE;
+        {   // pull the next frame's trigger record towards L1 while this frame is equalised
+            const int jn = j + gridDim.x;
+            if (tid == 0 && jn < nt) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(trig + jn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(cfo + jn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(trig_stream + jn));
+            }
+        }
 
         // ---- payload: rounds of up to W symbols; round 0 already holds payload symbols 0 .. W-4
         int cbase = 0;                                // serialised symbols before payload symbol `first`
@@ -437,7 +476,7 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                     v |= ((unsigned)(syms[si] >> sb) & 1u) << b;
                 }
             }
-            const uint8_t o = (uint8_t)v ^ p.keystream[mb];
+            const uint8_t o = (uint8_t)v ^ ks[mb];
             pk[mb] = o;
             bytes_out[(long long)j * byte_stride + mb] = o;
         }
@@ -446,7 +485,7 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
         if (p.crc_mode) {
             if (nbytes < 4) crc_ok = false;
             else {
-                const uint32_t c = crc32_block(pk, nbytes - 4, p.crc_tab, p.crc_pow, scratch);
+                const uint32_t c = crc32_block(pk, nbytes - 4, s_crc_tab, s_crc_pow, scratch);
                 const uint32_t got = (uint32_t)pk[nbytes - 4] | ((uint32_t)pk[nbytes - 3] << 8)
                                      | ((uint32_t)pk[nbytes - 2] << 16) | ((uint32_t)pk[nbytes - 1] << 24);
                 crc_ok = (c == got);
@@ -461,5 +500,5 @@ static inline size_t frame1024_smem_bytes(int W, int n_occ_u, int hl, int max_pk
 {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     return (size_t)W * F1K_SLOT * 8 + 1024 * 8 + (size_t)n_occ_u * 8 + 64 * 8 + 64 + 64 + al16(hl) + al16(max_pkt_syms)
-           + al16(max_pkt_bytes) + 32;
+           + 2 * al16(max_pkt_bytes) + 32;
 }

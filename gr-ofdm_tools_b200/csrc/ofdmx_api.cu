@@ -4,6 +4,7 @@
 #include "ofdmx_sync.cuh"
 #include "ofdmx_sync_tma.cuh"
 #include "ofdmx_frame1024.cuh"
+#include "ofdmx_frame1024w.cuh"
 #include "ofdmx_chain.cuh"
 
 #include <algorithm>
@@ -61,7 +62,12 @@ struct ofdmx_ctx {
     int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
     bool no_tma = false;            // OFDMX_NO_TMA=1: use the plain-load sync kernel
     bool emit_all = false;          // ofdmx_set_emit_all: frames_out receives every trigger's record
+    bool no_warp_frame = false;     // OFDMX_NO_WARP_FRAME=1: use the CTA-per-frame fft_len-1024 kernel
     bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
+    bool frame1kw = false;          // fft_len 1024 warp-per-frame kernel eligible
+    size_t frame1kw_smem = 0;
+    int frame1kw_warps = FW_WARPS;
+    uint32_t x_2048 = 0;            // x^(8*2048) mod P
     int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
 };
 
@@ -574,6 +580,22 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     for (int l = 0; l < 24; l++)
         crc8_bit[l] = (uint8_t)(crc8_bytes(l < 12 ? (1u << l) : 0u, l < 12 ? 0u : (1u << (l - 12))) ^ kp.crc8_zero);
 
+    std::vector<uint32_t> crc_pow64(32);
+    {
+        uint32_t x = 0x80000000u;
+        for (int l = 31; l >= 0; l--) {
+            crc_pow64[l] = x;
+            for (int b = 0; b < 512; b++) x = h_gf2_mul_x(x);
+        }
+        c->x_2048 = x;      // after 32 steps of 512 bits: x^16384
+    }
+    kp.y1_lo = 0;
+    kp.y1_span = 1;
+    if (!cv_k.empty()) {
+        kp.y1_lo = *std::min_element(cv_k.begin(), cv_k.end()) + kp.gneg;
+        kp.y1_span = *std::max_element(cv_k.begin(), cv_k.end()) + kp.gpos - kp.y1_lo + 1;
+    }
+
 #define UP(vec, field)                                          \
     if ((rc = upload(c, vec, &kp.field)) != 0) return bail(rc);
     UP(tw, tw) UP(occ_bins, occ_bins) UP(occ_base, occ_base) UP(occ_size, occ_size) UP(occ_u, occ_u)
@@ -581,7 +603,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(pil_size, pil_size) UP(pil_sym, pil_sym) UP(pil_sym_base, pil_sym_base) UP(sw1, sw1) UP(sw2, sw2)
     UP(cv_k, cv_k) UP(cv_conj, cv_conj) UP(inv_sw2, inv_sw2) UP(hdr_mask, hdr_mask) UP(keystream, keystream)
     UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
-    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit)
+    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64)
 #undef UP
 
     // shared-memory budgets
@@ -609,6 +631,29 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             if (e1 != cudaSuccess)
                 return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(e1)));
         }
+        {
+            const int ngc = (kp.gpos - kp.gneg) / 2 + 1;
+            const bool simple = (kp.n_occ_sets == 1 && kp.n_pil_sets <= 1 && !kp.pil_in_occ);
+            c->frame1kw_warps = FW_WARPS;
+            while (c->frame1kw_warps > 4 && frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, kp.max_pkt_bytes, c->frame1kw_warps) > 227 * 1024)
+                c->frame1kw_warps--;
+            c->frame1kw_smem = frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, kp.max_pkt_bytes, c->frame1kw_warps);
+            c->frame1kw = (N == 1024 && simple && ngc <= 4 && kp.bps_h == 1 && c->hl >= 32 && c->hl <= 1024
+                           && (occ_size[0] * kp.bps_p) % 8 == 0 && c->frame1kw_smem <= 227 * 1024);
+            if (c->frame1kw) {
+                cudaError_t e1 = cudaSuccess;
+#define FW_ATTR(B, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_frame1024w_kernel<B, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
+                switch (kp.bps_p) {
+                case 1: FW_ATTR(1, false) FW_ATTR(1, true) break;
+                case 2: FW_ATTR(2, false) FW_ATTR(2, true) break;
+                case 3: FW_ATTR(3, false) FW_ATTR(3, true) break;
+                case 4: FW_ATTR(4, false) FW_ATTR(4, true) break;
+                default: FW_ATTR(6, false) FW_ATTR(6, true) break;
+                }
+#undef FW_ATTR
+                if (e1 != cudaSuccess) c->frame1kw = false;
+            }
+        }
         c->sync_tma_smem = sync_tma_smem_bytes(N);
         if (N >= 32 && cudaFuncSetAttribute(sync_metric_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_tma_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -630,6 +675,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                              cudaGetErrorString(cudaGetLastError())));
     }
     if (const char *fg = getenv("OFDMX_FORCE_GENERIC")) c->force_generic = (fg[0] == '1');
+    if (const char *nw = getenv("OFDMX_NO_WARP_FRAME")) c->no_warp_frame = (nw[0] == '1');
     c->no_tma = true;   // the plain-load kernel is currently the faster one; OFDMX_USE_TMA=1 selects the TMA ring kernel
     if (const char *ut = getenv("OFDMX_USE_TMA")) c->no_tma = (ut[0] != '1');
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -743,7 +789,26 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     const float2 *smp = (const float2 *)samples_dev;
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
     ofdmx_ctx *ctx_ = c;
-    if (c->frame1k_warps > 0 && !c->force_generic) {
+    if (c->frame1kw && !c->force_generic && !c->no_warp_frame) {
+        KT(K_FRAME);
+#define FW_LAUNCH(B)                                                                                               \
+    do {                                                                                                           \
+        if (z_out) rx_frame1024w_kernel<B, true><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(               \
+            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,         \
+            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048);                                         \
+        else rx_frame1024w_kernel<B, false><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(                    \
+            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,         \
+            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048);                                         \
+    } while (0)
+        switch (c->kp.bps_p) {
+        case 1: FW_LAUNCH(1); break;
+        case 2: FW_LAUNCH(2); break;
+        case 3: FW_LAUNCH(3); break;
+        case 4: FW_LAUNCH(4); break;
+        default: FW_LAUNCH(6); break;
+        }
+#undef FW_LAUNCH
+    } else if (c->frame1k_warps > 0 && !c->force_generic) {
         KT(K_FRAME);
 #define F1K_LAUNCH3(B, S, Z)                                                                                       \
     rx_frame1024_kernel<B, S, Z><<<c->sm_count * 2, F1K_THREADS, c->frame1k_smem, st>>>(                           \

@@ -1,0 +1,313 @@
+// ofdmx_frame1024w.cuh -- K1+K3+K4, fft_len 1024, ONE WARP PER FRAME.
+//
+// The CTA-per-frame kernel (ofdmx_frame1024.cuh) spends ~40 % of its instructions on redundancy: ten
+// warps each run the per-frame scalar code, the header/CRC/pack phases and wait at ~10 block barriers
+// per frame.  Here a frame belongs to a single warp, which streams its OFDM symbols one at a time:
+//     load + derotate + 1024-point register FFT (f1k_symbol)  ->  equalise/demap the symbol with the
+//     lanes spread over the carriers  ->  pack + descramble its bytes
+// keeping only one symbol (8.5 KB), the channel state (4.8 KB) and the packet bytes in shared memory.
+// There is no block-level synchronisation after the prologue; 13 independent warps per SM sit in
+// different phases (FP32-heavy FFT, LDS-heavy equaliser, integer CRC) and fill each other's stalls.
+//
+// Preconditions checked by the host (otherwise the CTA-per-frame kernel runs): one carrier set, no pilot
+// inside the occupied set, BPSK header with >= 32 items, <= 4 integer-offset candidates
+// (max_carr_offset given), bits per OFDM symbol a multiple of 8, <= 1024 occupied carriers.
+#pragma once
+#include "ofdmx_frame1024.cuh"
+
+#define FW_WARPS 13
+#define FW_THREADS (FW_WARPS * 32)
+
+// zlib CRC-32 of msg[0..len) by one warp: 64-byte chunks per lane inside 2048-byte super-chunks (leading
+// zero padding, init folded into the first 4 bytes), terms shifted by x^(512*(31-lane)) and XOR-reduced.
+__device__ __forceinline__ uint32_t crc32_warp(const uint8_t *msg, int len, const uint32_t *tab,
+                                               const uint32_t *pow64, uint32_t x_2048, int lane)
+{
+    if (len < 4) {
+        uint32_t c = 0xFFFFFFFFu;
+        for (int i = 0; i < len; i++) c = tab[(c ^ msg[i]) & 0xFF] ^ (c >> 8);
+        return c ^ 0xFFFFFFFFu;
+    }
+    uint32_t total = 0;
+    int done = 0;
+    int first = len & 2047;
+    if (first == 0) first = 2048;
+    while (done < len) {
+        const int clen = done ? 2048 : first;
+        const int pad = 2048 - clen;
+        uint32_t reg = 0;
+        for (int q = 0; q < 64; q++) {
+            const int vp = lane * 64 + q - pad;
+            if (vp < 0) continue;
+            const int gi = done + vp;
+            uint8_t b = msg[gi];
+            if (gi < 4) b ^= 0xFF;
+            reg = tab[(reg ^ b) & 0xFF] ^ (reg >> 8);
+        }
+        uint32_t term = reg ? gf2_mul(reg, pow64[lane]) : 0u;
+        for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
+        total = (total ? gf2_mul(total, x_2048) : 0u) ^ term;
+        done += clen;
+    }
+    return total ^ 0xFFFFFFFFu;
+}
+
+template <int BPS_P, bool WANT_Z>
+__global__ void __launch_bounds__(FW_THREADS, 1)
+rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
+                     const long long *__restrict__ trig, const int *__restrict__ trig_stream,
+                     const float *__restrict__ cfo, const int *__restrict__ stream_start,
+                     const int *__restrict__ n_trig_dev, ofdmx_frame *__restrict__ spec,
+                     uint8_t *__restrict__ bytes_out, long long byte_stride, float2 *__restrict__ z_out,
+                     long long z_stride, uint32_t x_2048)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NTH = blockDim.x, NWARP = blockDim.x >> 5;
+    const int nu = p.n_occ_u;
+    const int hsz = (max(nu, p.y1_span) + 1) & ~1;              // H area also parks the Y1 bins chanest needs
+    // ---- CTA-shared tables
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024]
+    float2 *ipts = tws + 1024;                                    // [64]
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [256]
+    uint32_t *s_pow = s_tab + 256;                                // [32]
+    uint16_t *s_occ = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] union bin of carrier u
+    uint16_t *s_pos = s_occ + ((nu + 7) & ~7);                    // [nu] position in the serialiser order
+    uint8_t *lut = reinterpret_cast<uint8_t *>(s_pos + ((nu + 7) & ~7));   // [64]
+    uint8_t *ks = lut + 64;                                       // [max_pkt_bytes]
+    // ---- per-warp buffers
+    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64
+                                + (size_t)((p.max_pkt_bytes + 15) & ~15);
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (size_t)((p.max_pkt_bytes + 15) & ~15)
+                            + (size_t)((nu + 15) & ~15) + 64;
+    unsigned char *wbase = smem_raw + ((shared_bytes + 15) & ~(size_t)15) + (size_t)wid * per_warp;
+    float2 *Y = reinterpret_cast<float2 *>(wbase);                // F1K_SLOT
+    float2 *Hs = Y + F1K_SLOT;                                    // hsz
+    uint8_t *pk = reinterpret_cast<uint8_t *>(Hs + hsz);          // packet bytes
+    uint8_t *dec = pk + ((p.max_pkt_bytes + 15) & ~15);           // decisions of the current symbol
+    uint8_t *hb = dec + ((nu + 15) & ~15);                        // 64 header items
+
+    for (int i = tid; i < 1024; i += NTH) {
+        const int k1 = i >> 5, b = i & 31;
+        float sn, cs;
+        sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
+        tws[i] = make_float2(cs, sn);
+    }
+    for (int i = tid; i < p.max_pkt_bytes; i += NTH) ks[i] = p.keystream[i];
+    for (int i = tid; i < nu; i += NTH) { s_occ[i] = (uint16_t)p.occ_u[i]; s_pos[i] = (uint16_t)p.pos_su[i]; }
+    if (tid < 256) s_tab[tid] = p.crc_tab[tid];
+    if (tid < 32) s_pow[tid] = p.crc_pow64[tid];
+    if (tid < 64) {
+        lut[tid] = p.lut_p[tid];
+        ipts[tid] = (tid < (1 << BPS_P)) ? p.inv_ppts[tid] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    const int nt = *n_trig_dev;
+    const int N = 1024, D = p.D;
+    const float al = p.alpha, oma = 1.0f - p.alpha;
+    const int size0 = p.occ_size[0];
+    const int sym_bytes = size0 * BPS_P / 8;
+    const int ng = (p.gpos - p.gneg) / 2 + 1;
+    const int y1_lo = p.y1_lo;                                    // first shifted bin parked from Y1
+
+    for (int j = blockIdx.x * NWARP + wid; j < nt; j += gridDim.x * NWARP) {
+        const int st = trig_stream[j];
+        const long long t = trig[j];
+        const float2 *r = samples + (long long)st * stride;
+        const int jend = stream_start[st + 1];
+        ofdmx_frame rec;
+        rec.trigger = t; rec.cfo = cfo[j]; rec.stream = st; rec.flags = 0; rec.pkt_len = 0; rec.pkt_num = 0;
+        rec.frame_syms = 0; rec.carr_offset = 0; rec.slot = (uint32_t)j;
+        const long long rem = n - t;
+        if (3LL * D > rem) {
+            if (lane == 0) spec[j] = rec;
+            continue;
+        }
+        const long long tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
+        const double kappa = (double)rec.cfo * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+
+        // ---- sync word 1: transform, park the bins chanest needs in the (still unused) H area
+        long long i0 = t + p.cp;
+        f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+        __syncwarp();
+        for (int q = lane; q < p.y1_span; q += 32) Hs[q] = Y[(y1_lo + q) ^ 512];
+        __syncwarp();
+        // ---- sync word 2, integer carrier offset (ofdm_chanest_vcvc)
+        i0 += D;
+        f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+        __syncwarp();
+        int off = 0;
+        {
+            float2 acc[4];
+#pragma unroll
+            for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
+            for (int c = lane; c < p.n_cv; c += 32) {
+                const int kc = p.cv_k[c];
+                const float2 cvc = p.cv_conj[c];
+#pragma unroll
+                for (int gi = 0; gi < 4; gi++)
+                    if (gi < ng) {
+                        const int k = kc + p.gneg + 2 * gi;
+                        acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ 512], Hs[k - y1_lo]), cvc));
+                    }
+            }
+            float b = 0.f;
+#pragma unroll
+            for (int gi = 0; gi < 4; gi++) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc[gi].x += __shfl_xor_sync(0xffffffffu, acc[gi].x, o);
+                    acc[gi].y += __shfl_xor_sync(0xffffffffu, acc[gi].y, o);
+                }
+                const float v = acc[gi].x * acc[gi].x + acc[gi].y * acc[gi].y;
+                if (gi < ng && v > b) { b = v; off = p.gneg + 2 * gi; }
+            }
+        }
+        __syncwarp();
+        // ---- channel taps H[k] = Y2[k+off] / sw2[k] (overwrites the parked Y1 bins)
+        for (int u = lane; u < nu; u += 32) {
+            const int k = s_occ[u];
+            const int src = k + off;
+            float2 Hk = make_float2(0.f, 0.f);
+            if (src >= 0 && src < N) Hk = cmul(Y[src ^ 512], p.inv_sw2[k]);
+            Hs[u] = Hk;
+        }
+        __syncwarp();
+        // ---- header symbol: frame equaliser (offset shift + phase fix) + simpledfe with the BPSK header
+        i0 += D;
+        f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+        __syncwarp();
+        {
+            float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);
+            if (off != 0) {
+                float sn, cs;
+                sincosf((float)(-TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                pc = make_float2(cs, sn);
+                sincosf((float)(TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                rot = make_float2(cs, sn);
+            }
+            for (int u = lane; u < nu; u += 32) {
+                const int src = (int)s_occ[u] + off;
+                float2 y = make_float2(0.f, 0.f);
+                if (src >= 0 && src < N) y = cmul(Y[src ^ 512], pc);
+                float2 Hk = Hs[u];
+                const float2 z = cdivf(y, Hk);
+                const int d = z.x > 0.f;
+                const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
+                Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                const int pos = s_pos[u];
+                if (pos < 64) hb[pos] = (uint8_t)d ^ p.hdr_mask[pos];
+                if (WANT_Z) z_out[(long long)j * z_stride + pos] = z;
+                Hs[u] = cmul(Hk, rot);
+            }
+        }
+        __syncwarp();
+        int ok, plen, pnum, psyms, fsyms;
+        {
+            const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1);
+            plen = (int)(bits & 0xFFFu);
+            pnum = (int)((bits >> 12) & 0xFFFu);
+            unsigned c8 = (lane < 24 && ((bits >> lane) & 1u)) ? (unsigned)p.crc8_bit[lane] : 0u;
+            for (int o = 16; o > 0; o >>= 1) c8 ^= __shfl_xor_sync(0xffffffffu, c8, o);
+            ok = ((c8 ^ p.crc8_zero) == (bits >> 24));
+            psyms = (plen * 8 + BPS_P - 1) / BPS_P;
+            fsyms = (psyms + size0 - 1) / size0;
+        }
+        rec.flags = OFDMX_F_HDR_SEEN;
+        rec.carr_offset = (int16_t)off;
+        rec.pkt_len = (uint16_t)plen;
+        rec.pkt_num = (uint16_t)pnum;
+        rec.frame_syms = (uint16_t)fsyms;
+        if (!ok) {
+            if (lane == 0) spec[j] = rec;
+            continue;
+        }
+        rec.flags |= OFDMX_F_HDR_OK;
+        if ((long long)(3 + fsyms) * D > rem || plen > p.max_pkt_bytes) {
+            if (lane == 0) spec[j] = rec;
+            continue;
+        }
+        rec.flags |= OFDMX_F_COMPLETE;
+        // ---- payload symbols, one at a time
+        const int nbytes = min(psyms * BPS_P / 8, p.max_pkt_bytes);
+        for (int i = 0; i < fsyms; i++) {
+            i0 += D;
+            f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+            __syncwarp();
+            float2 pc = make_float2(1.f, 0.f);
+            if (off != 0) {
+                float sn, cs;
+                sincosf((float)(-TWO_PI_D * off * p.cp / N * (i + 1)), &sn, &cs);
+                pc = make_float2(cs, sn);
+            }
+            const int cb = i * size0;
+            for (int u = lane; u < nu; u += 32) {
+                const int src = (int)s_occ[u] + off;
+                float2 y = make_float2(0.f, 0.f);
+                if (src >= 0 && src < N) {
+                    y = Y[src ^ 512];
+                    if (off != 0) y = cmul(y, pc);
+                }
+                float2 Hk = Hs[u];
+                const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
+                const float2 nn = cmul_conj(y, Hk);
+                const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
+                const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                const float2 q = cmul(y, ipts[d]);
+                Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                const int pos = s_pos[u];
+                dec[pos] = (uint8_t)d;
+                if (WANT_Z) {
+                    const int idx = cb + pos;
+                    if (idx < psyms && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
+                }
+            }
+            __syncwarp();
+            // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes
+            const int b0 = i * sym_bytes;
+            for (int m = lane; m < sym_bytes; m += 32) {
+                const int gb = b0 + m;
+                if (gb >= nbytes) break;
+                unsigned v = 0;
+                if (BPS_P == 4) v = (unsigned)dec[2 * m] | ((unsigned)dec[2 * m + 1] << 4);
+                else if (BPS_P == 2)
+                    v = (unsigned)dec[4 * m] | ((unsigned)dec[4 * m + 1] << 2) | ((unsigned)dec[4 * m + 2] << 4) | ((unsigned)dec[4 * m + 3] << 6);
+                else if (BPS_P == 1) {
+                    for (int b = 0; b < 8; b++) v |= (unsigned)dec[8 * m + b] << b;
+                } else {
+                    for (int b = 0; b < 8; b++) {
+                        const int bi = m * 8 + b;
+                        const int si = bi / BPS_P, sb = bi - si * BPS_P;
+                        v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
+                    }
+                }
+                const uint8_t o = (uint8_t)v ^ ks[gb];
+                pk[gb] = o;
+                bytes_out[(long long)j * byte_stride + gb] = o;
+            }
+            __syncwarp();
+        }
+        bool crc_ok = true;
+        if (p.crc_mode) {
+            if (nbytes < 4) crc_ok = false;
+            else {
+                const uint32_t c = crc32_warp(pk, nbytes - 4, s_tab, s_pow, x_2048, lane);
+                const uint32_t got = (uint32_t)pk[nbytes - 4] | ((uint32_t)pk[nbytes - 3] << 8)
+                                     | ((uint32_t)pk[nbytes - 2] << 16) | ((uint32_t)pk[nbytes - 1] << 24);
+                crc_ok = (c == got);
+            }
+        }
+        if (crc_ok) rec.flags |= OFDMX_F_CRC_OK;
+        if (lane == 0) spec[j] = rec;
+        __syncwarp();
+    }
+}
+
+static inline size_t frame1024w_smem_bytes(int n_occ_u, int y1_span, int max_pkt_bytes, int warps)
+{
+    auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t nu8 = (size_t)((n_occ_u + 7) & ~7);
+    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64 + al16(max_pkt_bytes);
+    const size_t hsz = (size_t)((std::max(n_occ_u, y1_span) + 1) & ~1);
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + al16(max_pkt_bytes) + al16(n_occ_u) + 64;
+    return al16(shared_bytes) + (size_t)warps * per_warp + 16;
+}

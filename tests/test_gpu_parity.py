@@ -344,3 +344,21 @@ def test_facade_loopbacks():
     s2, _ = radio.tx(pk[:2])
     r2 = radio.rx(torch.cat([pad, s2, pad]))
     assert list(r2.frames["pkt_num"]) == [7, 8]
+
+
+def test_frame_kernel_variants_agree(monkeypatch):
+    """fft_len 1024: warp-per-frame kernel (default when eligible) vs CTA-per-frame kernel vs oracle."""
+    cfg = cm.cfg_c3()
+    rng = np.random.default_rng(66)
+    pk, fr = _frames(cfg, rng, 7, 1500)
+    x = cm.channel(fr, rng, gaps=(0, 0), lead=100, tail=3000, snr_db=40.0, cfo=0.3 - 2, fft_len=1024, taps=cm.MULTIPATH)
+    warp = cm.make_phy(cfg, max_pkt_bytes=1504).rx(_to_dev(x), want_z=True)
+    monkeypatch.setenv("OFDMX_NO_WARP_FRAME", "1")
+    cta = cm.make_phy(cfg, max_pkt_bytes=1504).rx(_to_dev(x), want_z=True)
+    assert np.array_equal(warp.frames, cta.frames) and warp.payloads() == cta.payloads() == pk
+    assert np.all(warp.frames["carr_offset"] == -2)
+    assert cm.rel_evm(warp.z.cpu().numpy()[:7, :3608], cta.z.cpu().numpy()[:7, :3608]) < 1e-5
+    ref = cm.make_oracle(cfg).rx(x, byte_stride=1504, want_z=True, max_pkt_syms=1504 * 2 + 1)
+    assert np.array_equal(warp.frames["trigger"], ref["frames"]["trigger"])
+    for i in range(7):
+        assert cm.rel_evm(warp.z.cpu().numpy()[i, :3608], ref["z"][i, :3608]) <= 1e-4

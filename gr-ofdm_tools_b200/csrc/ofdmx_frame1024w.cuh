@@ -126,165 +126,157 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         const long long tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
         const double kappa = (double)rec.cfo * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
 
-        // ---- sync word 1: transform, park the bins chanest needs in the (still unused) H area
-        long long i0 = t + p.cp;
-        f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
-        __syncwarp();
-        for (int q = lane; q < p.y1_span; q += 32) Hs[q] = Y[(y1_lo + q) ^ 512];
-        __syncwarp();
-        // ---- sync word 2, integer carrier offset (ofdm_chanest_vcvc)
-        i0 += D;
-        f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
-        __syncwarp();
-        int off = 0;
-        {
-            float2 acc[4];
-#pragma unroll
-            for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
-            for (int c = lane; c < p.n_cv; c += 32) {
-                const int kc = p.cv_k[c];
-                const float2 cvc = p.cv_conj[c];
-#pragma unroll
-                for (int gi = 0; gi < 4; gi++)
-                    if (gi < ng) {
-                        const int k = kc + p.gneg + 2 * gi;
-                        acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ 512], Hs[k - y1_lo]), cvc));
-                    }
-            }
-            float b = 0.f;
-#pragma unroll
-            for (int gi = 0; gi < 4; gi++) {
-                for (int o = 16; o > 0; o >>= 1) {
-                    acc[gi].x += __shfl_xor_sync(0xffffffffu, acc[gi].x, o);
-                    acc[gi].y += __shfl_xor_sync(0xffffffffu, acc[gi].y, o);
-                }
-                const float v = acc[gi].x * acc[gi].x + acc[gi].y * acc[gi].y;
-                if (gi < ng && v > b) { b = v; off = p.gneg + 2 * gi; }
-            }
-        }
-        __syncwarp();
-        // ---- channel taps H[k] = Y2[k+off] / sw2[k] (overwrites the parked Y1 bins)
-        for (int u = lane; u < nu; u += 32) {
-            const int k = s_occ[u];
-            const int src = k + off;
-            float2 Hk = make_float2(0.f, 0.f);
-            if (src >= 0 && src < N) Hk = cmul(Y[src ^ 512], p.inv_sw2[k]);
-            Hs[u] = Hk;
-        }
-        __syncwarp();
-        // ---- header symbol: frame equaliser (offset shift + phase fix) + simpledfe with the BPSK header
-        i0 += D;
-        f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
-        __syncwarp();
-        {
-            float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);
-            if (off != 0) {
-                float sn, cs;
-                sincosf((float)(-TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
-                pc = make_float2(cs, sn);
-                sincosf((float)(TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
-                rot = make_float2(cs, sn);
-            }
-            for (int u = lane; u < nu; u += 32) {
-                const int src = (int)s_occ[u] + off;
-                float2 y = make_float2(0.f, 0.f);
-                if (src >= 0 && src < N) y = cmul(Y[src ^ 512], pc);
-                float2 Hk = Hs[u];
-                const float2 z = cdivf(y, Hk);
-                const int d = z.x > 0.f;
-                const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
-                Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
-                const int pos = s_pos[u];
-                if (pos < 64) hb[pos] = (uint8_t)d ^ p.hdr_mask[pos];
-                if (WANT_Z) z_out[(long long)j * z_stride + pos] = z;
-                Hs[u] = cmul(Hk, rot);
-            }
-        }
-        __syncwarp();
-        int ok, plen, pnum, psyms, fsyms;
-        {
-            const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1);
-            plen = (int)(bits & 0xFFFu);
-            pnum = (int)((bits >> 12) & 0xFFFu);
-            unsigned c8 = (lane < 24 && ((bits >> lane) & 1u)) ? (unsigned)p.crc8_bit[lane] : 0u;
-            for (int o = 16; o > 0; o >>= 1) c8 ^= __shfl_xor_sync(0xffffffffu, c8, o);
-            ok = ((c8 ^ p.crc8_zero) == (bits >> 24));
-            psyms = (plen * 8 + BPS_P - 1) / BPS_P;
-            fsyms = (psyms + size0 - 1) / size0;
-        }
-        rec.flags = OFDMX_F_HDR_SEEN;
-        rec.carr_offset = (int16_t)off;
-        rec.pkt_len = (uint16_t)plen;
-        rec.pkt_num = (uint16_t)pnum;
-        rec.frame_syms = (uint16_t)fsyms;
-        if (!ok) {
-            if (lane == 0) spec[j] = rec;
-            continue;
-        }
-        rec.flags |= OFDMX_F_HDR_OK;
-        if ((long long)(3 + fsyms) * D > rem || plen > p.max_pkt_bytes) {
-            if (lane == 0) spec[j] = rec;
-            continue;
-        }
-        rec.flags |= OFDMX_F_COMPLETE;
-        // ---- payload symbols, one at a time
-        const int nbytes = min(psyms * BPS_P / 8, p.max_pkt_bytes);
-        for (int i = 0; i < fsyms; i++) {
-            i0 += D;
+        // One loop over the frame's OFDM symbols with a SINGLE call site of the (large, straight-line)
+        // FFT code, so that all warps of the SM share one copy in the instruction cache.
+        int off = 0, ok = 0, plen = 0, pnum = 0, psyms = 0, fsyms = 0, nbytes = 0;
+        int nsym = 3;                                   // grows to 3 + fsyms once the header is decoded
+        bool dead = false;
+        for (int sidx = 0; sidx < nsym; sidx++) {
+            const long long i0 = t + (long long)sidx * D + p.cp;
             f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
             __syncwarp();
-            float2 pc = make_float2(1.f, 0.f);
-            if (off != 0) {
-                float sn, cs;
-                sincosf((float)(-TWO_PI_D * off * p.cp / N * (i + 1)), &sn, &cs);
-                pc = make_float2(cs, sn);
-            }
-            const int cb = i * size0;
-            for (int u = lane; u < nu; u += 32) {
-                const int src = (int)s_occ[u] + off;
-                float2 y = make_float2(0.f, 0.f);
-                if (src >= 0 && src < N) {
-                    y = Y[src ^ 512];
-                    if (off != 0) y = cmul(y, pc);
+            if (sidx == 0) {
+                // sync word 1: park the bins chanest needs in the (still unused) H area
+                for (int q = lane; q < p.y1_span; q += 32) Hs[q] = Y[(y1_lo + q) ^ 512];
+            } else if (sidx == 1) {
+                // sync word 2: integer carrier offset (ofdm_chanest_vcvc), then the channel taps
+                float2 acc[4];
+#pragma unroll
+                for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
+                for (int c = lane; c < p.n_cv; c += 32) {
+                    const int kc = p.cv_k[c];
+                    const float2 cvc = p.cv_conj[c];
+#pragma unroll
+                    for (int gi = 0; gi < 4; gi++)
+                        if (gi < ng) {
+                            const int k = kc + p.gneg + 2 * gi;
+                            acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ 512], Hs[k - y1_lo]), cvc));
+                        }
                 }
-                float2 Hk = Hs[u];
-                const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
-                const float2 nn = cmul_conj(y, Hk);
-                const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
-                const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
-                const float2 q = cmul(y, ipts[d]);
-                Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
-                const int pos = s_pos[u];
-                dec[pos] = (uint8_t)d;
-                if (WANT_Z) {
-                    const int idx = cb + pos;
-                    if (idx < psyms && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
+                float b = 0.f;
+#pragma unroll
+                for (int gi = 0; gi < 4; gi++) {
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acc[gi].x += __shfl_xor_sync(0xffffffffu, acc[gi].x, o);
+                        acc[gi].y += __shfl_xor_sync(0xffffffffu, acc[gi].y, o);
+                    }
+                    const float v = acc[gi].x * acc[gi].x + acc[gi].y * acc[gi].y;
+                    if (gi < ng && v > b) { b = v; off = p.gneg + 2 * gi; }
                 }
-            }
-            __syncwarp();
-            // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes
-            const int b0 = i * sym_bytes;
-            for (int m = lane; m < sym_bytes; m += 32) {
-                const int gb = b0 + m;
-                if (gb >= nbytes) break;
-                unsigned v = 0;
-                if (BPS_P == 4) v = (unsigned)dec[2 * m] | ((unsigned)dec[2 * m + 1] << 4);
-                else if (BPS_P == 2)
-                    v = (unsigned)dec[4 * m] | ((unsigned)dec[4 * m + 1] << 2) | ((unsigned)dec[4 * m + 2] << 4) | ((unsigned)dec[4 * m + 3] << 6);
-                else if (BPS_P == 1) {
-                    for (int b = 0; b < 8; b++) v |= (unsigned)dec[8 * m + b] << b;
-                } else {
-                    for (int b = 0; b < 8; b++) {
-                        const int bi = m * 8 + b;
-                        const int si = bi / BPS_P, sb = bi - si * BPS_P;
-                        v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
+                __syncwarp();
+                // H[k] = Y2[k+off] / sw2[k] (overwrites the parked Y1 bins)
+                for (int u = lane; u < nu; u += 32) {
+                    const int k = s_occ[u];
+                    const int src = k + off;
+                    float2 Hk = make_float2(0.f, 0.f);
+                    if (src >= 0 && src < N) Hk = cmul(Y[src ^ 512], p.inv_sw2[k]);
+                    Hs[u] = Hk;
+                }
+            } else if (sidx == 2) {
+                // header symbol: frame equaliser (offset shift + phase fix) + simpledfe with the BPSK header
+                float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);
+                if (off != 0) {
+                    float sn, cs;
+                    sincosf((float)(-TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                    pc = make_float2(cs, sn);
+                    sincosf((float)(TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                    rot = make_float2(cs, sn);
+                }
+                for (int u = lane; u < nu; u += 32) {
+                    const int src = (int)s_occ[u] + off;
+                    float2 y = make_float2(0.f, 0.f);
+                    if (src >= 0 && src < N) y = cmul(Y[src ^ 512], pc);
+                    float2 Hk = Hs[u];
+                    const float2 z = cdivf(y, Hk);
+                    const int d = z.x > 0.f;
+                    const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
+                    Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                    const int pos = s_pos[u];
+                    if (pos < 64) hb[pos] = (uint8_t)d ^ p.hdr_mask[pos];
+                    if (WANT_Z) z_out[(long long)j * z_stride + pos] = z;
+                    Hs[u] = cmul(Hk, rot);
+                }
+                __syncwarp();
+                const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1);
+                plen = (int)(bits & 0xFFFu);
+                pnum = (int)((bits >> 12) & 0xFFFu);
+                unsigned c8 = (lane < 24 && ((bits >> lane) & 1u)) ? (unsigned)p.crc8_bit[lane] : 0u;
+                for (int o = 16; o > 0; o >>= 1) c8 ^= __shfl_xor_sync(0xffffffffu, c8, o);
+                ok = ((c8 ^ p.crc8_zero) == (bits >> 24));
+                psyms = (plen * 8 + BPS_P - 1) / BPS_P;
+                fsyms = (psyms + size0 - 1) / size0;
+                rec.flags = OFDMX_F_HDR_SEEN;
+                rec.carr_offset = (int16_t)off;
+                rec.pkt_len = (uint16_t)plen;
+                rec.pkt_num = (uint16_t)pnum;
+                rec.frame_syms = (uint16_t)fsyms;
+                if (!ok) { dead = true; break; }
+                rec.flags |= OFDMX_F_HDR_OK;
+                if ((long long)(3 + fsyms) * D > rem || plen > p.max_pkt_bytes) { dead = true; break; }
+                rec.flags |= OFDMX_F_COMPLETE;
+                nbytes = min(psyms * BPS_P / 8, p.max_pkt_bytes);
+                nsym = 3 + fsyms;
+            } else {
+                // payload symbol i: equalise + demap with the lanes over the carriers, then pack its bytes
+                const int i = sidx - 3;
+                float2 pc = make_float2(1.f, 0.f);
+                if (off != 0) {
+                    float sn, cs;
+                    sincosf((float)(-TWO_PI_D * off * p.cp / N * (i + 1)), &sn, &cs);
+                    pc = make_float2(cs, sn);
+                }
+                const int cb = i * size0;
+                for (int u = lane; u < nu; u += 32) {
+                    const int src = (int)s_occ[u] + off;
+                    float2 y = make_float2(0.f, 0.f);
+                    if (src >= 0 && src < N) {
+                        y = Y[src ^ 512];
+                        if (off != 0) y = cmul(y, pc);
+                    }
+                    float2 Hk = Hs[u];
+                    const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
+                    const float2 nn = cmul_conj(y, Hk);
+                    const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
+                    const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                    const float2 q = cmul(y, ipts[d]);
+                    Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                    const int pos = s_pos[u];
+                    dec[pos] = (uint8_t)d;
+                    if (WANT_Z) {
+                        const int idx = cb + pos;
+                        if (idx < psyms && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
                     }
                 }
-                const uint8_t o = (uint8_t)v ^ ks[gb];
-                pk[gb] = o;
-                bytes_out[(long long)j * byte_stride + gb] = o;
+                __syncwarp();
+                // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes
+                const int b0 = i * sym_bytes;
+                for (int m = lane; m < sym_bytes; m += 32) {
+                    const int gb = b0 + m;
+                    if (gb >= nbytes) break;
+                    unsigned v = 0;
+                    if (BPS_P == 4) v = (unsigned)dec[2 * m] | ((unsigned)dec[2 * m + 1] << 4);
+                    else if (BPS_P == 2)
+                        v = (unsigned)dec[4 * m] | ((unsigned)dec[4 * m + 1] << 2) | ((unsigned)dec[4 * m + 2] << 4) | ((unsigned)dec[4 * m + 3] << 6);
+                    else if (BPS_P == 1) {
+                        for (int b = 0; b < 8; b++) v |= (unsigned)dec[8 * m + b] << b;
+                    } else {
+                        for (int b = 0; b < 8; b++) {
+                            const int bi = m * 8 + b;
+                            const int si = bi / BPS_P, sb = bi - si * BPS_P;
+                            v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
+                        }
+                    }
+                    const uint8_t o = (uint8_t)v ^ ks[gb];
+                    pk[gb] = o;
+                    bytes_out[(long long)j * byte_stride + gb] = o;
+                }
             }
             __syncwarp();
+        }
+        if (dead) {
+            if (lane == 0) spec[j] = rec;
+            __syncwarp();
+            continue;
         }
         bool crc_ok = true;
         if (p.crc_mode) {

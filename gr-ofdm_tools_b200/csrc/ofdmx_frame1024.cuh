@@ -21,6 +21,18 @@
 #define F1K_ROW 34                      // float2 per transpose row (272 B: 16-byte aligned, conflict-free)
 #define F1K_SLOT (32 * F1K_ROW)         // float2 per warp buffer (>= 1024)
 
+// exact NCO phasor at item i (piecewise accumulation over the raw triggers); kept out of line: it is only
+// needed for the few samples that follow another trigger inside a frame
+__device__ __noinline__ float2 f1k_exact_phasor(long long i, int j, int jend, const long long *__restrict__ trig,
+                                                const float *__restrict__ cfo)
+{
+    double turns = nco_turns(i, j, jend, trig, cfo, 1024);
+    turns -= rint(turns);
+    float s2, c2;
+    sincospif(2.0f * (float)turns, &s2, &c2);
+    return make_float2(c2, s2);
+}
+
 // One symbol: load + derotate + 1024-point FFT.  Result: Tw[k] = X[k], natural order, k < 1024.
 __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict__ r, long long n, long long i0,
                                            long long t, double kappa, bool slow, int j, int jend,
@@ -39,7 +51,7 @@ __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict
             v[a] = (s >= 0 && s < n) ? __ldg(&r[s]) : make_float2(0.f, 0.f);
         }
     }
-    if (!slow) {
+    {
         // phase(i) = 2 pi kappa (i - t + 1); phasor recurrence over a (step = 32 samples)
         double tb = kappa * (double)(i0 + lane - t + 1);
         tb -= rint(tb);
@@ -50,20 +62,25 @@ __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict
         sincospif(2.0f * (float)tsd, &ssn, &scs);
         float2 ph = make_float2(cs, sn);
         const float2 st = make_float2(scs, ssn);
+        if (!slow) {
 #pragma unroll
-        for (int a = 0; a < 32; a++) {
-            v[a] = cmul(v[a], ph);
-            ph = cmul(ph, st);
-        }
-    } else {
-        // another raw trigger falls inside this symbol: the sample-and-hold value changes mid-symbol
+            for (int a = 0; a < 32; a++) {
+                v[a] = cmul(v[a], ph);
+                ph = cmul(ph, st);
+            }
+        } else {
+            // another raw trigger falls inside (or before) this symbol: the sample-and-hold value changes
+            // there.  Samples before it keep the recurrence; the others get their phase from the piecewise
+            // accumulation (nco_turns).
+            const long long tnx = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
 #pragma unroll
-        for (int a = 0; a < 32; a++) {
-            double turns = nco_turns(i0 + lane + 32 * a, j, jend, trig, cfo, 1024);
-            turns -= rint(turns);
-            float sn, cs;
-            sincospif(2.0f * (float)turns, &sn, &cs);
-            v[a] = cmul(v[a], make_float2(cs, sn));
+            for (int a = 0; a < 32; a++) {
+                const long long i = i0 + lane + 32 * a;
+                float2 pa = ph;
+                if (i >= tnx) pa = f1k_exact_phasor(i, j, jend, trig, cfo);
+                v[a] = cmul(v[a], pa);
+                ph = cmul(ph, st);
+            }
         }
     }
     // n = 32 a + b (b = lane):  y_b[k1] = sum_a x[32 a + b] W32^(a k1)

@@ -226,25 +226,32 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     pc = make_float2(cs, sn);
                 }
                 const int cb = i * size0;
-                for (int u = lane; u < nu; u += 32) {
-                    const int src = (int)s_occ[u] + off;
-                    float2 y = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) {
-                        y = Y[src ^ 512];
-                        if (off != 0) y = cmul(y, pc);
-                    }
-                    float2 Hk = Hs[u];
-                    const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
-                    const float2 nn = cmul_conj(y, Hk);
-                    const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
-                    const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
-                    const float2 q = cmul(y, ipts[d]);
-                    Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
-                    const int pos = s_pos[u];
-                    dec[pos] = (uint8_t)d;
-                    if (WANT_Z) {
-                        const int idx = cb + pos;
-                        if (idx < psyms && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
+                for (int u0 = lane; u0 < nu; u0 += 128) {
+                    // four carriers per lane per trip: independent chains for the scheduler to interleave
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) {
+                        const int u = u0 + 32 * w4;
+                        if (u < nu) {
+                            const int src = (int)s_occ[u] + off;
+                            float2 y = make_float2(0.f, 0.f);
+                            if (src >= 0 && src < N) {
+                                y = Y[src ^ 512];
+                                if (off != 0) y = cmul(y, pc);
+                            }
+                            float2 Hk = Hs[u];
+                            const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
+                            const float2 nn = cmul_conj(y, Hk);
+                            const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
+                            const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                            const float2 q = cmul(y, ipts[d]);
+                            Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                            const int pos = s_pos[u];
+                            dec[pos] = (uint8_t)d;
+                            if (WANT_Z) {
+                                const int idx = cb + pos;
+                                if (idx < psyms && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
+                            }
+                        }
                     }
                 }
                 __syncwarp();

@@ -15,7 +15,7 @@
 #pragma once
 #include "ofdmx_frame1024.cuh"
 
-#define FW_WARPS 13
+#define FW_WARPS 15
 #define FW_THREADS (FW_WARPS * 32)
 
 // zlib CRC-32 of msg[0..len) by one warp: 64-byte chunks per lane inside 2048-byte super-chunks (leading
@@ -77,13 +77,11 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     // ---- per-warp buffers
     const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64
                                 + (size_t)((p.max_pkt_bytes + 15) & ~15);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (size_t)((p.max_pkt_bytes + 15) & ~15)
-                            + (size_t)((nu + 15) & ~15) + 64;
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (size_t)((nu + 15) & ~15) + 64;
     unsigned char *wbase = smem_raw + ((shared_bytes + 15) & ~(size_t)15) + (size_t)wid * per_warp;
     float2 *Y = reinterpret_cast<float2 *>(wbase);                // F1K_SLOT
     float2 *Hs = Y + F1K_SLOT;                                    // hsz
-    uint8_t *pk = reinterpret_cast<uint8_t *>(Hs + hsz);          // packet bytes
-    uint8_t *dec = pk + ((p.max_pkt_bytes + 15) & ~15);           // decisions of the current symbol
+    uint8_t *dec = reinterpret_cast<uint8_t *>(Hs + hsz);         // decisions of the current symbol
     uint8_t *hb = dec + ((nu + 15) & ~15);                        // 64 header items
 
     for (int i = tid; i < 1024; i += NTH) {
@@ -134,6 +132,13 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         for (int sidx = 0; sidx < nsym; sidx++) {
             const long long i0 = t + (long long)sidx * D + p.cp;
             f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+            {   // pull the next symbol's 8 KB towards L2 while this one is processed
+                const long long sn = i0 + D - p.D + lane * 32;
+                if (sn >= 0 && sn + 32 <= n) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r + sn));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r + sn + 16));
+                }
+            }
             __syncwarp();
             if (sidx == 0) {
                 // sync word 1: park the bins chanest needs in the (still unused) H area
@@ -273,9 +278,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                             v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
                         }
                     }
-                    const uint8_t o = (uint8_t)v ^ ks[gb];
-                    pk[gb] = o;
-                    bytes_out[(long long)j * byte_stride + gb] = o;
+                    bytes_out[(long long)j * byte_stride + gb] = (uint8_t)v ^ ks[gb];
                 }
             }
             __syncwarp();
@@ -289,6 +292,9 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         if (p.crc_mode) {
             if (nbytes < 4) crc_ok = false;
             else {
+                // the packet bytes were written by this warp: read them back (L1/L2) for the CRC
+                __syncwarp();
+                const uint8_t *pk = bytes_out + (long long)j * byte_stride;
                 const uint32_t c = crc32_warp(pk, nbytes - 4, s_tab, s_pow, x_2048, lane);
                 const uint32_t got = (uint32_t)pk[nbytes - 4] | ((uint32_t)pk[nbytes - 3] << 8)
                                      | ((uint32_t)pk[nbytes - 2] << 16) | ((uint32_t)pk[nbytes - 1] << 24);
@@ -307,6 +313,6 @@ static inline size_t frame1024w_smem_bytes(int n_occ_u, int y1_span, int max_pkt
     const size_t nu8 = (size_t)((n_occ_u + 7) & ~7);
     const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64 + al16(max_pkt_bytes);
     const size_t hsz = (size_t)((std::max(n_occ_u, y1_span) + 1) & ~1);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + al16(max_pkt_bytes) + al16(n_occ_u) + 64;
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + al16(n_occ_u) + 64;
     return al16(shared_bytes) + (size_t)warps * per_warp + 16;
 }

@@ -323,11 +323,11 @@ __device__ __forceinline__ double nco_turns(long long i, int j, int jend, const 
     while (m + 1 < jend) {
         const long long tn = trig[m + 1];
         if (tn > i) break;
-        acc += (double)cfo[m] * (double)(tn - tm);
+        acc += (double)__ldcg(&cfo[m]) * (double)(tn - tm);
         m++;
         tm = tn;
     }
-    acc += (double)cfo[m] * (double)(i - tm + 1);
+    acc += (double)__ldcg(&cfo[m]) * (double)(i - tm + 1);   // L2 load: the frame kernel may have just written it
     return acc * (-2.0 / (double)N) * (1.0 / TWO_PI_D);
 }
 

@@ -44,7 +44,7 @@ __device__ __forceinline__ void sv_products(const float4 *__restrict__ r4, int j
 }
 
 template <int NT>   // NT = fft_len at compile time, or 0 to use the runtime value
-__global__ void __launch_bounds__(SV_THREADS, 3)
+__global__ void __launch_bounds__(SV_THREADS, 4)
 sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int Nrt, float thr_f,
                         double thr_d, uint32_t *__restrict__ detmask, long long wps)
 {
@@ -102,10 +102,12 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
 
     // ---- phase 1: products and chunk totals
     const int J = nhc + tid;                // this thread's tile chunk
-    float2 x[SV_C];
-    float e[SV_C];
-    sv_products(r4, J, J - hc, x, e);
     {
+        // only the totals are kept: most warps never need the per-sample products again (chunk-level
+        // rejection below), the others recompute them from shared memory
+        float2 x[SV_C];
+        float e[SV_C];
+        sv_products(r4, J, J - hc, x, e);
         float sxr = 0.f, sxi = 0.f, se = 0.f;
 #pragma unroll
         for (int q = 0; q < SV_C; q++) { sxr += x[q].x; sxi += x[q].y; se += e[q]; }
@@ -139,8 +141,23 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
         }
         if (lane == 31) { wsum[0][wid] = ia; wsum[1][wid] = ib; wsum[2][wid] = ic; }
         __syncthreads();
-        float oa = 0.f, ob = 0.f, oc = 0.f;
-        for (int w = 0; w < wid; w++) { oa += wsum[0][w]; ob += wsum[1][w]; oc += wsum[2][w]; }
+        // exclusive prefix over the 8 warp totals: lanes 0..7 hold them, 3 shuffle steps, pick lane wid
+        float oa = (lane < SV_THREADS / 32) ? wsum[0][lane] : 0.f;
+        float ob = (lane < SV_THREADS / 32) ? wsum[1][lane] : 0.f;
+        float oc = (lane < SV_THREADS / 32) ? wsum[2][lane] : 0.f;
+        {
+            const float sa = oa, sb = ob, sc = oc;
+#pragma unroll
+            for (int o = 1; o < SV_THREADS / 32; o <<= 1) {
+                const float pa = __shfl_up_sync(0xffffffffu, oa, o);
+                const float pb = __shfl_up_sync(0xffffffffu, ob, o);
+                const float pc = __shfl_up_sync(0xffffffffu, oc, o);
+                if (lane >= o) { oa += pa; ob += pb; oc += pc; }
+            }
+            oa = __shfl_sync(0xffffffffu, oa - sa, wid);
+            ob = __shfl_sync(0xffffffffu, ob - sb, wid);
+            oc = __shfl_sync(0xffffffffu, oc - sc, wid);
+        }
         const float ea = oa + ia - ta, eb = ob + ib - tb, ec = oc + ic - tc;   // exclusive prefix at j0
         if (j0 < nch) { TXr[j0] = ea; TXi[j0] = eb; TE[j0] = ec; }
         if (j1 < nch) { TXr[j1] = ea + a0; TXi[j1] = eb + b0; TE[j1] = ec + c0; }
@@ -174,17 +191,21 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     if (!__all_sync(0xffffffffu, skip)) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
+        const float4 a = r4[sv_off(J, q)];           // r[n]
         const float4 b = r4[sv_off(jd, q)];          // r[n - N/2]
         const float4 c = r4[sv_off(jn, q)];          // r[n - N]
 #pragma unroll
         for (int s = 0; s < 2; s++) {
+            const float ar = s ? a.z : a.x, ai = s ? a.w : a.y;
             const float br = s ? b.z : b.x, bi = s ? b.w : b.y, cr = s ? c.z : c.x, ci = s ? c.w : c.y;
+            const float xnr = fmaf(ar, br, ai * bi), xni = fmaf(ai, br, -(ar * bi));   // x[n]
+            const float en = fmaf(ar, ar, ai * ai);                                       // e[n]
             const float xdr = fmaf(br, cr, bi * ci), xdi = fmaf(bi, cr, -(br * ci));   // x[n - N/2]
             const float ed = fmaf(cr, cr, ci * ci);                                       // e[n - N]
             const int k = 2 * q + s;
-            Pr += x[k].x - xdr;
-            Pi += x[k].y - xdi;
-            E += e[k] - ed;
+            Pr += xnr - xdr;
+            Pi += xni - xdi;
+            E += en - ed;
             const float d = fmaf(Pr, Pr, Pi * Pi) - thr4 * E * E;
             // |Pr| + |Pi| <= 0.71 E (Cauchy-Schwarz on the two half windows), pm2 + rhs <= 0.5 E^2
             const float aE = fabsf(E);

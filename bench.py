@@ -291,7 +291,7 @@ def main():
         dom_ms, dom_calls = prof[dom]
         # algorithmic bytes one launch of the dominant kernel is responsible for:
         # the frame kernel: 80 444 B per frame; the sync kernel: 8 B per sample.
-        algo = {"rx_frame_kernel": FRAME_ALGO_BYTES * args.frames, "sync_metric_kernel": 8 * n}.get(dom, 8 * n)
+        algo = FRAME_ALGO_BYTES * args.frames if dom.startswith("rx_frame") else 8 * n
         achieved = algo / (dom_ms / dom_calls * 1e-3) / 1e9
         chain_gbs = (8 * n + args.frames * (1500 + 32)) * world * args.steps / (ms * 1e-3) / 1e9
         out = {

@@ -29,11 +29,13 @@ struct DevBuf {
 }  // namespace
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
-             K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_NSLOTS };
+             K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
+             K_SYNC_TMA, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "trig_count_kernel", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
-    "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel" };
+    "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
+    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -331,13 +333,13 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         const long long spans = (tiles + ST_SPAN_TILES - 1) / ST_SPAN_TILES;
         const long long total = spans * n_streams;
         const unsigned grid = (unsigned)std::min<long long>(total, (long long)ctx->sm_count * ctx->sync_tma_occ);
-        KT(K_SYNC);
+        KT(K_SYNC_TMA);
         sync_metric_tma_kernel<<<grid, SV_THREADS, ctx->sync_tma_smem, st>>>(tmap, samples, n_samples, stride, kp.N, (float)kp.thr,
                                                                               kp.thr, w.detmask, w.wps, tiles, spans, total);
     } else if (kp.N >= 32) {
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
         dim3 grid((unsigned)tiles, (unsigned)n_streams);
-        KT(K_SYNC);
+        KT(K_SYNC_FAST);
 #define SVF(NN) sync_metric_fast_kernel<NN><<<grid, SV_THREADS, ctx->sync_fast_smem, st>>>(samples, n_samples, stride, kp.N, (float)kp.thr, kp.thr, w.detmask, w.wps)
         switch (kp.N) {
         case 64: SVF(64); break;
@@ -676,8 +678,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     }
     if (const char *fg = getenv("OFDMX_FORCE_GENERIC")) c->force_generic = (fg[0] == '1');
     if (const char *nw = getenv("OFDMX_NO_WARP_FRAME")) c->no_warp_frame = (nw[0] == '1');
-    c->no_tma = true;   // the plain-load kernel is currently the faster one; OFDMX_USE_TMA=1 selects the TMA ring kernel
-    if (const char *ut = getenv("OFDMX_USE_TMA")) c->no_tma = (ut[0] != '1');
+    if (const char *nt = getenv("OFDMX_NO_TMA")) c->no_tma = (nt[0] == '1');   // plain-load sync kernel instead of the TMA ring
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
     *out = c;
@@ -790,7 +791,7 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
     ofdmx_ctx *ctx_ = c;
     if (c->frame1kw && !c->force_generic && !c->no_warp_frame) {
-        KT(K_FRAME);
+        KT(K_FRAME1KW);
 #define FW_LAUNCH(B)                                                                                               \
     do {                                                                                                           \
         if (z_out) rx_frame1024w_kernel<B, true><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(               \
@@ -809,7 +810,7 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
         }
 #undef FW_LAUNCH
     } else if (c->frame1k_warps > 0 && !c->force_generic) {
-        KT(K_FRAME);
+        KT(K_FRAME1K);
 #define F1K_LAUNCH3(B, S, Z)                                                                                       \
     rx_frame1024_kernel<B, S, Z><<<c->sm_count * 2, F1K_THREADS, c->frame1k_smem, st>>>(                           \
         c->kp, c->frame1k_warps, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig,   \

@@ -56,10 +56,13 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     const int hc = h >> 4;                  // chunks per half window
     const int nch = nhc + SV_THREADS;       // chunks staged
     float4 *r4 = reinterpret_cast<float4 *>(smem_raw);            // 9 * nch float4
-    float *TXr = reinterpret_cast<float *>(r4 + 9 * nch);         // nch + 1 each
-    float *TXi = TXr + nch + 1;
-    float *TE = TXi + nch + 1;
-    __shared__ float wsum[3][SV_THREADS / 32 + 1];
+    // chunk totals and their exclusive prefix live in float64: the scan covers the whole tile, and a
+    // float32 prefix would make every window inherit the rounding error of the strongest burst in the tile
+    double *TXr = reinterpret_cast<double *>(r4 + 9 * nch);       // nch + 2 each
+    double *TXi = TXr + nch + 2;
+    double *TE = TXi + nch + 2;
+    float *CE = reinterpret_cast<float *>(TE + nch + 2);          // chunk energies, nch
+    __shared__ double wsum[3][SV_THREADS / 32 + 1];
 
     const long long ts = (long long)blockIdx.x * SV_T;
     const float2 *r = samples + (long long)blockIdx.y * stride;
@@ -111,7 +114,7 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
         float sxr = 0.f, sxi = 0.f, se = 0.f;
 #pragma unroll
         for (int q = 0; q < SV_C; q++) { sxr += x[q].x; sxi += x[q].y; se += e[q]; }
-        TXr[J] = sxr; TXi[J] = sxi; TE[J] = se;
+        TXr[J] = (double)sxr; TXi[J] = (double)sxi; TE[J] = (double)se; CE[J] = se;
     }
     for (int j = tid; j < nhc; j += SV_THREADS) {      // halo chunks: totals only
         float2 hx[SV_C];
@@ -120,45 +123,45 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
         float sxr = 0.f, sxi = 0.f, se = 0.f;
 #pragma unroll
         for (int q = 0; q < SV_C; q++) { sxr += hx[q].x; sxi += hx[q].y; se += he[q]; }
-        TXr[j] = sxr; TXi[j] = sxi; TE[j] = se;
+        TXr[j] = (double)sxr; TXi[j] = (double)sxi; TE[j] = (double)se; CE[j] = se;
     }
     __syncthreads();
 
     // ---- phase 2: exclusive scan of the chunk totals (<= 512 entries, 2 per thread)
     {
         const int j0 = 2 * tid, j1 = 2 * tid + 1;
-        const float a0 = (j0 < nch) ? TXr[j0] : 0.f, a1 = (j1 < nch) ? TXr[j1] : 0.f;
-        const float b0 = (j0 < nch) ? TXi[j0] : 0.f, b1 = (j1 < nch) ? TXi[j1] : 0.f;
-        const float c0 = (j0 < nch) ? TE[j0] : 0.f, c1 = (j1 < nch) ? TE[j1] : 0.f;
-        float ia = a0 + a1, ib = b0 + b1, ic = c0 + c1;
-        const float ta = ia, tb = ib, tc = ic;
+        const double a0 = (j0 < nch) ? TXr[j0] : 0.0, a1 = (j1 < nch) ? TXr[j1] : 0.0;
+        const double b0 = (j0 < nch) ? TXi[j0] : 0.0, b1 = (j1 < nch) ? TXi[j1] : 0.0;
+        const double c0 = (j0 < nch) ? TE[j0] : 0.0, c1 = (j1 < nch) ? TE[j1] : 0.0;
+        double ia = a0 + a1, ib = b0 + b1, ic = c0 + c1;
+        const double ta = ia, tb = ib, tc = ic;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const float pa = __shfl_up_sync(0xffffffffu, ia, o);
-            const float pb = __shfl_up_sync(0xffffffffu, ib, o);
-            const float pc = __shfl_up_sync(0xffffffffu, ic, o);
+            const double pa = __shfl_up_sync(0xffffffffu, ia, o);
+            const double pb = __shfl_up_sync(0xffffffffu, ib, o);
+            const double pc = __shfl_up_sync(0xffffffffu, ic, o);
             if (lane >= o) { ia += pa; ib += pb; ic += pc; }
         }
         if (lane == 31) { wsum[0][wid] = ia; wsum[1][wid] = ib; wsum[2][wid] = ic; }
         __syncthreads();
         // exclusive prefix over the 8 warp totals: lanes 0..7 hold them, 3 shuffle steps, pick lane wid
-        float oa = (lane < SV_THREADS / 32) ? wsum[0][lane] : 0.f;
-        float ob = (lane < SV_THREADS / 32) ? wsum[1][lane] : 0.f;
-        float oc = (lane < SV_THREADS / 32) ? wsum[2][lane] : 0.f;
+        double oa = (lane < SV_THREADS / 32) ? wsum[0][lane] : 0.0;
+        double ob = (lane < SV_THREADS / 32) ? wsum[1][lane] : 0.0;
+        double oc = (lane < SV_THREADS / 32) ? wsum[2][lane] : 0.0;
         {
-            const float sa = oa, sb = ob, sc = oc;
+            const double sa = oa, sb = ob, sc = oc;
 #pragma unroll
             for (int o = 1; o < SV_THREADS / 32; o <<= 1) {
-                const float pa = __shfl_up_sync(0xffffffffu, oa, o);
-                const float pb = __shfl_up_sync(0xffffffffu, ob, o);
-                const float pc = __shfl_up_sync(0xffffffffu, oc, o);
+                const double pa = __shfl_up_sync(0xffffffffu, oa, o);
+                const double pb = __shfl_up_sync(0xffffffffu, ob, o);
+                const double pc = __shfl_up_sync(0xffffffffu, oc, o);
                 if (lane >= o) { oa += pa; ob += pb; oc += pc; }
             }
             oa = __shfl_sync(0xffffffffu, oa - sa, wid);
             ob = __shfl_sync(0xffffffffu, ob - sb, wid);
             oc = __shfl_sync(0xffffffffu, oc - sc, wid);
         }
-        const float ea = oa + ia - ta, eb = ob + ib - tb, ec = oc + ic - tc;   // exclusive prefix at j0
+        const double ea = oa + ia - ta, eb = ob + ib - tb, ec = oc + ic - tc;   // exclusive prefix at j0
         if (j0 < nch) { TXr[j0] = ea; TXi[j0] = eb; TE[j0] = ec; }
         if (j1 < nch) { TXr[j1] = ea + a0; TXi[j1] = eb + b0; TE[j1] = ec + c0; }
         if (tid == ((nch - 1) >> 1)) {               // element nch = grand total (a1/b1/c1 are 0 past the end)
@@ -168,11 +171,14 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     __syncthreads();
 
     // ---- phase 3: sliding window inside the chunk, filtered comparison
-    const float A = TE[nch];                         // total energy staged: bounds every partial sum
-    const float eps = 1.0e-5f * A;                   // bound on the float32 error of Pr, Pi, E
-    float Pr = TXr[J] - TXr[J - hc];
-    float Pi = TXi[J] - TXi[J - hc];
-    float E = TE[J] - TE[J - nhc];
+    float Pr = (float)(TXr[J] - TXr[J - hc]);
+    float Pi = (float)(TXi[J] - TXi[J - hc]);
+    float E = (float)(TE[J] - TE[J - nhc]);
+    const float cJ = CE[J], cD = CE[J - hc], cN = CE[J - nhc];
+    // every partial sum formed for this chunk is bounded by the window energy plus the three chunk
+    // energies that enter or leave: float32 chunk totals (16 terms), <= 32 sliding updates
+    const float A = E + cJ + cD + cN;
+    const float eps = 6.0e-6f * A;                   // bound on the float32 error of Pr, Pi, E
     const float thr4 = 0.25f * thr_f;
     const float e3 = 3.5f * eps, e33 = 3.0f * eps * eps;
     unsigned det = 0, unc = 0;
@@ -183,7 +189,6 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     // skipped -- decided per warp, so noise and payload regions cost no phase-3 work.
     bool skip;
     {
-        const float cJ = TE[J + 1] - TE[J], cD = TE[jd + 1] - TE[jd], cN = TE[jn + 1] - TE[jn];
         const float pmax = fabsf(Pr) + fabsf(Pi) + 0.5f * (cJ + 2.0f * cD + cN) + 4.0f * eps;
         const float emin = E - cN - 4.0f * eps;
         skip = (emin > 0.0f) && (pmax * pmax < 0.999f * thr4 * emin * emin);
@@ -215,7 +220,7 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
         }
     }
     }
-    if (A == 0.0f) { det = 0; unc = 0; }             // all-zero tile: R^2 > 0 is false everywhere
+    if (A == 0.0f) { det = 0; unc = 0; }             // all-zero windows: R^2 > 0 is false everywhere
     {   // samples beyond the end of the stream never detect
         const long long first = ts + (long long)tid * SV_C;
         if (first + SV_C > n) {
@@ -270,5 +275,5 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
 static inline size_t sync_fast_smem_bytes(int N)
 {
     const int nch = (N >> 4) + SV_THREADS;
-    return (size_t)nch * 9 * 16 + 3 * (size_t)(nch + 1) * 4 + 16;
+    return (size_t)nch * 9 * 16 + 3 * (size_t)(nch + 2) * 8 + (size_t)nch * 4 + 16;
 }

@@ -84,11 +84,11 @@ sync_metric_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float2 *_
     float *CXr = reinterpret_cast<float *>(ring + RB * ST_BOX_BYTES);   // chunk totals, indexed by ring row
     float *CXi = CXr + RR;
     float *CE = CXi + RR;
-    float *TXr = CE + RR;                                  // prefix sums in logical chunk order, nch + 1 each
-    float *TXi = TXr + nch + 1;
-    float *TE = TXi + nch + 1;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(TE + nch + 1 + ((nch + 1) & 1));   // two barriers
-    __shared__ float wsum[3][SV_THREADS / 32 + 1];
+    double *TXr = reinterpret_cast<double *>(CE + RR);     // float64 prefix sums in logical chunk order, nch + 2 each
+    double *TXi = TXr + nch + 2;
+    double *TE = TXi + nch + 2;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(TE + nch + 2);   // two barriers
+    __shared__ double wsum[3][SV_THREADS / 32 + 1];
 
     if (tid == 0) { st_mbar_init(bar, 1); st_mbar_init(bar + 1, 1); }
     __syncthreads();
@@ -185,23 +185,23 @@ sync_metric_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float2 *_
                 if (q0 >= RR) q0 -= RR;
                 if (q1 < 0) q1 += RR;
                 if (q1 >= RR) q1 -= RR;
-                const float a0 = (j0 < nch) ? CXr[q0] : 0.f, a1 = (j1 < nch) ? CXr[q1] : 0.f;
-                const float b0 = (j0 < nch) ? CXi[q0] : 0.f, b1 = (j1 < nch) ? CXi[q1] : 0.f;
-                const float c0 = (j0 < nch) ? CE[q0] : 0.f, c1 = (j1 < nch) ? CE[q1] : 0.f;
-                float ia = a0 + a1, ib = b0 + b1, ic = c0 + c1;
-                const float ta = ia, tb = ib, tc = ic;
+                const double a0 = (j0 < nch) ? CXr[q0] : 0.0, a1 = (j1 < nch) ? CXr[q1] : 0.0;
+                const double b0 = (j0 < nch) ? CXi[q0] : 0.0, b1 = (j1 < nch) ? CXi[q1] : 0.0;
+                const double c0 = (j0 < nch) ? CE[q0] : 0.0, c1 = (j1 < nch) ? CE[q1] : 0.0;
+                double ia = a0 + a1, ib = b0 + b1, ic = c0 + c1;
+                const double ta = ia, tb = ib, tc = ic;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const float pa = __shfl_up_sync(0xffffffffu, ia, o);
-                    const float pb = __shfl_up_sync(0xffffffffu, ib, o);
-                    const float pc = __shfl_up_sync(0xffffffffu, ic, o);
+                    const double pa = __shfl_up_sync(0xffffffffu, ia, o);
+                    const double pb = __shfl_up_sync(0xffffffffu, ib, o);
+                    const double pc = __shfl_up_sync(0xffffffffu, ic, o);
                     if (lane >= o) { ia += pa; ib += pb; ic += pc; }
                 }
                 if (lane == 31) { wsum[0][wid] = ia; wsum[1][wid] = ib; wsum[2][wid] = ic; }
                 __syncthreads();
-                float oa = 0.f, ob = 0.f, oc = 0.f;
+                double oa = 0.0, ob = 0.0, oc = 0.0;
                 for (int w = 0; w < wid; w++) { oa += wsum[0][w]; ob += wsum[1][w]; oc += wsum[2][w]; }
-                const float ea = oa + ia - ta, eb = ob + ib - tb, ec = oc + ic - tc;
+                const double ea = oa + ia - ta, eb = ob + ib - tb, ec = oc + ic - tc;
                 if (j0 < nch) { TXr[j0] = ea; TXi[j0] = eb; TE[j0] = ec; }
                 if (j1 < nch) { TXr[j1] = ea + a0; TXi[j1] = eb + b0; TE[j1] = ec + c0; }
                 if (tid == ((nch - 1) >> 1)) { TXr[nch] = ea + a0 + a1; TXi[nch] = eb + b0 + b1; TE[nch] = ec + c0 + c1; }
@@ -209,16 +209,16 @@ sync_metric_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float2 *_
             __syncthreads();
             // ---- phase 3: sliding window inside the chunk, filtered comparison
             const int J = nhc + tid;
-            const float A = TE[nch];
-            const float eps = 1.0e-5f * A;
-            float Pr = TXr[J] - TXr[J - hc];
-            float Pi = TXi[J] - TXi[J - hc];
-            float E = TE[J] - TE[J - nhc];
+            float Pr = (float)(TXr[J] - TXr[J - hc]);
+            float Pi = (float)(TXi[J] - TXi[J - hc]);
+            float E = (float)(TE[J] - TE[J - nhc]);
+            const float cJ = CE[rown], cD = CE[rdel], cN = CE[rdn];
+            const float A = E + cJ + cD + cN;                // local bound (see ofdmx_sync.cuh)
+            const float eps = 6.0e-6f * A;
             const float e3 = 3.5f * eps, e33 = 3.0f * eps * eps;
             unsigned det = 0, unc = 0;
             bool skip;
             {   // chunk-level rejection (see ofdmx_sync.cuh)
-                const float cJ = TE[J + 1] - TE[J], cD = TE[J - hc + 1] - TE[J - hc], cN = TE[J - nhc + 1] - TE[J - nhc];
                 const float pmax = fabsf(Pr) + fabsf(Pi) + 0.5f * (cJ + 2.0f * cD + cN) + 4.0f * eps;
                 const float emin = E - cN - 4.0f * eps;
                 skip = (emin > 0.0f) && (pmax * pmax < 0.999f * thr4 * emin * emin);
@@ -314,5 +314,5 @@ static inline size_t sync_tma_smem_bytes(int N)
 {
     const int nhc = N >> 4, nch = nhc + SV_THREADS;
     const int hb = (nhc + ST_BOX_ROWS - 1) / ST_BOX_ROWS, RB = 2 * ST_TILE_BOXES + hb, RR = RB * ST_BOX_ROWS;
-    return (size_t)RB * ST_BOX_BYTES + 3 * (size_t)RR * 4 + 3 * (size_t)(nch + 1) * 4 + 8 + 16 + 1024;
+    return (size_t)RB * ST_BOX_BYTES + 3 * (size_t)RR * 4 + 3 * (size_t)(nch + 2) * 8 + 16 + 16 + 1024;
 }

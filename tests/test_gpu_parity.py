@@ -310,8 +310,8 @@ def test_generic_kernel_at_1024_matches_fast_path(monkeypatch):
     monkeypatch.setenv("OFDMX_FORCE_GENERIC", "1")
     gen = cm.make_phy(cfg).rx(_to_dev(x), want_z=True)
     monkeypatch.setenv("OFDMX_FORCE_GENERIC", "0")
-    monkeypatch.setenv("OFDMX_USE_TMA", "1")
-    tma = cm.make_phy(cfg).rx(_to_dev(x))
+    monkeypatch.setenv("OFDMX_NO_TMA", "1")
+    tma = cm.make_phy(cfg).rx(_to_dev(x))          # plain-load sync kernel (the TMA ring kernel is the default)
     assert np.array_equal(fast.frames, gen.frames) and fast.payloads() == gen.payloads() == pk
     assert np.array_equal(fast.frames, tma.frames) and tma.payloads() == pk
     assert cm.rel_evm(fast.z.cpu().numpy()[:5, :3000], gen.z.cpu().numpy()[:5, :3000]) < 1e-5

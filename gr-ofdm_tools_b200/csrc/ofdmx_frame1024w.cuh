@@ -192,7 +192,9 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     float2 y = make_float2(0.f, 0.f);
                     if (src >= 0 && src < N) y = cmul(Y[src ^ 512], pc);
                     float2 Hk = Hs[u];
-                    const float2 z = cdivf(y, Hk);
+                    const float hinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
+                    const float2 hn = cmul_conj(y, Hk);
+                    const float2 z = make_float2(hn.x * hinv, hn.y * hinv);
                     const int d = z.x > 0.f;
                     const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
                     Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));

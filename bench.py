@@ -293,6 +293,12 @@ def main():
         # the frame kernel: 80 444 B per frame; the sync kernel: 8 B per sample.
         algo = FRAME_ALGO_BYTES * args.frames if dom.startswith("rx_frame") else 8 * n
         achieved = algo / (dom_ms / dom_calls * 1e-3) / 1e9
+        traffic = None
+        try:   # dram bytes per algorithmic byte from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr[dom]["dram_bytes_per_algorithmic_byte"] * algo
+        except Exception:
+            pass
         chain_gbs = (8 * n + args.frames * (1500 + 32)) * world * args.steps / (ms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -302,7 +308,7 @@ def main():
                        "l2": "inputs (%.1f GB/GPU) larger than L2" % (8 * n / 1e9),
                        "parallelism": "independent streams sharded 1/GPU; per-frame stats all-gathered over NCCL"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_share_of_step": dom_ms / tot_ms,
                          "chain_frac": chain_gbs / world / peak,
                          "note": "achieved = algorithmic bytes of the kernel's launch / its mean CUDA-event duration; "

@@ -325,7 +325,7 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
 {
     const KP &kp = ctx->kp;
     ofdmx_ctx *ctx_ = ctx;
-    CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(w.blocksum, 0, sizeof(int) * (size_t)(w.nb + 1), st));   // per-block trigger counts (plateau_kernel)
     CUtensorMap tmap;
     if (kp.N >= 32 && !ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
         // TMA path: 3-D map {32 floats, rows of 16 samples, streams}; whole rows only (the kernel patches the tail)
@@ -335,12 +335,12 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         const unsigned grid = (unsigned)std::min<long long>(total, (long long)ctx->sm_count * ctx->sync_tma_occ);
         KT(K_SYNC_TMA);
         sync_metric_tma_kernel<<<grid, SV_THREADS, ctx->sync_tma_smem, st>>>(tmap, samples, n_samples, stride, kp.N, (float)kp.thr,
-                                                                              kp.thr, w.detmask, w.wps, tiles, spans, total);
+                                                                              kp.thr, w.detmask, w.trigmask, w.wps, tiles, spans, total);
     } else if (kp.N >= 32) {
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
         dim3 grid((unsigned)tiles, (unsigned)n_streams);
         KT(K_SYNC_FAST);
-#define SVF(NN) sync_metric_fast_kernel<NN><<<grid, SV_THREADS, ctx->sync_fast_smem, st>>>(samples, n_samples, stride, kp.N, (float)kp.thr, kp.thr, w.detmask, w.wps)
+#define SVF(NN) sync_metric_fast_kernel<NN><<<grid, SV_THREADS, ctx->sync_fast_smem, st>>>(samples, n_samples, stride, kp.N, (float)kp.thr, kp.thr, w.detmask, w.trigmask, w.wps)
         switch (kp.N) {
         case 64: SVF(64); break;
         case 128: SVF(128); break;
@@ -352,12 +352,13 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
     } else {
         const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
         dim3 grid((unsigned)tiles, (unsigned)n_streams);
+        CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
         KT(K_SYNC);
         sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr, w.detmask, w.wps);
     }
-    const long long pb = (w.n_words + OFDMX_THREADS - 1) / OFDMX_THREADS;
-    { KT(K_PLATEAU); plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp); }
-    { KT(K_TRIG_COUNT); trig_count_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.blocksum); }
+    const long long pb = (w.n_words + OFDMX_THREADS * PL_WPT - 1) / (OFDMX_THREADS * PL_WPT);
+    { KT(K_PLATEAU); plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp,
+                                                                            w.blocksum); }
     { KT(K_TRIG_SCAN); trig_scan_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nb, (int)max_trig, counts_dev, w.n_trig, w.stream_start, n_streams); }
     { KT(K_TRIG_SCATTER); trig_scatter_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.wps, w.blocksum, (int)max_trig,
                                                                              w.trig, w.trig_stream, w.stream_start); }

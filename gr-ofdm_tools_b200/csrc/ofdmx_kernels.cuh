@@ -13,6 +13,7 @@
 #include "ofdmx.h"
 
 #define TWO_PI_D 6.283185307179586476925286766559
+#define TRIG_WPT 4   // trigger-mask words per thread in the compaction kernels
 
 // =============================================================================================
 // K2: Schmidl & Cox metric.  Replaces ofdm_sync_sc_cfb's delay/conj/multiply/moving-average/
@@ -155,43 +156,50 @@ __device__ long long next_bit(const uint32_t *m, long long i, long long limit, i
     return limit;
 }
 
+#define PL_WPT 8   // detect words per thread
 __global__ void __launch_bounds__(OFDMX_THREADS)
 plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trigmask, long long n,
-               long long wps, long long n_streams, int cp)
+               long long wps, long long n_streams, int cp, int *__restrict__ blocksum)
 {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= wps * n_streams) return;
-    const long long s = g / wps, w = g - s * wps;
-    const uint32_t *m = detmask + s * wps;
-    uint32_t *tm = trigmask + s * wps;
-    const uint32_t word = m[w];
-    if (!word) return;
-    const uint32_t prev = (w > 0) ? (m[w - 1] >> 31) : 0u;
-    uint32_t rising = word & ~((word << 1) | prev);
-    while (rising) {
-        const int b = __ffs(rising) - 1;
-        rising &= rising - 1;
-        long long i = (w << 5) + b;
-        if (!bits_clear(m, i - (cp + 1), i, wps)) continue;   // reached in non-fresh state: owned by an earlier cluster
-        // sequential walk of this cluster
-        for (;;) {
-            if (n - i < 2LL * cp) break;                       // "come back later": never at stream end
-            const long long start = i;
-            i = next_bit(m, i, n, 0, wps);                     // end of run (exclusive)
-            if (i - start > 1) {
-                const long long tp = start + (i - start) / 2;
-                atomicOr(&tm[tp >> 5], 1u << (tp & 31));
-                i = (i + cp < n - 1) ? i + cp : n - 1;
+    const long long total = wps * n_streams;
+    const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PL_WPT;
+    for (int qq = 0; qq < PL_WPT; qq++) {
+        const long long g = g0 + qq;
+        if (g >= total) return;
+        const uint32_t word = detmask[g];
+        if (!word) continue;
+        const long long s = g / wps, w = g - s * wps;
+        const uint32_t *m = detmask + s * wps;
+        uint32_t *tm = trigmask + s * wps;
+        const uint32_t prev = (w > 0) ? (m[w - 1] >> 31) : 0u;
+        uint32_t rising = word & ~((word << 1) | prev);
+        while (rising) {
+            const int b = __ffs(rising) - 1;
+            rising &= rising - 1;
+            long long i = (w << 5) + b;
+            if (!bits_clear(m, i - (cp + 1), i, wps)) continue;   // reached in non-fresh state: owned by an earlier cluster
+            // sequential walk of this cluster
+            for (;;) {
+                if (n - i < 2LL * cp) break;                       // "come back later": never at stream end
+                const long long start = i;
+                i = next_bit(m, i, n, 0, wps);                     // end of run (exclusive)
+                if (i - start > 1) {
+                    const long long tp = start + (i - start) / 2;
+                    atomicOr(&tm[tp >> 5], 1u << (tp & 31));
+                    // per-block trigger count for the ordered compaction (same partition as trig_scatter_kernel)
+                    atomicAdd(&blocksum[(s * wps + (tp >> 5)) / (OFDMX_THREADS * TRIG_WPT)], 1);
+                    i = (i + cp < n - 1) ? i + cp : n - 1;
+                }
+                i++;                                               // the for-loop increment
+                if (i >= n) break;
+                // next flank the sequential scan would see
+                const long long lim = (i + cp + 2 < n) ? i + cp + 2 : n;
+                const long long j = next_bit(m, i, lim, 1, wps);
+                if (j >= lim) break;                               // >= cp+1 clear bits follow: next start is independent
+                const bool rising_j = !mbit(m, j - 1, n, wps);
+                if (rising_j && bits_clear(m, j - (cp + 1), j, wps)) break;   // independent start: its own thread walks it
+                i = j;
             }
-            i++;                                               // the for-loop increment
-            if (i >= n) break;
-            // next flank the sequential scan would see
-            const long long lim = (i + cp + 2 < n) ? i + cp + 2 : n;
-            const long long j = next_bit(m, i, lim, 1, wps);
-            if (j >= lim) break;                               // >= cp+1 clear bits follow: next start is independent
-            const bool rising_j = !mbit(m, j - 1, n, wps);
-            if (rising_j && bits_clear(m, j - (cp + 1), j, wps)) break;   // independent start: its own thread walks it
-            i = j;
         }
     }
 }
@@ -199,7 +207,6 @@ plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trig
 // ---------------------------------------------------------------------------------------------
 // Ordered compaction of the trigger bitmask.
 // ---------------------------------------------------------------------------------------------
-#define TRIG_WPT 4   // words per thread
 __global__ void __launch_bounds__(OFDMX_THREADS)
 trig_count_kernel(const uint32_t *__restrict__ trigmask, long long n_words, int *__restrict__ blocksum)
 {

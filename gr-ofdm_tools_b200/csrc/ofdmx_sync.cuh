@@ -46,7 +46,7 @@ __device__ __forceinline__ void sv_products(const float4 *__restrict__ r4, int j
 template <int NT>   // NT = fft_len at compile time, or 0 to use the runtime value
 __global__ void __launch_bounds__(SV_THREADS, 4)
 sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long long stride, int Nrt, float thr_f,
-                        double thr_d, uint32_t *__restrict__ detmask, long long wps)
+                        double thr_d, uint32_t *__restrict__ detmask, uint32_t *__restrict__ trigmask, long long wps)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -268,7 +268,10 @@ sync_metric_fast_kernel(const float2 *__restrict__ samples, long long n, long lo
     const unsigned hi = __shfl_down_sync(0xffffffffu, det, 1);
     if (!(tid & 1)) {
         const long long w = (ts >> 5) + (tid >> 1);
-        if (w < wps) detmask[(long long)blockIdx.y * wps + w] = (det & 0xffffu) | (hi << 16);
+        if (w < wps) {
+            detmask[(long long)blockIdx.y * wps + w] = (det & 0xffffu) | (hi << 16);
+            trigmask[(long long)blockIdx.y * wps + w] = 0u;      // cleared here: saves a memset pass
+        }
     }
 }
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void st_products(const unsigned char *ring, int rown,
 __global__ void __launch_bounds__(SV_THREADS, 2)
 sync_metric_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float2 *__restrict__ samples, long long n,
                        long long stride, int N, float thr_f, double thr_d, uint32_t *__restrict__ detmask,
-                       long long wps, long long tiles_per_stream, long long spans_per_stream, long long total_spans)
+                       uint32_t *__restrict__ trigmask, long long wps, long long tiles_per_stream, long long spans_per_stream, long long total_spans)
 {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // SWIZZLE_128B needs the ring 1024-byte aligned in the shared address space
@@ -301,7 +301,10 @@ sync_metric_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float2 *_
             const unsigned hi = __shfl_down_sync(0xffffffffu, det, 1);
             if (!(tid & 1)) {
                 const long long w = (g0 >> 1) + (tid >> 1);
-                if (w < wps) detmask[(long long)s * wps + w] = (det & 0xffffu) | (hi << 16);
+                if (w < wps) {
+                    detmask[(long long)s * wps + w] = (det & 0xffffu) | (hi << 16);
+                    trigmask[(long long)s * wps + w] = 0u;         // cleared here: saves a memset pass
+                }
             }
             // all generic-proxy reads of the ring are done before the next TMA overwrites dead boxes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

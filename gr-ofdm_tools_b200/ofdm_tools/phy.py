@@ -276,23 +276,29 @@ class OfdmPhy(object):
         return self.rx_collect(bufs)
 
     def rx_host(self, samples, max_frames=None):
-        """Same through ofdmx_rx_host: numpy complex64 in, numpy out (H2D/D2H inside the call)."""
+        """Same through ofdmx_rx_host: numpy complex64 in, numpy out (H2D/D2H inside the call).  The
+        output staging buffers are pinned and reused across calls (the returned arrays are views that
+        stay valid until the next rx_host call on this object)."""
         s = np.ascontiguousarray(samples, np.complex64)
         if s.ndim == 1:
             s = s[None, :]
         n_streams, n = s.shape
-        D = self.fft_len + self.cp_len
         if max_frames is None:
-            max_frames = int(n_streams * (n // (3 * D) + 4))
-        frames = np.zeros(max_frames, FRAME_DTYPE)
-        slots = np.zeros((max_frames, self.byte_stride), np.uint8)
+            max_frames = self.default_max_frames(n_streams, n)
+        hb = getattr(self, "_host_bufs", None)
+        if hb is None or hb[0] < max_frames:
+            torch = self._torch()
+            fr = torch.empty(max_frames * 32, dtype=torch.uint8, pin_memory=True)
+            sl = torch.empty((max_frames, self.byte_stride), dtype=torch.uint8, pin_memory=True)
+            hb = self._host_bufs = (max_frames, fr, sl, fr.numpy().view(FRAME_DTYPE), sl.numpy())
+        _, _, _, frames, slots = hb
         cnt = _lib.Counts()
         _lib.check(_lib.load().ofdmx_rx_host(self.ctx, s.ctypes.data, n_streams, n, frames.ctypes.data, max_frames,
                                              slots.ctypes.data, self.byte_stride, C.byref(cnt)), self.ctx)
         if cnt.overflow:
             raise BufferError("more triggers (%d) than max_frames (%d)" % (cnt.n_triggers, max_frames))
         c = np.array([cnt.n_triggers, cnt.n_frames, cnt.overflow, 0], np.int32)
-        return RxResult(frames[: cnt.n_frames].copy(), slots, c, None, self.crc_mode, cnt.n_triggers)
+        return RxResult(frames[: cnt.n_frames], slots, c, None, self.crc_mode, cnt.n_triggers)
 
     def sync(self, samples, max_trig=None):
         """Schmidl & Cox only: returns (trigger indices int64, cfo float32, stream int32) as numpy."""

@@ -592,6 +592,14 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         }
         c->x_2048 = x;      // after 32 steps of 512 bits: x^16384
     }
+    std::vector<uint32_t> crc_pow8(65);
+    {
+        uint32_t x = 0x80000000u;
+        for (int t = 0; t <= 64; t++) {
+            crc_pow8[t] = x;
+            for (int b = 0; b < 8; b++) x = h_gf2_mul_x(x);
+        }
+    }
     kp.y1_lo = 0;
     kp.y1_span = 1;
     if (!cv_k.empty()) {
@@ -606,7 +614,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(pil_size, pil_size) UP(pil_sym, pil_sym) UP(pil_sym_base, pil_sym_base) UP(sw1, sw1) UP(sw2, sw2)
     UP(cv_k, cv_k) UP(cv_conj, cv_conj) UP(inv_sw2, inv_sw2) UP(hdr_mask, hdr_mask) UP(keystream, keystream)
     UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
-    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64)
+    UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64) UP(crc_pow8, crc_pow8)
 #undef UP
 
     // shared-memory budgets

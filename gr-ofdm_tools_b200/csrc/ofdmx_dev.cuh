@@ -49,6 +49,7 @@ struct KP {
     const uint8_t *crc8_bit;     // [24] CRC-8 contribution of header bit l (len bits 0..11, counter bits 12..23)
     unsigned crc8_zero;          // CRC-8 of the all-zero header fields
     const uint32_t *crc_pow64;   // [32] x^(512*(31-l)) mod P (warp CRC)
+    const uint32_t *crc_pow8;    // [65] x^(8*t) mod P (warp CRC tail shift)
     int y1_lo, y1_span;          // shifted-bin range of sync symbol 1 that the offset search reads
     int pil_in_occ;              // some pilot carrier is also in occupied_carriers (equaliser pilot branch reachable)
 };

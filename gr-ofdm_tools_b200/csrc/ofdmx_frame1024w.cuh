@@ -18,6 +18,18 @@
 #define FW_WARPS 15
 #define FW_THREADS (FW_WARPS * 32)
 
+// Per-warp frame state kept in shared memory: these values live across the register-hungry FFT of every
+// symbol, where the compiler would otherwise spill them to local memory (whose reloads miss the small L1
+// that the sample stream keeps flushing).
+struct __align__(16) FwState {
+    ofdmx_frame rec;        // record under construction (written out once per frame)
+    double kappa;           // NCO turns per sample
+    long long tnext;        // next raw trigger of the stream
+    int nsym;               // symbols of this frame: 3, then 3 + frame_syms once the header is decoded
+    int nbytes;             // packet bytes to produce
+    int pad[2];
+};
+
 // zlib CRC-32 of msg[0..len) by one warp: 64-byte chunks per lane inside 2048-byte super-chunks (leading
 // zero padding, init folded into the first 4 bytes), terms shifted by x^(512*(31-lane)) and XOR-reduced.
 __device__ __forceinline__ uint32_t crc32_warp(const uint8_t *msg, int len, const uint32_t *tab,
@@ -52,6 +64,73 @@ __device__ __forceinline__ uint32_t crc32_warp(const uint8_t *msg, int len, cons
     return total ^ 0xFFFFFFFFu;
 }
 
+// Same CRC for a 16-byte aligned message of >= 4 bytes, by words with slicing-by-4 (tab = T0|T1|T2|T3, 1024 entries).
+// Lane L of a 2048-byte super-chunk owns message bytes [64L, 64L+64); with R bytes left at the start of the
+// last super-chunk, R = 64*nq + tail (1 <= tail <= 64): lanes < nq are shifted by x^(512*(nq-1-L)), the
+// running total by x^(512*nq), the XOR of those by x^(8*tail), and lane nq (the tail) is added unshifted.
+__device__ __forceinline__ uint32_t crc32_warp_words(const uint8_t *msg, int len, const uint32_t *tab,
+                                                     const uint32_t *pow64, const uint32_t *__restrict__ pow8,
+                                                     uint32_t x_2048, int lane)
+{
+    uint32_t total = 0;
+    for (int base = 0; base < len; base += 2048) {
+        const int R = len - base;
+        const int mb = min(64, R - 64 * lane);                  // bytes this lane owns (<= 0: none)
+        uint32_t reg = 0;
+        if (mb > 0) {
+            const uint4 *wp = reinterpret_cast<const uint4 *>(msg + base + 64 * lane);
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (16 * q < mb) {
+                    const uint4 v = wp[q];
+                    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+            if (base == 0 && lane == 0) w[0] ^= 0xFFFFFFFFu;    // CRC init folded into the first 4 bytes
+            const int nw = mb >> 2;                             // whole words; mb & 3 bytes follow in word nw
+            uint32_t x = 0;
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                if (q < nw) {
+                    reg ^= w[q];
+                    reg = tab[768 + (reg & 0xFF)] ^ tab[512 + ((reg >> 8) & 0xFF)] ^ tab[256 + ((reg >> 16) & 0xFF)]
+                          ^ tab[reg >> 24];
+                }
+                if (q == nw) x = w[q];
+            }
+#pragma unroll 1
+            for (int b = mb & 3; b > 0; b--, x >>= 8) reg = tab[(reg ^ x) & 0xFF] ^ (reg >> 8);
+        }
+        if (R > 2048) {
+            uint32_t term = reg ? gf2_mul(reg, pow64[lane]) : 0u;
+            for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
+            total = (total ? gf2_mul(total, x_2048) : 0u) ^ term;
+        } else {
+            const int nq = (R - 1) >> 6, tail = R - 64 * nq;
+            const uint32_t a = (lane < nq) ? reg : (lane == nq ? total : 0u);
+            uint32_t term = a ? gf2_mul(a, pow64[lane < nq ? 32 - nq + lane : 31 - nq]) : 0u;
+            for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
+            const uint32_t last = __shfl_sync(0xffffffffu, reg, nq);
+            total = (term ? gf2_mul(term, pow8[tail]) : 0u) ^ last;
+        }
+    }
+    return total ^ 0xFFFFFFFFu;
+}
+
+// lane 0 copies the finished record to global memory (two 16-byte moves)
+__device__ __forceinline__ void fw_flush(volatile FwState *fs, ofdmx_frame *dst, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(const_cast<const FwState *>(fs));
+        const uint4 a = s4[0], b = s4[1];
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        d4[0] = a;
+        d4[1] = b;
+    }
+    __syncwarp();
+}
+
 template <int BPS_P, bool WANT_Z>
 __global__ void __launch_bounds__(FW_THREADS, 1)
 rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
@@ -68,21 +147,22 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     // ---- CTA-shared tables
     float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024]
     float2 *ipts = tws + 1024;                                    // [64]
-    uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [256]
-    uint32_t *s_pow = s_tab + 256;                                // [32]
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [1024] slicing-by-4 CRC tables T0..T3
+    uint32_t *s_pow = s_tab + 1024;                                // [32]
     uint16_t *s_occ = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] union bin of carrier u
     uint16_t *s_pos = s_occ + ((nu + 7) & ~7);                    // [nu] position in the serialiser order
     uint8_t *lut = reinterpret_cast<uint8_t *>(s_pos + ((nu + 7) & ~7));   // [64]
     uint8_t *ks = lut + 64;                                       // [max_pkt_bytes]
     // ---- per-warp buffers
-    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64
+    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 1024 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64
                                 + (size_t)((p.max_pkt_bytes + 15) & ~15);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (size_t)((nu + 15) & ~15) + 64;
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (size_t)((nu + 15) & ~15) + 64 + sizeof(FwState);
     unsigned char *wbase = smem_raw + ((shared_bytes + 15) & ~(size_t)15) + (size_t)wid * per_warp;
     float2 *Y = reinterpret_cast<float2 *>(wbase);                // F1K_SLOT
     float2 *Hs = Y + F1K_SLOT;                                    // hsz
     uint8_t *dec = reinterpret_cast<uint8_t *>(Hs + hsz);         // decisions of the current symbol
     uint8_t *hb = dec + ((nu + 15) & ~15);                        // 64 header items
+    volatile FwState *fs = reinterpret_cast<volatile FwState *>(hb + 64);
 
     for (int i = tid; i < 1024; i += NTH) {
         const int k1 = i >> 5, b = i & 31;
@@ -99,6 +179,13 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         ipts[tid] = (tid < (1 << BPS_P)) ? p.inv_ppts[tid] : make_float2(0.f, 0.f);
     }
     __syncthreads();
+    for (int k = 1; k < 4; k++) {                                 // T[k][i] = (T[k-1][i] >> 8) ^ T0[T[k-1][i] & 0xFF]
+        if (tid < 256) {
+            const uint32_t v = s_tab[(k - 1) * 256 + tid];
+            s_tab[k * 256 + tid] = (v >> 8) ^ s_tab[v & 0xFF];
+        }
+        __syncthreads();
+    }
 
     const int nt = *n_trig_dev;
     const int N = 1024, D = p.D;
@@ -107,31 +194,37 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     const int sym_bytes = size0 * BPS_P / 8;
     const int ng = (p.gpos - p.gneg) / 2 + 1;
     const int y1_lo = p.y1_lo;                                    // first shifted bin parked from Y1
+    const unsigned hmask32 = __ballot_sync(0xffffffffu, p.hdr_mask[lane] & 1);   // header scrambler, bits 0..31
+    const bool words_ok = ((reinterpret_cast<uintptr_t>(bytes_out) | (uintptr_t)byte_stride) & 15) == 0;
 
     for (int j = blockIdx.x * NWARP + wid; j < nt; j += gridDim.x * NWARP) {
         const int st = trig_stream[j];
         const long long t = trig[j];
         const float2 *r = samples + (long long)st * stride;
         const int jend = stream_start[st + 1];
-        ofdmx_frame rec;
-        rec.trigger = t; rec.cfo = cfo[j]; rec.stream = st; rec.flags = 0; rec.pkt_len = 0; rec.pkt_num = 0;
-        rec.frame_syms = 0; rec.carr_offset = 0; rec.slot = (uint32_t)j;
         const long long rem = n - t;
+        if (lane == 0) {
+            const float cf = cfo[j];
+            fs->rec.trigger = t; fs->rec.cfo = cf; fs->rec.stream = st; fs->rec.flags = 0; fs->rec.pkt_len = 0;
+            fs->rec.pkt_num = 0; fs->rec.frame_syms = 0; fs->rec.carr_offset = 0; fs->rec.slot = (uint32_t)j;
+            fs->kappa = (double)cf * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+            fs->tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
+            fs->nsym = 3;
+            fs->nbytes = 0;
+        }
+        __syncwarp();
         if (3LL * D > rem) {
-            if (lane == 0) spec[j] = rec;
+            fw_flush(fs, spec + j, lane);
             continue;
         }
-        const long long tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
-        const double kappa = (double)rec.cfo * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
 
         // One loop over the frame's OFDM symbols with a SINGLE call site of the (large, straight-line)
         // FFT code, so that all warps of the SM share one copy in the instruction cache.
-        int off = 0, ok = 0, plen = 0, pnum = 0, psyms = 0, fsyms = 0, nbytes = 0;
-        int nsym = 3;                                   // grows to 3 + fsyms once the header is decoded
+        int off = 0, psyms = 0;
         bool dead = false;
-        for (int sidx = 0; sidx < nsym; sidx++) {
+        for (int sidx = 0; sidx < fs->nsym; sidx++) {
             const long long i0 = t + (long long)sidx * D + p.cp;
-            f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+            f1k_symbol(p, r, n, i0, t, fs->kappa, fs->tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
             {   // pull the next symbol's 8 KB towards L2 while this one is processed
                 const long long sn = i0 + D - p.D + lane * 32;
                 if (sn >= 0 && sn + 32 <= n) {
@@ -148,15 +241,26 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                 float2 acc[4];
 #pragma unroll
                 for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
-                for (int c = lane; c < p.n_cv; c += 32) {
-                    const int kc = p.cv_k[c];
-                    const float2 cvc = p.cv_conj[c];
+                for (int c0 = lane; c0 < p.n_cv; c0 += 128) {
+                    // four table entries per lane per trip, loaded together (global, L2-resident)
+                    int kc[4];
+                    float2 cvc[4];
 #pragma unroll
-                    for (int gi = 0; gi < 4; gi++)
-                        if (gi < ng) {
-                            const int k = kc + p.gneg + 2 * gi;
-                            acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ 512], Hs[k - y1_lo]), cvc));
-                        }
+                    for (int w4 = 0; w4 < 4; w4++) {
+                        const int c = c0 + 32 * w4;
+                        kc[w4] = (c < p.n_cv) ? p.cv_k[c] : -1;
+                        cvc[w4] = (c < p.n_cv) ? p.cv_conj[c] : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) {
+                        if (kc[w4] < 0) continue;
+#pragma unroll
+                        for (int gi = 0; gi < 4; gi++)
+                            if (gi < ng) {
+                                const int k = kc[w4] + p.gneg + 2 * gi;
+                                acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ 512], Hs[k - y1_lo]), cvc[w4]));
+                            }
+                    }
                 }
                 float b = 0.f;
 #pragma unroll
@@ -181,10 +285,10 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                 // header symbol: frame equaliser (offset shift + phase fix) + simpledfe with the BPSK header
                 float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);
                 if (off != 0) {
+                    // exp(-+ j 2 pi off cp / N): the turn count is reduced exactly in integers
                     float sn, cs;
-                    sincosf((float)(-TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
-                    pc = make_float2(cs, sn);
-                    sincosf((float)(TWO_PI_D * off * p.cp / N * 1), &sn, &cs);
+                    sincospif((float)((off * p.cp) & (N - 1)) * (2.0f / N), &sn, &cs);
+                    pc = make_float2(cs, -sn);
                     rot = make_float2(cs, sn);
                 }
                 for (int u = lane; u < nu; u += 32) {
@@ -199,38 +303,39 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
                     Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                     const int pos = s_pos[u];
-                    if (pos < 64) hb[pos] = (uint8_t)d ^ p.hdr_mask[pos];
+                    if (pos < 64) hb[pos] = (uint8_t)d;          // descrambled after the ballot (hmask32)
                     if (WANT_Z) z_out[(long long)j * z_stride + pos] = z;
                     Hs[u] = cmul(Hk, rot);
                 }
                 __syncwarp();
-                const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1);
-                plen = (int)(bits & 0xFFFu);
-                pnum = (int)((bits >> 12) & 0xFFFu);
+                const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1) ^ hmask32;
+                const int plen = (int)(bits & 0xFFFu);
+                const int pnum = (int)((bits >> 12) & 0xFFFu);
                 unsigned c8 = (lane < 24 && ((bits >> lane) & 1u)) ? (unsigned)p.crc8_bit[lane] : 0u;
                 for (int o = 16; o > 0; o >>= 1) c8 ^= __shfl_xor_sync(0xffffffffu, c8, o);
-                ok = ((c8 ^ p.crc8_zero) == (bits >> 24));
+                const bool ok = ((c8 ^ p.crc8_zero) == (bits >> 24));
                 psyms = (plen * 8 + BPS_P - 1) / BPS_P;
-                fsyms = (psyms + size0 - 1) / size0;
-                rec.flags = OFDMX_F_HDR_SEEN;
-                rec.carr_offset = (int16_t)off;
-                rec.pkt_len = (uint16_t)plen;
-                rec.pkt_num = (uint16_t)pnum;
-                rec.frame_syms = (uint16_t)fsyms;
-                if (!ok) { dead = true; break; }
-                rec.flags |= OFDMX_F_HDR_OK;
-                if ((long long)(3 + fsyms) * D > rem || plen > p.max_pkt_bytes) { dead = true; break; }
-                rec.flags |= OFDMX_F_COMPLETE;
-                nbytes = min(psyms * BPS_P / 8, p.max_pkt_bytes);
-                nsym = 3 + fsyms;
+                const int fsyms = (psyms + size0 - 1) / size0;
+                const bool complete = ok && !((long long)(3 + fsyms) * D > rem || plen > p.max_pkt_bytes);
+                if (lane == 0) {
+                    fs->rec.flags = OFDMX_F_HDR_SEEN | (ok ? OFDMX_F_HDR_OK : 0) | (complete ? OFDMX_F_COMPLETE : 0);
+                    fs->rec.carr_offset = (int16_t)off;
+                    fs->rec.pkt_len = (uint16_t)plen;
+                    fs->rec.pkt_num = (uint16_t)pnum;
+                    fs->rec.frame_syms = (uint16_t)fsyms;
+                    fs->nbytes = min(psyms * BPS_P / 8, p.max_pkt_bytes);
+                    if (complete) fs->nsym = 3 + fsyms;
+                }
+                __syncwarp();
+                if (!complete) { dead = true; break; }
             } else {
                 // payload symbol i: equalise + demap with the lanes over the carriers, then pack its bytes
                 const int i = sidx - 3;
                 float2 pc = make_float2(1.f, 0.f);
                 if (off != 0) {
                     float sn, cs;
-                    sincosf((float)(-TWO_PI_D * off * p.cp / N * (i + 1)), &sn, &cs);
-                    pc = make_float2(cs, sn);
+                    sincospif((float)((off * p.cp * (i + 1)) & (N - 1)) * (2.0f / N), &sn, &cs);
+                    pc = make_float2(cs, -sn);
                 }
                 const int cb = i * size0;
                 for (int u0 = lane; u0 < nu; u0 += 128) {
@@ -264,6 +369,36 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                 __syncwarp();
                 // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes
                 const int b0 = i * sym_bytes;
+                const int nbytes = fs->nbytes;
+                if ((BPS_P == 4 || BPS_P == 2) && words_ok && (sym_bytes & 3) == 0) {
+                    // four bytes per lane: decisions read as words, nibbles / bit pairs squeezed together
+                    const uint32_t *dw = reinterpret_cast<const uint32_t *>(dec);
+                    const uint32_t *kw = reinterpret_cast<const uint32_t *>(ks + b0);
+                    uint8_t *orow = bytes_out + (long long)j * byte_stride + b0;
+                    for (int m = lane; 4 * m < sym_bytes; m += 32) {
+                        const int gb = b0 + 4 * m;
+                        if (gb >= nbytes) break;
+                        uint32_t v;
+                        if (BPS_P == 4) {
+                            uint32_t lo = dw[2 * m], hi = dw[2 * m + 1];
+                            lo = (lo | (lo >> 4)) & 0x00FF00FFu; lo = (lo | (lo >> 8)) & 0xFFFFu;
+                            hi = (hi | (hi >> 4)) & 0x00FF00FFu; hi = (hi | (hi >> 8)) & 0xFFFFu;
+                            v = lo | (hi << 16);
+                        } else {
+                            v = 0;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                uint32_t x = dw[4 * m + q];
+                                x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;
+                                v |= x << (8 * q);
+                            }
+                        }
+                        v ^= kw[m];
+                        if (gb + 4 <= nbytes) *reinterpret_cast<uint32_t *>(orow + 4 * m) = v;
+                        else
+                            for (int b = 0; gb + b < nbytes; b++) orow[4 * m + b] = (uint8_t)(v >> (8 * b));
+                    }
+                } else
                 for (int m = lane; m < sym_bytes; m += 32) {
                     const int gb = b0 + m;
                     if (gb >= nbytes) break;
@@ -286,26 +421,26 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
             __syncwarp();
         }
         if (dead) {
-            if (lane == 0) spec[j] = rec;
-            __syncwarp();
+            fw_flush(fs, spec + j, lane);
             continue;
         }
         bool crc_ok = true;
         if (p.crc_mode) {
+            const int nbytes = fs->nbytes;
             if (nbytes < 4) crc_ok = false;
             else {
-                // the packet bytes were written by this warp: read them back (L1/L2) for the CRC
+                // the packet bytes were written by this warp: read them back (L2) for the CRC
                 __syncwarp();
                 const uint8_t *pk = bytes_out + (long long)j * byte_stride;
-                const uint32_t c = crc32_warp(pk, nbytes - 4, s_tab, s_pow, x_2048, lane);
+                const uint32_t c = (words_ok && nbytes >= 8) ? crc32_warp_words(pk, nbytes - 4, s_tab, s_pow, p.crc_pow8, x_2048, lane)
+                                            : crc32_warp(pk, nbytes - 4, s_tab, s_pow, x_2048, lane);
                 const uint32_t got = (uint32_t)pk[nbytes - 4] | ((uint32_t)pk[nbytes - 3] << 8)
                                      | ((uint32_t)pk[nbytes - 2] << 16) | ((uint32_t)pk[nbytes - 1] << 24);
                 crc_ok = (c == got);
             }
         }
-        if (crc_ok) rec.flags |= OFDMX_F_CRC_OK;
-        if (lane == 0) spec[j] = rec;
-        __syncwarp();
+        if (crc_ok && lane == 0) fs->rec.flags = fs->rec.flags | OFDMX_F_CRC_OK;
+        fw_flush(fs, spec + j, lane);
     }
 }
 
@@ -313,8 +448,8 @@ static inline size_t frame1024w_smem_bytes(int n_occ_u, int y1_span, int max_pkt
 {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t nu8 = (size_t)((n_occ_u + 7) & ~7);
-    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64 + al16(max_pkt_bytes);
+    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 1024 * 4 + 32 * 4 + 2 * nu8 * 2 + 64 + al16(max_pkt_bytes);
     const size_t hsz = (size_t)((std::max(n_occ_u, y1_span) + 1) & ~1);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + al16(n_occ_u) + 64;
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + al16(n_occ_u) + 64 + sizeof(FwState);
     return al16(shared_bytes) + (size_t)warps * per_warp + 16;
 }

@@ -362,3 +362,24 @@ def test_frame_kernel_variants_agree(monkeypatch):
     assert np.array_equal(warp.frames["trigger"], ref["frames"]["trigger"])
     for i in range(7):
         assert cm.rel_evm(warp.z.cpu().numpy()[i, :3608], ref["z"][i, :3608]) <= 1e-4
+
+
+@pytest.mark.parametrize("bps", [1, 2, 3, 4, 6])
+def test_warp_frame_kernel_ragged_lengths(bps):
+    """fft_len 1024 warp-per-frame kernel: every payload modulation, packet lengths around the edges of the
+    word-wise pack and CRC code (1..5 bytes, 64-byte lane chunks, OFDM-symbol multiples, > 2048 bytes, the
+    12-bit maximum), default max_pkt_bytes (4095).  Bytes and flags bit-exact against the oracle."""
+    cfg = cm.cfg_c3(bps_payload=bps)
+    rng = np.random.default_rng(900 + bps)
+    sym = 600 * bps // 8
+    lens = [1, 2, 3, 4, 5, 59, 60, 61, 63, 64, 65, 124, 127, 128, sym - 4, sym - 3, sym, sym + 1, 1000, 1499, 2043,
+            2044, 2045, 2047, 2052, 2053, 3001, 4091]
+    if bps == 1:
+        lens = [n for n in lens if n <= 1499]          # keep the BPSK stream short
+    pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    s, off = cm.make_oracle(cfg).tx(pk)
+    stream = cm.channel(cm.split_frames(s, off), rng, gaps=(0, 300), lead=500, tail=3000, snr_db=60.0, cfo=0.2,
+                        fft_len=1024)
+    res, ref = _compare_rx(cfg, stream, check_z=False)
+    assert res.payloads() == pk
+    assert np.all(res.frames["flags"] & 2)

@@ -33,9 +33,19 @@ __device__ __noinline__ float2 f1k_exact_phasor(long long i, int j, int jend, co
     return make_float2(c2, s2);
 }
 
+// phasor of 32 samples of NCO advance (the recurrence step of f1k_symbol); constant over a frame
+__device__ __forceinline__ float2 f1k_step_phasor(double kappa)
+{
+    double tsd = kappa * 32.0;
+    tsd -= rint(tsd);
+    float ssn, scs;
+    sincospif(2.0f * (float)tsd, &ssn, &scs);
+    return make_float2(scs, ssn);
+}
+
 // One symbol: load + derotate + 1024-point FFT.  Result: Tw[k] = X[k], natural order, k < 1024.
 __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict__ r, long long n, long long i0,
-                                           long long t, double kappa, bool slow, int j, int jend,
+                                           long long t, double kappa, float2 st, bool slow, int j, int jend,
                                            const long long *__restrict__ trig, const float *__restrict__ cfo,
                                            float2 *__restrict__ Tw, const float2 *__restrict__ tws, int lane)
 {
@@ -55,13 +65,9 @@ __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict
         // phase(i) = 2 pi kappa (i - t + 1); phasor recurrence over a (step = 32 samples)
         double tb = kappa * (double)(i0 + lane - t + 1);
         tb -= rint(tb);
-        double tsd = kappa * 32.0;
-        tsd -= rint(tsd);
-        float sn, cs, ssn, scs;
+        float sn, cs;
         sincospif(2.0f * (float)tb, &sn, &cs);
-        sincospif(2.0f * (float)tsd, &ssn, &scs);
         float2 ph = make_float2(cs, sn);
-        const float2 st = make_float2(scs, ssn);
         if (!slow) {
 #pragma unroll
             for (int a = 0; a < 32; a++) {
@@ -200,11 +206,12 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
         }
         const long long tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
         const double kappa = (double)rec.cfo * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+        const float2 kstep = f1k_step_phasor(kappa);
         const long long rem = n - t;
         // ---- round 0: symbols 0 .. W-1 (those that fit in the buffer), one per warp
         if (wid < W && (long long)(wid + 1) * D <= rem) {
             const long long i0 = t + (long long)wid * D + p.cp;
-            f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
+            f1k_symbol(p, r, n, i0, t, kappa, kstep, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
         }
         __syncthreads();
         const float2 *Y1 = T, *Y2 = T + F1K_SLOT, *Y3 = T + 2 * F1K_SLOT;
@@ -471,7 +478,7 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
             slot0 = 0;
             if (wid < in_round) {
                 const long long i0 = t + (long long)(3 + first + wid) * D + p.cp;
-                f1k_symbol(p, r, n, i0, t, kappa, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
+                f1k_symbol(p, r, n, i0, t, kappa, kstep, tnext <= i0 + 1023, j, jend, trig, cfo, T + wid * F1K_SLOT, tws, lane);
             }
             __syncthreads();
         }

@@ -17,6 +17,9 @@
 
 #define FW_WARPS 15
 #define FW_THREADS (FW_WARPS * 32)
+#ifndef FW_DFE_UNROLL
+#define FW_DFE_UNROLL 2
+#endif
 
 // Per-warp frame state kept in shared memory: these values live across the register-hungry FFT of every
 // symbol, where the compiler would otherwise spill them to local memory (whose reloads miss the small L1
@@ -27,7 +30,7 @@ struct __align__(16) FwState {
     long long tnext;        // next raw trigger of the stream
     int nsym;               // symbols of this frame: 3, then 3 + frame_syms once the header is decoded
     int nbytes;             // packet bytes to produce
-    int pad[2];
+    float stx, sty;         // phasor of 32 samples of NCO advance
 };
 
 // zlib CRC-32 of msg[0..len) by one warp: 64-byte chunks per lane inside 2048-byte super-chunks (leading
@@ -207,7 +210,9 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
             const float cf = cfo[j];
             fs->rec.trigger = t; fs->rec.cfo = cf; fs->rec.stream = st; fs->rec.flags = 0; fs->rec.pkt_len = 0;
             fs->rec.pkt_num = 0; fs->rec.frame_syms = 0; fs->rec.carr_offset = 0; fs->rec.slot = (uint32_t)j;
-            fs->kappa = (double)cf * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+            const double kap = (double)cf * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+            const float2 kst = f1k_step_phasor(kap);
+            fs->kappa = kap; fs->stx = kst.x; fs->sty = kst.y;
             fs->tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
             fs->nsym = 3;
             fs->nbytes = 0;
@@ -224,7 +229,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         bool dead = false;
         for (int sidx = 0; sidx < fs->nsym; sidx++) {
             const long long i0 = t + (long long)sidx * D + p.cp;
-            f1k_symbol(p, r, n, i0, t, fs->kappa, fs->tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+            f1k_symbol(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
             {   // pull the next symbol's 8 KB towards L2 while this one is processed
                 const long long sn = i0 + D - p.D + lane * 32;
                 if (sn >= 0 && sn + 32 <= n) {
@@ -338,10 +343,10 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     pc = make_float2(cs, -sn);
                 }
                 const int cb = i * size0;
-                for (int u0 = lane; u0 < nu; u0 += 128) {
-                    // four carriers per lane per trip: independent chains for the scheduler to interleave
+                for (int u0 = lane; u0 < nu; u0 += 32 * FW_DFE_UNROLL) {
+                    // several carriers per lane per trip: independent chains for the scheduler to interleave
 #pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) {
+                    for (int w4 = 0; w4 < FW_DFE_UNROLL; w4++) {
                         const int u = u0 + 32 * w4;
                         if (u < nu) {
                             const int src = (int)s_occ[u] + off;

@@ -18,7 +18,7 @@
 #define FW_WARPS 15
 #define FW_THREADS (FW_WARPS * 32)
 #ifndef FW_DFE_UNROLL
-#define FW_DFE_UNROLL 2
+#define FW_DFE_UNROLL 1
 #endif
 
 // Per-warp frame state kept in shared memory: these values live across the register-hungry FFT of every

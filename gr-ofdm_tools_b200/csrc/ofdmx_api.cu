@@ -5,6 +5,7 @@
 #include "ofdmx_sync_tma.cuh"
 #include "ofdmx_frame1024.cuh"
 #include "ofdmx_frame1024w.cuh"
+#include "ofdmx_cond.cuh"
 #include "ofdmx_chain.cuh"
 
 #include <algorithm>
@@ -30,12 +31,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "trig_count_kernel", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel" };
+    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -421,6 +422,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     kp.thr = (double)prm->threshold;
     kp.alpha = prm->alpha;
     kp.tx_scale = prm->tx_scale;
+    kp.tx_clip = prm->tx_clip;
 
     int rc = 0;
     auto bail = [&](int code) { ofdmx_destroy(c); return code; };
@@ -932,6 +934,22 @@ int ofdmx_crc32(ofdmx_ctx *c, const uint8_t *bytes_dev, const int64_t *pkt_off_d
     ofdmx_ctx *ctx_ = c;
     { KT(K_CRC); crc32_kernel<<<grid, OFDMX_THREADS, 0, st>>>(bytes_dev, (const long long *)pkt_off_dev, n_pkts, crc_out_dev,
                                                  c->kp.crc_tab, c->kp.crc_pow); }
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
+               float attack, float decay, float reference, float max_gain, float *gain_io_dev, void *stream)
+{
+    if (!c || !in_dev || !out_dev || !gain_io_dev || n_streams < 0 || n < 0 || stride < n || n_streams > (1 << 24))
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_agc2 arguments");
+    if (n_streams == 0 || n == 0) return OFDMX_OK;
+    if (int rc = check_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n_streams + 32 * AGC_WARPS - 1) / (32 * AGC_WARPS));
+    ofdmx_ctx *ctx_ = c;
+    { KT(K_AGC2); agc2_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
+                                                      attack, decay, reference, max_gain, gain_io_dev); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }

@@ -16,7 +16,7 @@ struct KP {
     int bps_h, bps_p, crc_mode, gneg, gpos, holdoff;
     int max_pkt_bytes, max_pkt_syms;
     double thr;
-    float alpha, tx_scale;
+    float alpha, tx_scale, tx_clip;
     const float2 *tw;            // [N] exp(-2 pi i k / N)
     const int *occ_bins;         // flat, set-major, list order, shifted bins
     const int *occ_base;         // [n_occ_sets]

@@ -827,7 +827,12 @@ tx_frame_kernel(const KP p, const uint8_t *__restrict__ payload, const long long
             float2 *dst = out + base + (long long)o * p.D;
             for (int m = tid; m < p.D; m += blockDim.x) {
                 const float2 v = buf[(m - p.cp + N) & (N - 1)];
-                dst[m] = make_float2(v.x * p.tx_scale, v.y * p.tx_scale);
+                float2 o = make_float2(v.x * p.tx_scale, v.y * p.tx_scale);
+                if (p.tx_clip > 0.f) {      // clipper: analog.rail_ff(-c, c) on re and im
+                    o.x = o.x < -p.tx_clip ? -p.tx_clip : (o.x > p.tx_clip ? p.tx_clip : o.x);
+                    o.y = o.y < -p.tx_clip ? -p.tx_clip : (o.y > p.tx_clip ? p.tx_clip : o.y);
+                }
+                dst[m] = o;
             }
             __syncthreads();
         }

@@ -25,7 +25,7 @@ class Params(C.Structure):
         ("scramble_header", C.c_int32), ("scramble_seed", C.c_int32),
         ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
         ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32),
-        ("max_pkt_bytes", C.c_int32),
+        ("max_pkt_bytes", C.c_int32), ("tx_clip", C.c_float),
     ]
 
 
@@ -56,6 +56,7 @@ SYMBOLS = {
     "ofdmx_profile_read": (C.c_int, [_P, _P, _P]),
     "ofdmx_fft": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P]),
     "ofdmx_crc32": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "ofdmx_agc2": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
 }
 
 _lib = None

@@ -1,8 +1,10 @@
-"""Hot-path part of python/ofdm_cr_tools.py: the carrier-plan / sync-word generators.
+"""Hot-path part of python/ofdm_cr_tools.py: the carrier-plan / sync-word generators, plus the MAC framing
+helpers either side of the PHY.
 
-Only `_make_sync_word1` (1.42-amplitude variant, :262-279), `_make_sync_word2` (:282-293) and
-`spectrum_enforcer` (:348-378) are on the OFDM PHY path; the rest of that file (PSD helpers, MAC
-framing, loggers) is out of scope.
+`_make_sync_word1` (1.42-amplitude variant, :262-279), `_make_sync_word2` (:282-293) and
+`spectrum_enforcer` (:348-378) are on the OFDM PHY path; `make_packet` / `unmake_packet` (:1741-1773) are
+the next row of SURVEY.md 8(f) (rank 3).  The rest of that file (PSD helpers, loggers, cognitive engine) is
+out of scope.
 """
 from . import phy
 
@@ -44,3 +46,46 @@ def spectrum_enforcer(fft_len, spectrum_constraint_fft, lobe_len):
     sync_word1 = _make_sync_word1(fft_len, occupied_carriers, pilot_carriers)
     sync_word2 = _make_sync_word2(fft_len, occupied_carriers, pilot_carriers)
     return occupied_carriers, pilot_carriers, _pilot_symbols, sync_word1.tolist(), sync_word2.tolist()
+
+
+# ---- MAC framing either side of the PHY -----------------------------------
+# Host-side byte-string helpers, as in the reference; bytes in / bytes out (the reference is Python 2 str).
+from . import crc as _crc  # noqa: E402
+
+
+def _b(s):
+    return s.encode('latin-1') if isinstance(s, str) else bytes(s)
+
+
+def make_packet(payload, pkt_size, type_pkt):
+    """python/ofdm_cr_tools.py:1741-1748: 4 ASCII digits of payload length + 1 type byte + payload +
+    0x55 padding up to pkt_size bytes."""
+    payload, type_pkt = _b(payload), _b(type_pkt)
+    length = len(payload)
+    digits = str(length).encode()
+    header = (4 - len(digits)) * b'0' + digits
+    packing = (pkt_size - (5 + length)) * b'\x55'
+    return header + type_pkt + payload + packing
+
+
+def unmake_packet(frame, w_crc):
+    """python/ofdm_cr_tools.py:1750-1773.  w_crc true: the in-flowgraph CRC already validated the frame;
+    false: the frame ends in the MAC-level CRC-32 (digital.crc.check_crc32).  Returns (payload, type, ok);
+    ('BAD', 'BAD', False) on a CRC failure, as the reference does."""
+    frame = _b(frame)
+    if w_crc:
+        try:
+            pld_len = int(frame[0:4])
+            tpe = frame[4:5]
+            return frame[5:5 + pld_len], tpe, True
+        except Exception:
+            return None
+    ok, frame = _crc.check_crc32(frame)
+    if not ok:
+        return 'BAD', 'BAD', ok
+    try:
+        pld_len = int(frame[0:4])
+        tpe = frame[4:5]
+        return frame[5:5 + pld_len], tpe, ok
+    except Exception:
+        return None

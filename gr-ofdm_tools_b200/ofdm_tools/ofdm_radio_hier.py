@@ -7,9 +7,13 @@ spectrum_enforcer(128, [], 10), python/ofdm_cr_tools.py:348-378).  Derived value
 scramble_header=True, chanest max_carr_offset=3, x0.01 TX scaling.
 
 Selectors (:137-178) become plain flags: scramble_mode (payload scrambler 0x7f), crc_mode (in-graph
-crc32_bb on both paths).  clipper_mode / filter_mode (TX clipper and 8th-order IIR, SURVEY.md 8(f)
-rank 2) and the RX AGC (rank 1) are not built: the flags are stored, TX output is the unconditioned
-x0.01 signal.
+crc32_bb on both paths), clipper_mode (ofdm_tools.clipper(clipping_factor) after the x0.01 scaling, :92,
+:229,:239 -- fused into the TX kernel as tx_clip).  The RX AGC (analog.agc2_cc(1e-1, 1e-2, 1.0, 1.0),
+max gain 65536, :180-181) runs in front of the receiver as in the reference; its loop gain is carried from
+one rx() call to the next.  It is a per-sample non-linear recurrence: streams are processed in parallel,
+the samples of one stream sequentially, so pass agc=False to rx() for long single streams whose level is
+already normalised.  filter_mode (8th-order iir_filter_ccd out-of-band filter) is
+not built: the flag is stored and the TX output is the unfiltered signal.
 """
 from .phy import OfdmPhy
 
@@ -61,8 +65,10 @@ class ofdm_radio_hier(object):
                            pilot_carriers=pilot_carriers, pilot_symbols=pilot_symbols,
                            sync_word1=sync_word1, sync_word2=sync_word2, bps_header=1, bps_payload=bps,
                            scramble_bits=bool(scramble_mode), scramble_header=True, crc_mode=int(crc_mode),
-                           max_carr_offset=3, tx_scale=0.01, **phy_kwargs)
+                           max_carr_offset=3, tx_scale=0.01,
+                           tx_clip=float(clipping_factor) if int(clipper_mode) else 0.0, **phy_kwargs)
         self._pkt_num = 0
+        self._agc_gain = None
 
     # port 0 (bytes) in -> port 1 (samples) out
     def tx(self, packets):
@@ -71,7 +77,9 @@ class ofdm_radio_hier(object):
         return out
 
     # port 1 (samples) in -> port 0 (bytes) out
-    def rx(self, samples, **kw):
+    def rx(self, samples, agc=True, **kw):
+        if agc:
+            samples, self._agc_gain = self.phy.agc2(samples, self._agc_gain, 1e-1, 1e-2, 1.0, 65536.0)
         return self.phy.rx(samples, **kw)
 
     # accessors as generated by GRC in the reference (python/ofdm_radio_hier.py:247-371); as there,

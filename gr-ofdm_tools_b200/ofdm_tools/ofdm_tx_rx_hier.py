@@ -1,9 +1,10 @@
 """B200 drop-in for python/ofdm_tx_rx_hier.py: `ofdm_tx_rx_hier(fft_len=64, payload_bps=2)`.
 
 TX path: ofdm_tx -> tag_gate -> x0.01 (python/ofdm_tx_rx_hier.py:55-63,74,85-87); the x0.01 is
-fused into the IFFT store.  RX path: ofdm_rx (:64-73).  The reference puts analog.agc2_cc in front
-of ofdm_rx (:75-76); that per-sample recurrence is SURVEY.md 8(f) rank 1 and not built yet, so parity
-is defined at the ofdm_rx input.
+fused into the IFFT store.  RX path: analog.agc2_cc(1e-1, 1e-2, 1.0, 1.0) with max gain 65536 (:75-76,
+:82-83) -> ofdm_rx (:64-73).  The AGC is a per-sample non-linear recurrence: streams run in parallel, the
+samples of one stream sequentially; its loop gain is carried from one rx() call to the next (pass
+agc=False to skip it for long, already normalised single streams).
 """
 from . import ofdm_txrx_modules
 
@@ -27,7 +28,10 @@ class ofdm_tx_rx_hier(object):
         return self.ofdm_tx.work(packets)
 
     # port 1 in -> port 0 out
-    def rx(self, samples, **kw):
+    def rx(self, samples, agc=True, **kw):
+        if agc:
+            samples, self._agc_gain = self.ofdm_rx.phy.agc2(samples, getattr(self, "_agc_gain", None),
+                                                            1e-1, 1e-2, 1.0, 65536.0)
         return self.ofdm_rx.work(samples, **kw)
 
     def get_fft_len(self):

@@ -94,7 +94,7 @@ class OfdmPhy(object):
                  pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
                  max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None,
-                 max_pkt_bytes=4095, device=0):
+                 max_pkt_bytes=4095, device=0, tx_clip=0.0):
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occupied_carriers = [list(map(int, s)) for s in occupied_carriers]
         self.pilot_carriers = [list(map(int, s)) for s in pilot_carriers]
@@ -139,6 +139,7 @@ class OfdmPhy(object):
         p.threshold, p.max_carr_offset, p.alpha, p.tx_scale = threshold, max_carr_offset, alpha, tx_scale
         p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
         p.max_pkt_bytes = self.max_pkt_bytes
+        p.tx_clip = float(tx_clip)
         self.params = p
         self._ctx = None
 
@@ -344,3 +345,25 @@ class OfdmPhy(object):
         _lib.check(_lib.load().ofdmx_crc32(self.ctx, payload.data_ptr(), off.data_ptr(), len(lens), out.data_ptr(),
                                            self._stream()), self.ctx)
         return out[: len(lens)].cpu().numpy().astype(np.uint32)
+
+    def agc2(self, samples, gain=None, attack=1e-1, decay=1e-2, reference=1.0, max_gain=65536.0, out=None):
+        """analog.agc2_cc(attack, decay, reference, 1.0) + set_max_gain, the block in front of ofdm_rx in both
+        hier surfaces (python/ofdm_tx_rx_hier.py:75-76, python/ofdm_radio_hier.py:180-181).  samples: cuda
+        complex64 [n] or [n_streams, n]; gain: None (1.0 per stream, a fresh block) or a cuda float32
+        [n_streams] tensor holding the loop gain left by the previous call -- it is updated in place.
+        Returns (out, gain).  Streams run in parallel, samples of one stream sequentially."""
+        torch = self._torch()
+        if samples.dim() == 1:
+            samples = samples.unsqueeze(0)
+        assert samples.is_cuda and samples.dtype == torch.complex64 and samples.stride(1) == 1
+        n_streams, n = samples.shape
+        if gain is None:
+            gain = torch.ones(n_streams, dtype=torch.float32, device=samples.device)
+        assert gain.is_cuda and gain.dtype == torch.float32 and gain.numel() == n_streams and gain.is_contiguous()
+        if out is None:
+            out = torch.empty_like(samples)
+        assert out.shape == samples.shape and out.stride() == samples.stride()
+        _lib.check(_lib.load().ofdmx_agc2(self.ctx, samples.data_ptr(), out.data_ptr(), n_streams, n,
+                                          samples.stride(0) if n_streams > 1 else max(n, 1), attack, decay, reference,
+                                          max_gain, gain.data_ptr(), self._stream()), self.ctx)
+        return out, gain

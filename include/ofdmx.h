@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OFDMX_ABI_VERSION 1
+#define OFDMX_ABI_VERSION 2
 
 typedef enum {
     OFDMX_OK = 0,
@@ -75,6 +75,9 @@ typedef struct {
     int32_t demux_holdoff;          /* header_payload_demux: items left unconsumed after a payload:
                                        fft_len+cp_len (GNU Radio < 3.7.10) or 1 (>= 3.7.10) */
     int32_t max_pkt_bytes;          /* largest header length field the caller sizes slots for (<=4095) */
+    float   tx_clip;                /* ofdm_tools.clipper(clipping_factor) fused after the scaling: re and im
+                                       railed to +-tx_clip (python/clipper.py:45-58,
+                                       python/ofdm_radio_hier.py:92,229,239); 0 = no clipper */
 } ofdmx_params;
 
 /* Per-frame record (replaces the stream tags / PMT header dict of the reference). 32 bytes. */
@@ -166,6 +169,16 @@ int ofdmx_fft(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_sym
 /* digital.crc32_bb arithmetic: zlib CRC-32 of each packet */
 int ofdmx_crc32(ofdmx_ctx *ctx, const uint8_t *bytes_dev, const int64_t *pkt_offsets_dev,
                 int64_t n_pkts, uint32_t *crc_out_dev, void *cuda_stream);
+
+/* ---- conditioning around the chain ---- */
+/* analog.agc2_cc(attack, decay, reference, gain) + set_max_gain(max_gain), the block both hier surfaces put in
+ * front of ofdm_rx (python/ofdm_tx_rx_hier.py:75-76,82-83; python/ofdm_radio_hier.py:180-181).  The gain
+ * recurrence is sequential per stream; streams run in parallel.  gain_io_dev[n_streams]: loop gain before the
+ * first sample on entry, after the last sample on return, so consecutive calls continue the stream exactly.
+ * in_dev == out_dev is allowed.  stride in complex samples. */
+int ofdmx_agc2(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n,
+               int64_t stride, float attack, float decay, float reference, float max_gain,
+               float *gain_io_dev, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -452,8 +452,13 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
             float *o_ = samples_out + 2 * (pos + (int64_t)o * (n + cp));
             for (int m = 0; m < n + cp; m++) {
                 cd v = td[(m - cp + n) % n] * (double)p->tx_scale;
-                o_[2 * m] = (float)creal(v);
-                o_[2 * m + 1] = (float)cimag(v);
+                float vr = (float)creal(v), vi = (float)cimag(v);
+                if (p->tx_clip > 0.0f) {   /* analog.rail_ff(-c, c) on re and im (python/clipper.py:45-58) */
+                    vr = vr < -p->tx_clip ? -p->tx_clip : (vr > p->tx_clip ? p->tx_clip : vr);
+                    vi = vi < -p->tx_clip ? -p->tx_clip : (vi > p->tx_clip ? p->tx_clip : vi);
+                }
+                o_[2 * m] = vr;
+                o_[2 * m + 1] = vi;
             }
         }
         pos += (int64_t)n_ofdm * (n + cp);
@@ -882,4 +887,46 @@ int orc_rx_baseline(const orc_params *p, const float *r, int64_t n_samp,
 {
     return rx_impl(p, r, n_samp, recs, max_frames, bytes_out, byte_stride, NULL, 0, n_frames,
                    trig, cfo, max_trig, n_trig, 1);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Next rows.
+ *
+ * analog.agc2_cc: python/ofdm_tx_rx_hier.py:75-76, python/ofdm_radio_hier.py:180-181 construct
+ * agc2_cc(1e-1, 1e-2, 1.0, 1.0) and set_max_gain(65536).  [UPSTREAM gr-analog
+ * include/gnuradio/analog/agc2.h, kernel::agc2_cc::scale(), restated from memory -- parity unpinned:]
+ *     output = input * gain
+ *     tmp    = -reference + sqrt(output.re^2 + output.im^2)
+ *     rate   = (tmp > gain) ? attack : decay
+ *     gain  -= tmp * rate
+ *     if (gain < 0) gain = 10e-5;  if (max_gain > 0 && gain > max_gain) gain = max_gain
+ * All in float32, one rounding per operation (this file is compiled with -ffp-contract=off). */
+void orc_agc2(const float *in, float *out, int64_t n, float attack, float decay, float reference,
+              float max_gain, float *gain)
+{
+    float g = *gain;
+    for (int64_t i = 0; i < n; i++) {
+        const float re = in[2 * i] * g, im = in[2 * i + 1] * g;
+        out[2 * i] = re;
+        out[2 * i + 1] = im;
+        const float rr = re * re, ii = im * im;
+        const float tmp = -reference + sqrtf(rr + ii);
+        const float rate = (tmp > g) ? attack : decay;
+        g -= tmp * rate;
+        if (g < 0.0f) g = 10e-5f;
+        if (max_gain > 0.0f && g > max_gain) g = max_gain;
+    }
+    *gain = g;
+}
+
+/* MAC-level CRC-32: [UPSTREAM gr-digital/lib/crc32.cc update_crc32: table-driven,
+ * crc = (crc << 8) ^ table[((crc >> 24) ^ byte) & 0xFF], init 0xFFFFFFFF, result ^ 0xFFFFFFFF]. */
+uint32_t orc_crc32_mac(const uint8_t *buf, int64_t len)
+{
+    uint32_t crc = 0xFFFFFFFFu;
+    for (int64_t i = 0; i < len; i++) {
+        crc ^= (uint32_t)buf[i] << 24;
+        for (int k = 0; k < 8; k++) crc = (crc & 0x80000000u) ? (crc << 1) ^ 0x04C11DB7u : (crc << 1);
+    }
+    return crc ^ 0xFFFFFFFFu;
 }

@@ -55,6 +55,8 @@ typedef struct {
     float   tx_scale;               /* multiply_const after the cyclic prefixer; 1.0 for bare ofdm_tx */
     int32_t demux_holdoff;          /* items left unconsumed after a payload:
                                        fft_len+cp_len (GNU Radio < 3.7.10) or 1 (>= 3.7.10) */
+    float   tx_clip;                /* ofdm_tools.clipper(clipping_factor) after the scaling: re and im railed to
+                                       +-tx_clip (python/clipper.py:45-58, ofdm_radio_hier.py:92,229); 0 = off */
 } orc_params;
 
 typedef struct {
@@ -114,6 +116,17 @@ int orc_rx(const orc_params *p, const float *samples, int64_t n,
 int orc_rx_baseline(const orc_params *p, const float *samples, int64_t n,
                     orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
                     int64_t *n_frames, int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig);
+
+/* ---- next rows of SURVEY.md 8(f) ---- */
+/* analog.agc2_cc(attack, decay, reference, gain) with set_max_gain (python/ofdm_tx_rx_hier.py:75-76,
+ * python/ofdm_radio_hier.py:180-181): one stream, float32 arithmetic in GNU Radio's order.
+ * *gain: loop gain before the first sample on entry, after the last sample on return. */
+void orc_agc2(const float *in, float *out, int64_t n, float attack, float decay, float reference,
+              float max_gain, float *gain);
+/* digital.crc32() of gr-digital/lib/crc32.cc as used by digital.crc.gen_and_append_crc32
+ * (examples/benchmarks.py:347, python/ofdm_cr_tools.py:1760): MSB-first, poly 0x04C11DB7,
+ * init and final XOR 0xFFFFFFFF; check value 0xFC891918. */
+uint32_t orc_crc32_mac(const uint8_t *buf, int64_t len);
 
 #ifdef __cplusplus
 }

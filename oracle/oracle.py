@@ -38,7 +38,7 @@ class _Params(C.Structure):
         ("bps_header", C.c_int32), ("bps_payload", C.c_int32),
         ("scramble_header", C.c_int32), ("scramble_seed", C.c_int32),
         ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
-        ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32),
+        ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32), ("tx_clip", C.c_float),
     ]
 
 
@@ -71,6 +71,10 @@ def lib():
         L.orc_fft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_tx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                              C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_agc2.restype = None
+        L.orc_agc2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orc_crc32_mac.restype = C.c_uint32
+        L.orc_crc32_mac.argtypes = [C.c_void_p, C.c_int64]
         L.orc_tx_frame_samples.restype = C.c_int64
         L.orc_tx_frame_samples.argtypes = [C.c_void_p, C.c_int64]
         L.orc_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
@@ -149,7 +153,7 @@ class Oracle:
     def __init__(self, fft_len=64, cp_len=16, occupied_carriers=None, pilot_carriers=None,
                  pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
-                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None):
+                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None, tx_clip=0.0):
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occ = [list(map(int, s)) for s in occupied_carriers]
         self.pil = [list(map(int, s)) for s in pilot_carriers]
@@ -183,6 +187,7 @@ class Oracle:
         p.crc_mode = self.crc_mode
         p.threshold, p.max_carr_offset, p.alpha, p.tx_scale = threshold, max_carr_offset, alpha, tx_scale
         p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
+        p.tx_clip = float(tx_clip)
         self.p = p
         self.L = lib()
 
@@ -303,6 +308,26 @@ def crc32(data):
 def crc8(data):
     a = np.frombuffer(bytes(data), np.uint8)
     return lib().orc_crc8(_ptr(a) if len(a) else None, len(a))
+
+
+def crc32_mac(data):
+    """MSB-first CRC-32 of digital.crc.gen_and_append_crc32."""
+    a = np.frombuffer(bytes(data), np.uint8)
+    return lib().orc_crc32_mac(_ptr(a) if len(a) else None, len(a))
+
+
+def agc2(samples, gain=1.0, attack=1e-1, decay=1e-2, reference=1.0, max_gain=65536.0):
+    """analog.agc2_cc over one stream (or each row of a 2-D array).  Returns (out, final gain(s))."""
+    x = np.ascontiguousarray(samples, np.complex64)
+    one = x.ndim == 1
+    x2 = x[None, :] if one else x
+    out = np.empty_like(x2)
+    g = np.broadcast_to(np.asarray(gain, np.float32), (x2.shape[0],)).copy()
+    for s in range(x2.shape[0]):
+        gs = np.array([g[s]], np.float32)
+        lib().orc_agc2(_ptr(x2[s]), _ptr(out[s]), x2.shape[1], attack, decay, reference, max_gain, _ptr(gs))
+        g[s] = gs[0]
+    return (out[0], float(g[0])) if one else (out, g)
 
 
 def lfsr_bits(mask, seed, reg_len, n):

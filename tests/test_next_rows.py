@@ -1,0 +1,251 @@
+"""AGC front end (rank 1), TX clipper (rank 2), MAC framing + PDU adaptors (rank 3).
+CPU part: oracle restatements against known answers and properties, host-side framing.  GPU part
+(-m gpu): CUDA kernels through the C ABI, bit-exact against the oracle."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import common as cm
+
+
+# ------------------------------------------------------------------------------------------- CPU
+def test_mac_crc32_check_values():
+    """MSB-first CRC-32 of digital.crc (SURVEY.md A.13 check value) in the oracle and in the host module."""
+    import oracle as O
+    from ofdm_tools import crc
+    assert O.crc32_mac(b"123456789") == 0xFC891918
+    assert crc.crc32(b"123456789") == 0xFC891918
+    assert O.crc32(b"123456789") == 0xCBF43926          # the in-graph one is a different CRC
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 3, 4, 5, 63, 64, 1000):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert crc.crc32(b) == O.crc32_mac(b)
+        framed = crc.gen_and_append_crc32(b)
+        assert framed[:-4] == b and struct.unpack(">I", framed[-4:])[0] == O.crc32_mac(b)
+        assert crc.check_crc32(framed) == (True, b)
+        if n:
+            bad = bytes([framed[0] ^ 1]) + framed[1:]
+            assert crc.check_crc32(bad)[0] is False
+    assert crc.check_crc32(b"abc") == (False, b"")
+
+
+def test_make_unmake_packet():
+    """python/ofdm_cr_tools.py:1741-1773 and the way examples/benchmarks.py:343-349 uses them."""
+    from ofdm_tools import crc
+    from ofdm_tools.ofdm_cr_tools import make_packet, unmake_packet
+    pkt = make_packet("0007" + "ab" * 15, 96, 'A')
+    assert len(pkt) == 96 and pkt[:4] == b"0034" and pkt[4:5] == b"A" and pkt[5:39] == b"0007" + b"ab" * 15
+    assert set(pkt[39:]) == {0x55}
+    assert unmake_packet(pkt, True) == (b"0007" + b"ab" * 15, b"A", True)
+    framed = crc.gen_and_append_crc32(make_packet(b"xyz", 96 - 4, b'B'))
+    assert len(framed) == 96
+    assert unmake_packet(framed, False) == (b"xyz", b"B", True)
+    corrupt = framed[:10] + bytes([framed[10] ^ 0x40]) + framed[11:]
+    assert unmake_packet(corrupt, False) == ('BAD', 'BAD', False)
+
+
+def test_pdu_adaptors_host():
+    """payload_source_pdu appends the in-graph CRC-32 (crc32_async_bb(False)), payload_sink_pdu checks and
+    strips it and calls callback(addr, tpe, nr, payload) (python/ofdm_cr_tools.py:2124-2151)."""
+    from ofdm_tools import payload_source_pdu, payload_sink_pdu
+    src = payload_source_pdu()
+    src.post_message(1, 2, 3, "hello")
+    src.post_message(9, 8, 7, b"\x00\xff" * 40)
+    pk = src.pop_packets()
+    assert pk[0][:3] == b"\x01\x02\x03" and pk[0][3:-4] == b"hello"
+    assert struct.unpack("<I", pk[0][-4:])[0] == zlib.crc32(pk[0][:-4]) & 0xFFFFFFFF
+    got = []
+    snk = payload_sink_pdu(lambda a, t, n, p: got.append((a, t, n, p)))
+    bad = pk[1][:5] + bytes([pk[1][5] ^ 1]) + pk[1][6:]
+    out = snk.deliver([pk[0], bad, pk[1], b"ab"])
+    assert got == [(1, 2, 3, b"hello"), (9, 8, 7, b"\x00\xff" * 40)]
+    assert out == [pk[0][:-4], pk[1][:-4]] and (snk.n_rcvd, snk.n_right) == (4, 2)
+
+
+def test_oracle_agc2_properties():
+    """agc2_cc restatement: hand-computed first steps, attack vs decay branch, clamps, and convergence of
+    the output level to the reference on a constant-envelope input."""
+    import oracle as O
+    f = np.float32
+    x = np.array([3 + 4j, 0.1 + 0j, 0, 1e-9], np.complex64)
+    y, g = O.agc2(x, gain=1.0)
+    # sample 0: out = 3+4j, |out| = 5, tmp = 4 > gain 1 -> attack 0.1: gain = 1 - 0.4 = 0.6
+    assert y[0] == 3 + 4j
+    g0 = f(1.0) - f(4.0) * f(0.1)
+    assert y[1] == np.complex64(complex(f(0.1) * g0, 0.0))
+    # sample 1: |out| = 0.06, tmp = -0.94 -> decay: gain += 0.0094
+    tmp1 = f(-1.0) + np.sqrt(f(f(0.1) * g0) * f(f(0.1) * g0), dtype=f)
+    g1 = f(g0 - f(tmp1 * f(0.01)))
+    assert y[2] == 0 and y[3] == np.complex64(complex(f(1e-9) * f(g1 - f(f(-1.0) * f(0.01))), 0.0))
+    # negative gain is replaced by 10e-5, the ceiling by max_gain
+    _, g = O.agc2(np.array([1000 + 0j], np.complex64), gain=1.0)
+    assert g == pytest.approx(10e-5)
+    _, g = O.agc2(np.zeros(10, np.complex64), gain=65535.995, max_gain=65536.0)
+    assert g == 65536.0
+    # convergence: constant envelope 7.3 -> output magnitude -> 1.0
+    t = np.arange(5000)
+    y, g = O.agc2((7.3 * np.exp(0.1j * t)).astype(np.complex64))
+    assert abs(np.abs(y[-1]) - 1.0) < 1e-3 and abs(g - 1 / 7.3) < 1e-3
+    # chunked == whole (state carried through the gain)
+    xr = (np.random.default_rng(1).standard_normal(2000) * 3).astype(np.complex64)
+    ya, ga = O.agc2(xr)
+    yb1, gb = O.agc2(xr[:777])
+    yb2, gb = O.agc2(xr[777:], gain=gb)
+    assert np.array_equal(ya, np.concatenate([yb1, yb2])) and ga == gb
+
+
+def test_oracle_tx_clip():
+    import oracle as O
+    cfg = cm.cfg_radio128(2, 1, 1)
+    cfg["tx_scale"] = 0.01
+    rng = np.random.default_rng(3)
+    pk = cm.rand_packets(rng, 3, 100)
+    s0, off0 = O.Oracle(**cfg).tx(pk)
+    s1, off1 = O.Oracle(tx_clip=0.05, **cfg).tx(pk)
+    assert np.array_equal(off0, off1)
+    ref = np.clip(s0.real, -0.05, 0.05) + 1j * np.clip(s0.imag, -0.05, 0.05)
+    assert np.array_equal(s1, ref.astype(np.complex64))
+    assert np.abs(s0.real).max() > 0.05                      # the rail is active on this signal
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def _dev():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _agc_input(rng, n_streams, n):
+    """Per-stream level steps over 9 decades, silences and bursts."""
+    x = (rng.standard_normal((n_streams, n)) + 1j * rng.standard_normal((n_streams, n))).astype(np.complex64)
+    for s in range(n_streams):
+        cuts = np.sort(rng.integers(0, n, 4))
+        lev = 10.0 ** rng.uniform(-6, 3, 5)
+        seg = np.split(np.arange(n), cuts)
+        for k, idx in enumerate(seg):
+            x[s, idx] *= np.float32(lev[k]) if (s + k) % 7 else np.float32(0.0)
+    return x
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_streams,n", [(1, 5000), (3, 1), (32, 31), (33, 1000), (70, 3001), (257, 640)])
+def test_agc2_parity(n_streams, n):
+    """ofdmx_agc2 against the oracle: output samples and final loop gains bit-exact; two chunked calls equal
+    one call (gain state carried); in place."""
+    import torch
+    import oracle as O
+    rng = np.random.default_rng(100 + n_streams)
+    x = _agc_input(rng, n_streams, n)
+    ref, gref = O.agc2(x)
+    phy = cm.make_phy(cm.cfg_c1())
+    xd = torch.from_numpy(x).to(_dev())
+    y, g = phy.agc2(xd)
+    assert np.array_equal(y.cpu().numpy().view(np.float32), ref.view(np.float32))
+    assert np.array_equal(g.cpu().numpy(), gref)
+    if n >= 2:
+        k = n // 3 + 1
+        buf = xd.clone()
+        _, g2 = phy.agc2(buf[:, :k].contiguous(), out=None)
+        ya, g2 = phy.agc2(xd[:, :k].contiguous())
+        yb, g2 = phy.agc2(xd[:, k:].contiguous(), gain=g2)
+        assert np.array_equal(torch.cat([ya, yb], 1).cpu().numpy().view(np.float32), ref.view(np.float32))
+        assert np.array_equal(g2.cpu().numpy(), gref)
+    z = xd.clone()
+    phy.agc2(z, out=z)
+    assert np.array_equal(z.cpu().numpy().view(np.float32), ref.view(np.float32))
+    # custom rates / reference / no ceiling
+    ref2, gref2 = O.agc2(x, gain=np.full(n_streams, 0.25, np.float32), attack=0.5, decay=1e-3, reference=0.3, max_gain=0.0)
+    y2, g2 = phy.agc2(xd, gain=torch.full((n_streams,), 0.25, device=_dev()), attack=0.5, decay=1e-3, reference=0.3, max_gain=0.0)
+    assert np.array_equal(y2.cpu().numpy().view(np.float32), ref2.view(np.float32)) and np.array_equal(g2.cpu().numpy(), gref2)
+
+
+@pytest.mark.gpu
+def test_tx_clip_parity():
+    """clipper fused into the TX kernel (ofdm_radio_hier clipper_mode=1) against the oracle."""
+    import oracle as O
+    cfg = cm.cfg_radio128(2, 1, 1)
+    cfg["tx_scale"] = 0.01
+    rng = np.random.default_rng(8)
+    pk = cm.rand_packets(rng, 5, 350)
+    ref, off = O.Oracle(tx_clip=0.05, **cfg).tx(pk)
+    s, soff = cm.make_phy(cfg, tx_clip=0.05).tx(pk)
+    s = s.cpu().numpy()
+    assert np.array_equal(soff.cpu().numpy(), off)
+    assert np.abs(s.real).max() <= np.float32(0.05) and np.abs(s.imag).max() <= np.float32(0.05)
+    assert (np.abs(s.real) == np.float32(0.05)).sum() > 10
+    assert np.linalg.norm(s - ref) / np.linalg.norm(ref) < 1e-5
+    # stand-alone block
+    import torch
+    from ofdm_tools import clipper
+    raw, _ = cm.make_phy(cfg).tx(pk)
+    c = clipper(0.05).work(raw).cpu().numpy()
+    assert np.array_equal(c, s)
+
+
+@pytest.mark.gpu
+def test_hier_facades_with_agc_and_clipper():
+    """ofdm_radio_hier / ofdm_tx_rx_hier with the RX AGC in front (reference wiring) on a nominal signal, one
+    1000x too weak and one 300x too strong: identical frames and payloads to oracle AGC -> oracle RX; the
+    AGC state is carried across rx() calls.  (On the 300x signal the fast attack of agc2_cc(1e-1, 1e-2)
+    modulates the envelope inside the OFDM symbols and every 16-QAM packet fails its CRC -- in the oracle
+    too: that case pins the parity of the failure path.)"""
+    import torch
+    import oracle as O
+    from ofdm_tools import ofdm_radio_hier, ofdm_tx_rx_hier
+    rng = np.random.default_rng(77)
+    radio = ofdm_radio_hier(payload_mod='qam16', scramble_mode=1, crc_mode=1, clipper_mode=1, clipping_factor=0.3)
+    pk = cm.rand_packets(rng, 6, 200)
+    s, off = radio.tx(pk)
+    s = s.cpu().numpy()
+    assert np.abs(s.real).max() <= np.float32(0.3)
+    cfg = cm.cfg_radio128(4, 1, 1)
+    cfg.update(tx_scale=0.01, max_carr_offset=3, scramble_header=True)
+    orc = O.Oracle(**cfg)
+    for scale in (1.0, 1e-3, 300.0):
+        x = cm.channel(cm.split_frames(s, off.cpu().numpy()), rng, gaps=(300, 900), tail=2000, snr_db=45.0, cfo=0.1,
+                       fft_len=128, scale=scale)
+        radio._agc_gain = None
+        res = radio.rx(torch.from_numpy(x).to(_dev()))
+        xa, g = O.agc2(x)
+        ref = orc.rx(xa, byte_stride=radio.phy.byte_stride, want_z=False)
+        assert np.array_equal(res.frames["trigger"], ref["frames"]["trigger"])
+        assert np.array_equal(res.frames["flags"] & 7, ref["frames"]["flags"] & 7)
+        assert res.payloads() == orc.payloads(ref)
+        assert (res.payloads() == pk) == (scale <= 1.0)
+        assert float(radio._agc_gain[0]) == g
+        # second call continues the loop gain
+        res2 = radio.rx(torch.from_numpy(x).to(_dev()))
+        xb, g2 = O.agc2(x, gain=g)
+        assert float(radio._agc_gain[0]) == g2
+        assert res2.payloads() == orc.payloads(orc.rx(xb, byte_stride=radio.phy.byte_stride, want_z=False))
+    trx = ofdm_tx_rx_hier(fft_len=64, payload_bps=2)
+    pk = cm.rand_packets(rng, 4, 96)
+    s, off = trx.tx(pk)
+    x = cm.channel(cm.split_frames(s.cpu().numpy(), off.cpu().numpy()), rng, gaps=(200, 500), tail=1500, snr_db=35.0,
+                   fft_len=64, scale=0.02)
+    c1 = cm.cfg_c1()
+    c1.update(bps_payload=2)
+    o1 = O.Oracle(**c1)
+    ref = o1.rx(O.agc2(x)[0], want_z=False)
+    assert trx.rx(torch.from_numpy(x).to(_dev())).payloads() == o1.payloads(ref) == pk
+
+
+@pytest.mark.gpu
+def test_pdu_adaptors_gpu_crc():
+    """payload_source_pdu / payload_sink_pdu with the CRC-32 batch computed by the CUDA crc32 kernel."""
+    from ofdm_tools import payload_source_pdu, payload_sink_pdu
+    phy = cm.make_phy(cm.cfg_c1())
+    rng = np.random.default_rng(2)
+    src, host = payload_source_pdu(phy=phy), payload_source_pdu()
+    for n in (0, 1, 5, 100, 1500):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        src.post_message(1, 2, n & 0xFF, b)
+        host.post_message(1, 2, n & 0xFF, b)
+    pk = src.pop_packets()
+    assert pk == host.pop_packets()
+    got = []
+    snk = payload_sink_pdu(lambda a, t, n, p: got.append(p), phy=phy)
+    snk.deliver(pk[:2] + [pk[2][:-1] + bytes([pk[2][-1] ^ 0x80])] + pk[3:])
+    assert [len(p) for p in got] == [0, 1, 100, 1500]

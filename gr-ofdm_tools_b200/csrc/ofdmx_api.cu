@@ -6,6 +6,7 @@
 #include "ofdmx_frame1024.cuh"
 #include "ofdmx_frame1024w.cuh"
 #include "ofdmx_cond.cuh"
+#include "ofdmx_sync_warp.cuh"
 #include "ofdmx_chain.cuh"
 
 #include <algorithm>
@@ -31,12 +32,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "trig_count_kernel", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel" };
+    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -64,6 +65,8 @@ struct ofdmx_ctx {
     size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0, frame1k_smem = 0, sync_tma_smem = 0;
     int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
     bool no_tma = false;            // OFDMX_NO_TMA=1: use the plain-load sync kernel
+    bool no_warp_sync = false;      // OFDMX_NO_WARP_SYNC=1: fft_len 1024 uses the TMA ring kernel instead of the warp-autonomous one
+    bool sync_warp_ok = false;
     bool emit_all = false;          // ofdmx_set_emit_all: frames_out receives every trigger's record
     bool no_warp_frame = false;     // OFDMX_NO_WARP_FRAME=1: use the CTA-per-frame fft_len-1024 kernel
     bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
@@ -328,7 +331,20 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
     ofdmx_ctx *ctx_ = ctx;
     CUDA_TRY(ctx, cudaMemsetAsync(w.blocksum, 0, sizeof(int) * (size_t)(w.nb + 1), st));   // per-block trigger counts (plateau_kernel)
     CUtensorMap tmap;
-    if (kp.N >= 32 && !ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
+    if (kp.N == 1024 && ctx->sync_warp_ok && !ctx->no_warp_sync && !ctx->no_tma && (reinterpret_cast<uintptr_t>(samples) & 15) == 0
+        && (n_streams == 1 || (stride & 1) == 0) && (n_samples / SW_TILE + 2) * n_streams < 0x7fffffffLL) {
+        // fft_len 1024: warp-autonomous streaming (no block barriers), spans of tiles of 512 samples per warp
+        const long long tiles = (n_samples + SW_TILE - 1) / SW_TILE;
+        const long long warps = (long long)ctx->sm_count * SW_WARPS;
+        long long span = (tiles * n_streams + 8 * warps - 1) / (8 * warps);
+        span = std::max<long long>(16, std::min<long long>(span, 1024));
+        const long long spans = (tiles + span - 1) / span;
+        const long long total = spans * n_streams;
+        const unsigned grid = (unsigned)std::min<long long>((total + SW_WARPS - 1) / SW_WARPS, (long long)ctx->sm_count);
+        KT(K_SYNC_WARP);
+        sync_metric_warp_kernel<<<grid, SW_WARPS * 32, SW_WARPS * SW_RING_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr,
+                                                                                      w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total);
+    } else if (kp.N >= 32 && !ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
         // TMA path: 3-D map {32 floats, rows of 16 samples, streams}; whole rows only (the kernel patches the tail)
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
         const long long spans = (tiles + ST_SPAN_TILES - 1) / ST_SPAN_TILES;
@@ -675,6 +691,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sync_metric_tma_kernel, SV_THREADS, c->sync_tma_smem) == cudaSuccess && occ > 0)
                 c->sync_tma_occ = occ;
         }
+        c->sync_warp_ok = (N == 1024) && cudaFuncSetAttribute(sync_metric_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                              SW_WARPS * SW_RING_BYTES) == cudaSuccess;
         c->sync_fast_smem = sync_fast_smem_bytes(N);
         if (cudaFuncSetAttribute(sync_metric_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
             || cudaFuncSetAttribute(sync_metric_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
@@ -690,6 +708,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     if (const char *fg = getenv("OFDMX_FORCE_GENERIC")) c->force_generic = (fg[0] == '1');
     if (const char *nw = getenv("OFDMX_NO_WARP_FRAME")) c->no_warp_frame = (nw[0] == '1');
     if (const char *nt = getenv("OFDMX_NO_TMA")) c->no_tma = (nt[0] == '1');   // plain-load sync kernel instead of the TMA ring
+    if (const char *ns = getenv("OFDMX_NO_WARP_SYNC")) c->no_warp_sync = (ns[0] == '1');
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
     *out = c;

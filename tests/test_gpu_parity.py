@@ -311,9 +311,13 @@ def test_generic_kernel_at_1024_matches_fast_path(monkeypatch):
     gen = cm.make_phy(cfg).rx(_to_dev(x), want_z=True)
     monkeypatch.setenv("OFDMX_FORCE_GENERIC", "0")
     monkeypatch.setenv("OFDMX_NO_TMA", "1")
-    tma = cm.make_phy(cfg).rx(_to_dev(x))          # plain-load sync kernel (the TMA ring kernel is the default)
+    tma = cm.make_phy(cfg).rx(_to_dev(x))          # plain-load sync kernel
+    monkeypatch.setenv("OFDMX_NO_TMA", "0")
+    monkeypatch.setenv("OFDMX_NO_WARP_SYNC", "1")
+    ring = cm.make_phy(cfg).rx(_to_dev(x))         # TMA ring sync kernel (fft_len 1024 defaults to the warp-autonomous one)
     assert np.array_equal(fast.frames, gen.frames) and fast.payloads() == gen.payloads() == pk
     assert np.array_equal(fast.frames, tma.frames) and tma.payloads() == pk
+    assert np.array_equal(fast.frames, ring.frames) and ring.payloads() == pk
     assert cm.rel_evm(fast.z.cpu().numpy()[:5, :3000], gen.z.cpu().numpy()[:5, :3000]) < 1e-5
 
 
@@ -383,3 +387,38 @@ def test_warp_frame_kernel_ragged_lengths(bps):
     res, ref = _compare_rx(cfg, stream, check_z=False)
     assert res.payloads() == pk
     assert np.all(res.frames["flags"] & 2)
+
+
+@pytest.mark.parametrize("n_streams,n,odd", [(1, 100000, False), (1, 77777, True), (3, 40001, False), (5, 3000, False),
+                                              (2, 600, False), (1, 16, False)])
+def test_sync_kernel_variants_detect_bits(monkeypatch, n_streams, n, odd):
+    """fft_len 1024: warp-autonomous sync kernel (default) vs TMA ring kernel vs plain-load kernel vs oracle on
+    streams with frames near both ends, odd lengths and several streams: identical triggers and CFO."""
+    cfg = cm.cfg_c3()
+    rng = np.random.default_rng(n + n_streams)
+    orc = cm.make_oracle(cfg)
+    pk, fr = _frames(cfg, rng, 2, 300)
+    xs = []
+    for s in range(n_streams):
+        x = 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        for o in (0, n // 2 + 37 * s, n - len(fr[0]) // 2):          # at the very start, mid, cut off at the end
+            if 0 <= o < n:
+                m = min(len(fr[0]), n - o)
+                x[o:o + m] += fr[s % 2][:m]
+        xs.append(x.astype(np.complex64))
+    x = np.stack(xs)
+    res = {}
+    for name, env in (("warp", {}), ("ring", {"OFDMX_NO_WARP_SYNC": "1"}), ("plain", {"OFDMX_NO_TMA": "1"})):
+        for k in ("OFDMX_NO_WARP_SYNC", "OFDMX_NO_TMA"):
+            monkeypatch.setenv(k, env.get(k, "0"))
+        phy = cm.make_phy(cfg)
+        res[name] = phy.sync(_to_dev(x if n_streams > 1 else x[0]))
+    ref_t, ref_s, ref_c = [], [], []
+    for s in range(n_streams):
+        t, c = orc.sync(x[s])
+        ref_t += list(t); ref_c += list(c); ref_s += [s] * len(t)
+    for name in ("warp", "ring", "plain"):
+        trig, cfo, st = res[name]
+        assert np.array_equal(trig, np.array(ref_t, np.int64)), name
+        assert np.array_equal(st, np.array(ref_s)), name
+        np.testing.assert_allclose(cfo, np.array(ref_c, np.float32), atol=2e-6, rtol=0)

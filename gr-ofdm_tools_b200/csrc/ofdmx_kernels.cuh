@@ -293,6 +293,25 @@ cfo_kernel(const float2 *__restrict__ samples, long long n, long long stride, in
         const long long t = trig[j];
         const float2 *r = samples + (long long)trig_stream[j] * stride;
         double sr = 0, si = 0;
+        if (t - 2 * h + 1 >= 0) {
+            // interior trigger: batches of 8 independent load pairs per lane (the rolled loop exposed one L2/HBM
+            // latency per 32 products)
+            const float2 *px = r + t - lane, *py = px - h;
+            for (int k0 = 0; k0 < h; k0 += 256) {
+                float2 x[8], y[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int k = k0 + 32 * u;
+                    if (k + lane < h) { x[u] = __ldg(px - k); y[u] = __ldg(py - k); }
+                    else { x[u] = make_float2(0.f, 0.f); y[u] = x[u]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    sr += (double)x[u].x * y[u].x + (double)x[u].y * y[u].y;
+                    si += (double)x[u].y * y[u].x - (double)x[u].x * y[u].y;
+                }
+            }
+        } else
         for (int k = lane; k < h; k += 32) {
             long long a = t - k, b = t - k - h;
             if (b < 0) continue;

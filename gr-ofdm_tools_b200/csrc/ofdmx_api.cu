@@ -73,6 +73,7 @@ struct ofdmx_ctx {
     bool frame1kw = false;          // fft_len 1024 warp-per-frame kernel eligible
     size_t frame1kw_smem = 0;
     int frame1kw_warps = FW_WARPS;
+    int frame1kw_dec_off = -1;      // float2 index inside the symbol buffer where the decisions live (-1: own array)
     uint32_t x_2048 = 0;            // x^(8*2048) mod P
     int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
 };
@@ -663,10 +664,29 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         {
             const int ngc = (kp.gpos - kp.gneg) / 2 + 1;
             const bool simple = (kp.n_occ_sets == 1 && kp.n_pil_sets <= 1 && !kp.pil_in_occ);
+            // guard band of the symbol buffer (natural bin order): the longest run of bins that no equaliser read
+            // (occupied carrier + any candidate offset) touches; the per-symbol decisions go there if they fit
+            c->frame1kw_dec_off = -1;
+            if (N == 1024) {
+                std::vector<char> used(1024, 0);
+                for (int u = 0; u < kp.n_occ_u; u++)
+                    for (int g = kp.gneg; g <= kp.gpos; g++) {
+                        const int b = occ_u[u] + g;
+                        if (b >= 0 && b < 1024) used[b ^ 512] = 1;
+                    }
+                int best = 0, best_at = -1, run = 0;
+                for (int i = 0; i < 1024; i++) {
+                    run = used[i] ? 0 : run + 1;
+                    if (run > best) { best = run; best_at = i - run + 1; }
+                }
+                const int at = (best_at + 1) & ~1;                       // 16-byte aligned
+                const int need = (kp.n_occ_u + 7) / 8 + 2;               // float2 slots for n_occ_u bytes
+                if (best_at >= 0 && at + need <= best_at + best) c->frame1kw_dec_off = at;
+            }
             c->frame1kw_warps = FW_WARPS;
-            while (c->frame1kw_warps > 4 && frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, kp.max_pkt_bytes, c->frame1kw_warps) > 227 * 1024)
+            while (c->frame1kw_warps > 4 && frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0) > 227 * 1024)
                 c->frame1kw_warps--;
-            c->frame1kw_smem = frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, kp.max_pkt_bytes, c->frame1kw_warps);
+            c->frame1kw_smem = frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0);
             c->frame1kw = (N == 1024 && simple && ngc <= 4 && kp.bps_h == 1 && c->hl >= 32 && c->hl <= 1024
                            && (occ_size[0] * kp.bps_p) % 8 == 0 && c->frame1kw_smem <= 227 * 1024);
             if (c->frame1kw) {
@@ -826,10 +846,10 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     do {                                                                                                           \
         if (z_out) rx_frame1024w_kernel<B, true><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(               \
             c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,         \
-            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048);                                         \
+            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off);                                         \
         else rx_frame1024w_kernel<B, false><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(                    \
             c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,         \
-            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048);                                         \
+            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off);                                         \
     } while (0)
         switch (c->kp.bps_p) {
         case 1: FW_LAUNCH(1); break;

@@ -15,7 +15,7 @@
 #pragma once
 #include "ofdmx_frame1024.cuh"
 
-#define FW_WARPS 15
+#define FW_WARPS 16
 #define FW_THREADS (FW_WARPS * 32)
 #ifndef FW_DFE_UNROLL
 #define FW_DFE_UNROLL 1
@@ -67,7 +67,8 @@ __device__ __forceinline__ uint32_t crc32_warp(const uint8_t *msg, int len, cons
     return total ^ 0xFFFFFFFFu;
 }
 
-// Same CRC for a 16-byte aligned message of >= 4 bytes, by words with slicing-by-4 (tab = T0|T1|T2|T3, 1024 entries).
+// Same CRC for a 16-byte aligned message of >= 4 bytes, read by 16-byte loads (one 256-entry table: four
+// dependent steps per word; shared memory is better spent on a 16th resident warp than on slicing tables).
 // Lane L of a 2048-byte super-chunk owns message bytes [64L, 64L+64); with R bytes left at the start of the
 // last super-chunk, R = 64*nq + tail (1 <= tail <= 64): lanes < nq are shifted by x^(512*(nq-1-L)), the
 // running total by x^(512*nq), the XOR of those by x^(8*tail), and lane nq (the tail) is added unshifted.
@@ -96,8 +97,10 @@ __device__ __forceinline__ uint32_t crc32_warp_words(const uint8_t *msg, int len
             for (int q = 0; q < 16; q++) {
                 if (q < nw) {
                     reg ^= w[q];
-                    reg = tab[768 + (reg & 0xFF)] ^ tab[512 + ((reg >> 8) & 0xFF)] ^ tab[256 + ((reg >> 16) & 0xFF)]
-                          ^ tab[reg >> 24];
+                    reg = tab[reg & 0xFF] ^ (reg >> 8);
+                    reg = tab[reg & 0xFF] ^ (reg >> 8);
+                    reg = tab[reg & 0xFF] ^ (reg >> 8);
+                    reg = tab[reg & 0xFF] ^ (reg >> 8);
                 }
                 if (q == nw) x = w[q];
             }
@@ -141,7 +144,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                      const float *__restrict__ cfo, const int *__restrict__ stream_start,
                      const int *__restrict__ n_trig_dev, ofdmx_frame *__restrict__ spec,
                      uint8_t *__restrict__ bytes_out, long long byte_stride, float2 *__restrict__ z_out,
-                     long long z_stride, uint32_t x_2048)
+                     long long z_stride, uint32_t x_2048, int dec_off)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NTH = blockDim.x, NWARP = blockDim.x >> 5;
@@ -150,21 +153,21 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     // ---- CTA-shared tables
     float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024]
     float2 *ipts = tws + 1024;                                    // [64]
-    uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [1024] slicing-by-4 CRC tables T0..T3
-    uint32_t *s_pow = s_tab + 1024;                                // [32]
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [256] CRC-32 table
+    uint32_t *s_pow = s_tab + 256;                                // [32]
     uint16_t *s_occ = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] union bin of carrier u
     uint16_t *s_pos = s_occ + ((nu + 7) & ~7);                    // [nu] position in the serialiser order
     uint8_t *lut = reinterpret_cast<uint8_t *>(s_pos + ((nu + 7) & ~7));   // [64]
-    uint8_t *ks = lut + 64;                                       // [max_pkt_bytes]
     // ---- per-warp buffers
-    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 1024 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64
-                                + (size_t)((p.max_pkt_bytes + 15) & ~15);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (size_t)((nu + 15) & ~15) + 64 + sizeof(FwState);
+    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64;
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (dec_off >= 0 ? 0 : (size_t)((nu + 15) & ~15)) + 64 + sizeof(FwState);
     unsigned char *wbase = smem_raw + ((shared_bytes + 15) & ~(size_t)15) + (size_t)wid * per_warp;
     float2 *Y = reinterpret_cast<float2 *>(wbase);                // F1K_SLOT
     float2 *Hs = Y + F1K_SLOT;                                    // hsz
-    uint8_t *dec = reinterpret_cast<uint8_t *>(Hs + hsz);         // decisions of the current symbol
-    uint8_t *hb = dec + ((nu + 15) & ~15);                        // 64 header items
+    // decisions of the current symbol: in the guard band of the symbol buffer when the carrier plan leaves one
+    // (bins no equaliser read touches; dead before the next FFT overwrites them), else in their own array
+    uint8_t *dec = (dec_off >= 0) ? reinterpret_cast<uint8_t *>(Y + dec_off) : reinterpret_cast<uint8_t *>(Hs + hsz);
+    uint8_t *hb = reinterpret_cast<uint8_t *>(Hs + hsz) + (dec_off >= 0 ? 0 : ((nu + 15) & ~15));   // 64 header items
     volatile FwState *fs = reinterpret_cast<volatile FwState *>(hb + 64);
 
     for (int i = tid; i < 1024; i += NTH) {
@@ -173,7 +176,6 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
         tws[i] = make_float2(cs, sn);
     }
-    for (int i = tid; i < p.max_pkt_bytes; i += NTH) ks[i] = p.keystream[i];
     for (int i = tid; i < nu; i += NTH) { s_occ[i] = (uint16_t)p.occ_u[i]; s_pos[i] = (uint16_t)p.pos_su[i]; }
     if (tid < 256) s_tab[tid] = p.crc_tab[tid];
     if (tid < 32) s_pow[tid] = p.crc_pow64[tid];
@@ -182,13 +184,6 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         ipts[tid] = (tid < (1 << BPS_P)) ? p.inv_ppts[tid] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    for (int k = 1; k < 4; k++) {                                 // T[k][i] = (T[k-1][i] >> 8) ^ T0[T[k-1][i] & 0xFF]
-        if (tid < 256) {
-            const uint32_t v = s_tab[(k - 1) * 256 + tid];
-            s_tab[k * 256 + tid] = (v >> 8) ^ s_tab[v & 0xFF];
-        }
-        __syncthreads();
-    }
 
     const int nt = *n_trig_dev;
     const int N = 1024, D = p.D;
@@ -378,7 +373,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                 if ((BPS_P == 4 || BPS_P == 2) && words_ok && (sym_bytes & 3) == 0) {
                     // four bytes per lane: decisions read as words, nibbles / bit pairs squeezed together
                     const uint32_t *dw = reinterpret_cast<const uint32_t *>(dec);
-                    const uint32_t *kw = reinterpret_cast<const uint32_t *>(ks + b0);
+                    const uint32_t *kw = reinterpret_cast<const uint32_t *>(p.keystream + b0);   // L1-resident
                     uint8_t *orow = bytes_out + (long long)j * byte_stride + b0;
                     for (int m = lane; 4 * m < sym_bytes; m += 32) {
                         const int gb = b0 + 4 * m;
@@ -398,7 +393,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                                 v |= x << (8 * q);
                             }
                         }
-                        v ^= kw[m];
+                        v ^= __ldg(&kw[m]);
                         if (gb + 4 <= nbytes) *reinterpret_cast<uint32_t *>(orow + 4 * m) = v;
                         else
                             for (int b = 0; gb + b < nbytes; b++) orow[4 * m + b] = (uint8_t)(v >> (8 * b));
@@ -420,7 +415,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                             v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
                         }
                     }
-                    bytes_out[(long long)j * byte_stride + gb] = (uint8_t)v ^ ks[gb];
+                    bytes_out[(long long)j * byte_stride + gb] = (uint8_t)v ^ __ldg(&p.keystream[gb]);
                 }
             }
             __syncwarp();
@@ -449,12 +444,12 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     }
 }
 
-static inline size_t frame1024w_smem_bytes(int n_occ_u, int y1_span, int max_pkt_bytes, int warps)
+static inline size_t frame1024w_smem_bytes(int n_occ_u, int y1_span, int warps, bool dec_in_guard)
 {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t nu8 = (size_t)((n_occ_u + 7) & ~7);
-    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 1024 * 4 + 32 * 4 + 2 * nu8 * 2 + 64 + al16(max_pkt_bytes);
+    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64;
     const size_t hsz = (size_t)((std::max(n_occ_u, y1_span) + 1) & ~1);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + al16(n_occ_u) + 64 + sizeof(FwState);
+    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + (dec_in_guard ? 0 : al16(n_occ_u)) + 64 + sizeof(FwState);
     return al16(shared_bytes) + (size_t)warps * per_warp + 16;
 }

@@ -43,6 +43,15 @@ __device__ __forceinline__ float2 f1k_step_phasor(double kappa)
     return make_float2(scs, ssn);
 }
 
+// streaming sample load: read-only path, no L1 allocation (the 24 KB of L1 left beside the 232 KB of shared
+// memory are kept for the small tables the frame loop reads from global memory)
+__device__ __forceinline__ float2 f1k_ld_stream(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
 // One symbol: load + derotate + 1024-point FFT.  Result: Tw[k] = X[k], natural order, k < 1024.
 __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict__ r, long long n, long long i0,
                                            long long t, double kappa, float2 st, bool slow, int j, int jend,
@@ -53,7 +62,7 @@ __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict
     const long long sbase = i0 - p.D + lane;          // stream index of this lane's first sample
     if (sbase - lane >= 0 && sbase - lane + 1024 <= n) {
 #pragma unroll
-        for (int a = 0; a < 32; a++) v[a] = __ldg(&r[sbase + 32 * a]);
+        for (int a = 0; a < 32; a++) v[a] = f1k_ld_stream(&r[sbase + 32 * a]);
     } else {
 #pragma unroll
         for (int a = 0; a < 32; a++) {

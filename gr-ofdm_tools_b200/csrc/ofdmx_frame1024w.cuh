@@ -304,7 +304,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                     const int pos = s_pos[u];
                     if (pos < 64) hb[pos] = (uint8_t)d;          // descrambled after the ballot (hmask32)
-                    if (WANT_Z) z_out[(long long)j * z_stride + pos] = z;
+                    if (WANT_Z) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + pos] = z;
                     Hs[u] = cmul(Hk, rot);
                 }
                 __syncwarp();
@@ -361,7 +361,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                             dec[pos] = (uint8_t)d;
                             if (WANT_Z) {
                                 const int idx = cb + pos;
-                                if (idx < psyms && p.hl + idx < z_stride) z_out[(long long)j * z_stride + p.hl + idx] = z;
+                                if (idx < psyms && p.hl + idx < z_stride) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + p.hl + idx] = z;
                             }
                         }
                     }
@@ -374,7 +374,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     // four bytes per lane: decisions read as words, nibbles / bit pairs squeezed together
                     const uint32_t *dw = reinterpret_cast<const uint32_t *>(dec);
                     const uint32_t *kw = reinterpret_cast<const uint32_t *>(p.keystream + b0);   // L1-resident
-                    uint8_t *orow = bytes_out + (long long)j * byte_stride + b0;
+                    uint8_t *orow = bytes_out + (unsigned long long)(unsigned)j * (unsigned long long)byte_stride + b0;
                     for (int m = lane; 4 * m < sym_bytes; m += 32) {
                         const int gb = b0 + 4 * m;
                         if (gb >= nbytes) break;
@@ -415,7 +415,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                             v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
                         }
                     }
-                    bytes_out[(long long)j * byte_stride + gb] = (uint8_t)v ^ __ldg(&p.keystream[gb]);
+                    bytes_out[(unsigned long long)(unsigned)j * (unsigned long long)byte_stride + gb] = (uint8_t)v ^ __ldg(&p.keystream[gb]);
                 }
             }
             __syncwarp();
@@ -431,7 +431,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
             else {
                 // the packet bytes were written by this warp: read them back (L2) for the CRC
                 __syncwarp();
-                const uint8_t *pk = bytes_out + (long long)j * byte_stride;
+                const uint8_t *pk = bytes_out + (unsigned long long)(unsigned)j * (unsigned long long)byte_stride;
                 const uint32_t c = (words_ok && nbytes >= 8) ? crc32_warp_words(pk, nbytes - 4, s_tab, s_pow, p.crc_pow8, x_2048, lane)
                                             : crc32_warp(pk, nbytes - 4, s_tab, s_pow, x_2048, lane);
                 const uint32_t got = (uint32_t)pk[nbytes - 4] | ((uint32_t)pk[nbytes - 3] << 8)

@@ -34,7 +34,7 @@ enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
              K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
-    "sync_metric_kernel", "plateau_kernel", "trig_count_kernel", "trig_scan_kernel", "trig_scatter_kernel",
+    "sync_metric_kernel", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
     "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel" };

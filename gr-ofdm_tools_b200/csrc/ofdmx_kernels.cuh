@@ -207,19 +207,6 @@ plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trig
 // ---------------------------------------------------------------------------------------------
 // Ordered compaction of the trigger bitmask.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(OFDMX_THREADS)
-trig_count_kernel(const uint32_t *__restrict__ trigmask, long long n_words, int *__restrict__ blocksum)
-{
-    __shared__ int wt[33];
-    const long long base = ((long long)blockIdx.x * OFDMX_THREADS + threadIdx.x) * TRIG_WPT;
-    int c = 0;
-    for (int q = 0; q < TRIG_WPT; q++)
-        if (base + q < n_words) c += __popc(trigmask[base + q]);
-    int total;
-    block_excl_scan(c, wt, total);
-    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
-}
-
 // single CTA: exclusive scan of blocksum[nb] in place; writes totals
 __global__ void __launch_bounds__(1024)
 trig_scan_kernel(int *__restrict__ blocksum, int nb, int max_trig, ofdmx_counts *__restrict__ counts,
@@ -615,116 +602,6 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
         }
         if (crc_ok) rec.flags |= OFDMX_F_CRC_OK;
         if (tid == 0) spec[j] = rec;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// header_payload_demux acceptance chain.  One CTA per stream.  next[i] = first trigger the demux
-// examines after trigger i; accepted set = orbit of the first trigger, found by pointer doubling.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-chain_kernel(const KP p, long long n, const long long *__restrict__ trig, const ofdmx_frame *__restrict__ spec,
-             const int *__restrict__ stream_start, int *__restrict__ jumpA, int *__restrict__ jumpB,
-             uint8_t *__restrict__ markA, uint8_t *__restrict__ markB, int *__restrict__ stream_count)
-{
-    const int s = blockIdx.x;
-    const int a = stream_start[s], b = stream_start[s + 1];
-    const int cnt = b - a;
-    __shared__ int wt[33];
-    if (cnt <= 0) {
-        if (threadIdx.x == 0) stream_count[s] = 0;
-        return;
-    }
-    // jump arrays are indexed by global ordinal; END sentinel = b
-    for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-        const ofdmx_frame f = spec[i];
-        long long resume = 0;
-        int nx = -1;
-        if (!(f.flags & OFDMX_F_HDR_SEEN)) nx = b;                   // demux stalls waiting for the header
-        else if (!(f.flags & OFDMX_F_HDR_OK)) resume = f.trigger + 1; // header CRC failed: resume right after
-        else if (!(f.flags & OFDMX_F_COMPLETE)) nx = b;              // demux stalls waiting for the payload
-        else
-            resume = (f.frame_syms > 0) ? f.trigger + (long long)(3 + f.frame_syms) * p.D - p.holdoff
-                                        : f.trigger + 3LL * p.D;
-        if (nx < 0) {   // lower_bound(trig[i+1..b), resume)
-            int lo = i + 1, hi = b;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (trig[mid] < resume) lo = mid + 1; else hi = mid;
-            }
-            nx = lo;
-        }
-        jumpA[i] = nx;
-        markA[i] = (i == a) ? 1 : 0;
-    }
-    __syncthreads();
-    int *jc = jumpA, *jn = jumpB;
-    uint8_t *mc = markA, *mn = markB;
-    for (int span = 1; span < cnt; span <<= 1) {
-        for (int i = a + threadIdx.x; i < b; i += blockDim.x) mn[i] = mc[i];
-        __syncthreads();
-        for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-            const int jx = jc[i];
-            if (mc[i] && jx < b) mn[jx] = 1;
-            jn[i] = (jx < b) ? jc[jx] : b;
-        }
-        __syncthreads();
-        int *tj = jc; jc = jn; jn = tj;
-        uint8_t *tmk = mc; mc = mn; mn = tmk;
-    }
-    // result marks -> markA (accepted & emitted flag), count
-    int local = 0;
-    for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-        const ofdmx_frame f = spec[i];
-        const uint8_t emit = (mc[i] && (f.flags & OFDMX_F_HDR_OK) && (f.flags & OFDMX_F_COMPLETE)) ? 1 : 0;
-        mn[i] = emit;     // the other mark buffer holds the emit flags
-        local += emit;
-    }
-    __syncthreads();
-    if (mn != markA)
-        for (int i = a + threadIdx.x; i < b; i += blockDim.x) markA[i] = mn[i];
-    int total;
-    block_excl_scan(local, wt, total);
-    if (threadIdx.x == 0) stream_count[s] = total;
-}
-
-__global__ void __launch_bounds__(1024)
-emit_scan_kernel(int *__restrict__ stream_count, long long n_streams, ofdmx_counts *__restrict__ counts)
-{
-    __shared__ int wt[33];
-    int carry = 0;
-    for (long long b0 = 0; b0 < n_streams; b0 += 1024) {
-        long long idx = b0 + threadIdx.x;
-        int v = (idx < n_streams) ? stream_count[idx] : 0;
-        int total;
-        int ex = block_excl_scan(v, wt, total);
-        if (idx < n_streams) stream_count[idx] = carry + ex;
-        carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) counts->n_frames = carry;
-}
-
-__global__ void __launch_bounds__(1024)
-emit_kernel(const ofdmx_frame *__restrict__ spec, const uint8_t *__restrict__ emit, const int *__restrict__ stream_start,
-            const int *__restrict__ stream_base, ofdmx_frame *__restrict__ frames_out)
-{
-    __shared__ int wt[33];
-    const int s = blockIdx.x;
-    const int a = stream_start[s], b = stream_start[s + 1];
-    int carry = stream_base[s];
-    for (int i0 = a; i0 < b; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        const int e = (i < b) ? emit[i] : 0;
-        int total;
-        const int ex = block_excl_scan(e, wt, total);
-        if (e) {
-            ofdmx_frame f = spec[i];
-            f.flags |= OFDMX_F_ACCEPTED;
-            frames_out[carry + ex] = f;
-        }
-        carry += total;
-        __syncthreads();
     }
 }
 

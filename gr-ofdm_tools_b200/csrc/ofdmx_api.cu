@@ -7,6 +7,7 @@
 #include "ofdmx_frame1024w.cuh"
 #include "ofdmx_cond.cuh"
 #include "ofdmx_sync_warp.cuh"
+#include "ofdmx_tx1024w.cuh"
 #include "ofdmx_chain.cuh"
 
 #include <algorithm>
@@ -32,12 +33,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel" };
+    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_frame1024w_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -73,6 +74,11 @@ struct ofdmx_ctx {
     bool frame1kw = false;          // fft_len 1024 warp-per-frame kernel eligible
     size_t frame1kw_smem = 0;
     int frame1kw_warps = FW_WARPS;
+    bool tx1kw = false;             // fft_len 1024 warp-per-packet TX kernel usable
+    bool no_warp_tx = false;        // OFDMX_NO_WARP_TX=1: generic TX kernel
+    size_t tx1kw_smem = 0;
+    const uint16_t *tx_map = nullptr;
+    const float2 *sync_td = nullptr;
     int frame1kw_dec_off = -1;      // float2 index inside the symbol buffer where the decisions live (-1: own array)
     uint32_t x_2048 = 0;            // x^(8*2048) mod P
     int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
@@ -635,6 +641,43 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
     UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64) UP(crc_pow8, crc_pow8)
 #undef UP
+    // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
+    if (N == 1024 && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && prm->n_pilot_sym_sets <= 1 && !kp.pil_in_occ
+        && kp.bps_h == 1 && c->hl >= 32) {
+        std::vector<uint16_t> tx_map(1024, (uint16_t)TXW_EMPTY);
+        for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ 512] = (uint16_t)q;   // later entries win, as in the scatter
+        for (int q = 0; q < (int)pil_bins.size(); q++) tx_map[pil_bins[q] ^ 512] = (uint16_t)(TXW_PILOT | q);
+        std::vector<float2> sync_td((size_t)2 * kp.D);
+        std::vector<double> cs(1024), sn(1024);
+        for (int k = 0; k < 1024; k++) { cs[k] = cos(2.0 * M_PI * k / 1024.0); sn[k] = sin(2.0 * M_PI * k / 1024.0); }
+        for (int o = 0; o < 2; o++) {
+            const float *sw = o ? prm->sync_word2 : prm->sync_word1;       // shifted order, (re, im)
+            std::vector<double> xr(1024), xi(1024);
+            for (int t = 0; t < 1024; t++) {
+                double ar = 0.0, ai = 0.0;
+                for (int nn = 0; nn < 1024; nn++) {
+                    const double vr = sw[2 * (nn ^ 512)], vi = sw[2 * (nn ^ 512) + 1];
+                    if (vr == 0.0 && vi == 0.0) continue;
+                    const int ph = (nn * t) & 1023;
+                    ar += vr * cs[ph] - vi * sn[ph];
+                    ai += vr * sn[ph] + vi * cs[ph];
+                }
+                xr[t] = ar; xi[t] = ai;
+            }
+            for (int m = 0; m < kp.D; m++) {
+                const int t = (m - kp.cp + 1024) & 1023;
+                float vr = (float)(xr[t] * (double)kp.tx_scale), vi = (float)(xi[t] * (double)kp.tx_scale);
+                if (kp.tx_clip > 0.f) {
+                    vr = vr < -kp.tx_clip ? -kp.tx_clip : (vr > kp.tx_clip ? kp.tx_clip : vr);
+                    vi = vi < -kp.tx_clip ? -kp.tx_clip : (vi > kp.tx_clip ? kp.tx_clip : vi);
+                }
+                sync_td[(size_t)o * kp.D + m] = make_float2(vr, vi);
+            }
+        }
+        if ((rc = upload(c, tx_map, &c->tx_map)) != 0) return bail(rc);
+        if ((rc = upload(c, sync_td, &c->sync_td)) != 0) return bail(rc);
+        c->tx1kw = true;
+    }
 
     // shared-memory budgets
     {
@@ -703,6 +746,20 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                 if (e1 != cudaSuccess) c->frame1kw = false;
             }
         }
+        if (c->tx1kw) {
+            c->tx1kw_smem = tx1024w_smem_bytes(kp.max_pkt_bytes, TXW_WARPS);
+            cudaError_t e1 = cudaSuccess;
+#define TXW_ATTR(B) { cudaError_t e2 = cudaFuncSetAttribute(tx_frame1024w_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
+            switch (kp.bps_p) {
+            case 1: TXW_ATTR(1) break;
+            case 2: TXW_ATTR(2) break;
+            case 3: TXW_ATTR(3) break;
+            case 4: TXW_ATTR(4) break;
+            default: TXW_ATTR(6) break;
+            }
+#undef TXW_ATTR
+            if (e1 != cudaSuccess || c->tx1kw_smem > 227 * 1024) c->tx1kw = false;
+        }
         c->sync_tma_smem = sync_tma_smem_bytes(N);
         if (N >= 32 && cudaFuncSetAttribute(sync_metric_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_tma_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -729,6 +786,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     if (const char *nw = getenv("OFDMX_NO_WARP_FRAME")) c->no_warp_frame = (nw[0] == '1');
     if (const char *nt = getenv("OFDMX_NO_TMA")) c->no_tma = (nt[0] == '1');   // plain-load sync kernel instead of the TMA ring
     if (const char *ns = getenv("OFDMX_NO_WARP_SYNC")) c->no_warp_sync = (ns[0] == '1');
+    if (const char *nx = getenv("OFDMX_NO_WARP_TX")) c->no_warp_tx = (nx[0] == '1');
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
     *out = c;
@@ -936,10 +994,27 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
     cudaStream_t st = (cudaStream_t)stream;
     ofdmx_ctx *ctx_ = c;
     { KT(K_TX_OFF); tx_offsets_kernel<<<1, 1024, 0, st>>>(c->kp, (const long long *)pkt_off_dev, n_pkts, (long long *)sample_off_dev); }
-    const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
-    { KT(K_TX); tx_frame_kernel<<<grid, OFDMX_THREADS, c->tx_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts,
+    if (c->tx1kw && !c->no_warp_tx && !c->force_generic) {
+        const unsigned grid = (unsigned)std::min<int64_t>((n_pkts + TXW_WARPS - 1) / TXW_WARPS, (int64_t)c->sm_count);
+        const int pbb = (int)tx1024w_pb_bytes(c->kp.max_pkt_bytes);
+        KT(K_TX1KW);
+#define TXW(B) tx_frame1024w_kernel<B><<<grid, TXW_WARPS * 32, c->tx1kw_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts, \
+            first_pkt_num, (float2 *)samples_out, cap_samples, (const long long *)sample_off_dev, c->tx_map, c->sync_td, c->x_2048, pbb)
+        switch (c->kp.bps_p) {
+        case 1: TXW(1); break;
+        case 2: TXW(2); break;
+        case 3: TXW(3); break;
+        case 4: TXW(4); break;
+        default: TXW(6); break;
+        }
+#undef TXW
+    } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
+        KT(K_TX);
+        tx_frame_kernel<<<grid, OFDMX_THREADS, c->tx_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts,
                                                               first_pkt_num, (float2 *)samples_out, cap_samples,
-                                                              (const long long *)sample_off_dev); }
+                                                              (const long long *)sample_off_dev);
+    }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }

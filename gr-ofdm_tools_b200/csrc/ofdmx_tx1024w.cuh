@@ -1,0 +1,165 @@
+// ofdmx_tx1024w.cuh -- K5+K1, fft_len 1024: the TX chain with ONE WARP PER PACKET.
+//
+// Mirror image of the warp-per-frame receiver (ofdmx_frame1024w.cuh).  The generic tx_frame_kernel gives a
+// 256-thread CTA to every packet and runs a radix-4 shared-memory IFFT with a block barrier per stage; here a
+// packet belongs to one warp, which
+//   * pulls the payload into shared memory, appends the CRC-32 (crc32_bb) and applies the additive scrambler;
+//   * copies the two sync symbols, whose time-domain samples (cyclic prefix, x tx_scale and clipper included) are a
+//     constant of the configuration computed once at context creation;
+//   * for the header and every payload symbol fills the IFFT input DIRECTLY IN REGISTERS from a per-bin map
+//     (data position / pilot / empty): repack_bits_bb + chunks_to_symbols + ofdm_carrier_allocator_cvc become 32
+//     table look-ups per lane, no zero-fill and no scatter pass;
+//   * runs the 1024-point inverse FFT as 32 x 32 in registers (same generated butterflies as the receiver, one
+//     transpose through shared memory) and stores the samples with the cyclic prefix, x tx_scale and the clipper
+//     straight from the registers in coalesced 256-byte rows.
+// Preconditions checked by the host (otherwise the generic kernel runs): fft_len 1024, one carrier set, at most
+// one pilot set with one pilot-symbol set, no pilot inside the occupied set, BPSK header.
+#pragma once
+#include "ofdmx_frame1024w.cuh"
+
+#define TXW_WARPS 16
+#define TXW_EMPTY 0xFFFFu
+#define TXW_PILOT 0x8000u
+
+template <int BPS_P>
+__global__ void __launch_bounds__(TXW_WARPS * 32, 1)
+tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long long *__restrict__ pkt_off,
+                     long long n_pkts, int first_num, float2 *__restrict__ out, long long cap,
+                     const long long *__restrict__ sample_off, const uint16_t *__restrict__ tx_map,
+                     const float2 *__restrict__ sync_td, uint32_t x_2048, int pb_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NTH = blockDim.x;
+    // ---- CTA-shared tables
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024] W1024^(b k1), forward sign
+    float2 *pts = tws + 1024;                                     // [64] payload constellation
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(pts + 64);     // [256] CRC-32 table
+    uint32_t *s_pow = s_tab + 256;                                // [32]
+    uint16_t *map = reinterpret_cast<uint16_t *>(s_pow + 32);     // [1024] natural bin -> data position / pilot / empty
+    uint8_t *hmask = reinterpret_cast<uint8_t *>(map + 1024);     // [1024] header scrambling mask (zero padded)
+    const size_t shared_bytes = 1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 1024 * 2 + 1024;
+    unsigned char *wbase = smem_raw + shared_bytes + (size_t)wid * ((size_t)F1K_SLOT * 8 + pb_bytes);
+    float2 *Tw = reinterpret_cast<float2 *>(wbase);               // F1K_SLOT
+    uint8_t *pb = reinterpret_cast<uint8_t *>(Tw + F1K_SLOT);     // packet bytes (+ CRC), 16-byte aligned
+
+    for (int i = tid; i < 1024; i += NTH) {
+        const int k1 = i >> 5, b = i & 31;
+        float sn, cs;
+        sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
+        tws[i] = make_float2(cs, sn);
+        map[i] = tx_map[i];
+        hmask[i] = (i < p.hl) ? p.hdr_mask[i] : 0;
+    }
+    if (tid < 256) s_tab[tid] = p.crc_tab[tid];
+    if (tid < 32) s_pow[tid] = p.crc_pow64[tid];
+    if (tid < 64) pts[tid] = (tid < (1 << BPS_P)) ? p.ppts[tid] : make_float2(0.f, 0.f);
+    __syncthreads();
+
+    const int N = 1024, D = p.D, cp = p.cp;
+    const int size0 = p.occ_size[0];
+    const float2 h0 = p.hpts[0], h1 = p.hpts[1];
+    const float sc = p.tx_scale, clip = p.tx_clip;
+    const int gw = blockIdx.x * (NTH >> 5) + wid, nw = gridDim.x * (NTH >> 5);
+
+    for (long long pk = gw; pk < n_pkts; pk += nw) {
+        const long long o0 = pkt_off[pk];
+        const int len = (int)(pkt_off[pk + 1] - o0);
+        const int lp = len + (p.crc_mode ? 4 : 0);
+        if (lp > p.max_pkt_bytes) continue;                       // rejected on the host as well
+        __syncwarp();
+        // ---- payload -> shared memory
+        const uint8_t *src = payload + o0;
+        {
+            const int full = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (len & ~15) : 0;   // whole 16-byte units
+            for (int m = lane * 16; m < full; m += 512) *reinterpret_cast<uint4 *>(pb + m) = __ldg(reinterpret_cast<const uint4 *>(src + m));
+            for (int m = full + lane; m < len; m += 32) pb[m] = __ldg(src + m);
+        }
+        __syncwarp();
+        if (p.crc_mode) {   // crc32_bb(check=False): append little-endian CRC
+            const uint32_t c = (len >= 4) ? crc32_warp_words(pb, len, s_tab, s_pow, p.crc_pow8, x_2048, lane)
+                                          : crc32_warp(pb, len, s_tab, s_pow, x_2048, lane);
+            __syncwarp();
+            if (lane < 4) pb[len + lane] = (uint8_t)(c >> (8 * lane));
+        }
+        __syncwarp();
+        // ---- additive_scrambler_bb; the two bytes after the packet read as zero (bit windows of the last chunk)
+        for (int m = lane; m < lp; m += 32) pb[m] ^= __ldg(&p.keystream[m]);
+        if (lane < 2) pb[lp + lane] = 0;
+        __syncwarp();
+        // ---- packet_header_default::header_formatter (BPSK: one bit per item)
+        const unsigned plen = (unsigned)lp & 0xFFFu, pnum = (unsigned)(first_num + (int)pk) & 0xFFFu;
+        const unsigned hbits = plen | (pnum << 12) | ((unsigned)crc8_hdr(plen, pnum) << 24);
+        const int ns = (lp * 8 + BPS_P - 1) / BPS_P;                   // repack_bits_bb(8, bps, key, False)
+        const int n_ofdm = 3 + (ns + size0 - 1) / size0;
+        const long long base = sample_off[pk];
+        if (base + (long long)n_ofdm * D > cap) continue;
+        // ---- sync symbols: constants of the configuration
+        for (int m = lane; m < 2 * D; m += 32) out[base + m] = __ldg(&sync_td[m]);
+        // ---- header and payload symbols
+        for (int o = 2; o < n_ofdm; o++) {
+            float2 v[32];
+            const int sbase = (o - 3) * size0;
+#pragma unroll
+            for (int a = 0; a < 32; a++) {
+                const unsigned code = map[32 * a + lane];
+                float2 val = make_float2(0.f, 0.f);
+                if (code < TXW_PILOT) {
+                    if (o == 2) {
+                        const unsigned bit = ((code < 32 ? (hbits >> code) : 0u) ^ hmask[code]) & 1u;
+                        val = bit ? h1 : h0;
+                    } else {
+                        const int si = sbase + (int)code;
+                        if (si < ns) {
+                            const int bi = si * BPS_P;
+                            unsigned c;
+                            if (BPS_P == 1 || BPS_P == 2 || BPS_P == 4) c = ((unsigned)pb[bi >> 3] >> (bi & 7)) & ((1u << BPS_P) - 1u);
+                            else {
+                                const unsigned w = (unsigned)pb[bi >> 3] | ((unsigned)pb[(bi >> 3) + 1] << 8);
+                                c = (w >> (bi & 7)) & ((1u << BPS_P) - 1u);
+                            }
+                            val = pts[c];
+                        }
+                    }
+                } else if (code != TXW_EMPTY) {
+                    val = __ldg(&p.pil_sym[code & 0x7FFFu]);
+                }
+                v[a] = val;
+            }
+            // x[k1 + 32 k2] = sum_b [ (sum_a X[32 a + b] W32^(-a k1)) W1024^(-b k1) ] W32^(-b k2)
+            fft32_inv(v);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+                const int k1 = brev5(q);
+                Tw[k1 * F1K_ROW + lane] = cmul_conj(v[q], tws[k1 * 32 + lane]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(&Tw[lane * F1K_ROW + 2 * q]);
+                v[2 * q] = make_float2(t4.x, t4.y);
+                v[2 * q + 1] = make_float2(t4.z, t4.w);
+            }
+            fft32_inv(v);
+            // ---- ofdm_cyclic_prefixer(rolloff 0) + multiply_const(tx_scale) + clipper, from the registers
+            float2 *dst = out + base + (long long)o * D;
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+                const int t = lane + 32 * brev5(q);
+                float2 w = make_float2(v[q].x * sc, v[q].y * sc);
+                if (clip > 0.f) {
+                    w.x = w.x < -clip ? -clip : (w.x > clip ? clip : w.x);
+                    w.y = w.y < -clip ? -clip : (w.y > clip ? clip : w.y);
+                }
+                dst[cp + t] = w;
+                if (t >= N - cp) dst[t - (N - cp)] = w;
+            }
+        }
+    }
+}
+
+static inline size_t tx1024w_pb_bytes(int max_pkt_bytes) { return ((size_t)max_pkt_bytes + 8 + 15) & ~(size_t)15; }
+static inline size_t tx1024w_smem_bytes(int max_pkt_bytes, int warps)
+{
+    return (size_t)(1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 1024 * 2 + 1024) + (size_t)warps * ((size_t)F1K_SLOT * 8 + tx1024w_pb_bytes(max_pkt_bytes));
+}

@@ -422,3 +422,52 @@ def test_sync_kernel_variants_detect_bits(monkeypatch, n_streams, n, odd):
         assert np.array_equal(trig, np.array(ref_t, np.int64)), name
         assert np.array_equal(st, np.array(ref_s)), name
         np.testing.assert_allclose(cfo, np.array(ref_c, np.float32), atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("bps,crc,scr,clip", [(1, 1, True, 0.0), (2, 0, False, 0.0), (3, 1, True, 0.0), (4, 1, True, 0.004),
+                                              (6, 1, True, 0.0), (4, 0, True, 0.0)])
+def test_tx_warp_kernel_ragged(monkeypatch, bps, crc, scr, clip):
+    """fft_len 1024 warp-per-packet TX kernel (default when eligible): every payload modulation, with and
+    without in-graph CRC / scrambler / clipper, packet lengths around the byte-window and symbol edges and packets
+    starting at unaligned payload offsets -- against the oracle and against the generic TX kernel."""
+    cfg = cm.cfg_c3(bps_payload=bps, crc_mode=crc, scramble_bits=scr)
+    cfg["tx_scale"] = 0.01
+    rng = np.random.default_rng(700 + bps + crc)
+    sym = 600 * bps // 8
+    lens = [1, 2, 3, 4, 5, 15, 16, 17, 63, 64, 65, sym - 4, sym - 1, sym, sym + 1, 2 * sym, 999, 1500, 2047, 2048, 2049]
+    if bps > 1:
+        lens += [3001, 4091 if crc else 4095]
+    pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    ref, roff = cm.make_oracle(dict(cfg, tx_clip=clip)).tx(pk, first_pkt_num=4090)     # the counter wraps at 4096
+    phy = cm.make_phy(cfg, tx_clip=clip)
+    s, soff = phy.tx(pk, first_pkt_num=4090)
+    s = s.cpu().numpy()
+    assert np.array_equal(soff.cpu().numpy(), roff)
+    for i in range(len(pk)):
+        a, b = s[roff[i]:roff[i + 1]], ref[roff[i]:roff[i + 1]]
+        e = np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert e < 1e-5, "frame %d (len %d): relative error %.3g" % (i, lens[i], e)
+    if clip:
+        assert np.abs(s.real).max() <= np.float32(clip) and (np.abs(s.real) == np.float32(clip)).sum() > 100
+    assert "tx_frame1024w_kernel" in _kernels_used(phy, lambda: phy.tx(pk))
+    monkeypatch.setenv("OFDMX_NO_WARP_TX", "1")
+    gen = cm.make_phy(cfg, tx_clip=clip)
+    g, goff = gen.tx(pk, first_pkt_num=4090)
+    assert "tx_frame_kernel" in _kernels_used(gen, lambda: gen.tx(pk))
+    assert np.array_equal(goff.cpu().numpy(), roff)
+    assert np.linalg.norm(g.cpu().numpy() - s) / np.linalg.norm(s) < 1e-5
+    if clip:
+        return          # the rail at 0.004 distorts the signal on purpose
+    # and the receiver decodes what the new transmitter sends
+    x = cm.channel(cm.split_frames(s, roff), rng, gaps=(0, 200), lead=400, tail=3000, snr_db=60.0, fft_len=1024,
+                   scale=100.0)
+    rx = cm.make_phy(cfg).rx(_to_dev(x), want_z=False)
+    assert rx.payloads() == pk
+
+
+def _kernels_used(phy, fn):
+    phy.profile(True)
+    fn()
+    used = set(phy.profile_read())
+    phy.profile(False)
+    return used

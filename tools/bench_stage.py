@@ -3,6 +3,12 @@
 headline RX metric).  Prints one JSON line per stage.
 
   python tools/bench_stage.py --stage agc2 [--streams 4096] [--samples 56320] [--steps 10]
+  python tools/bench_stage.py --stage tx [--frames 65536] [--steps 10]
+
+tx: the TX chain (CRC-32 append, header, scrambler, mapping, carrier allocation, IFFT, cyclic prefix, x0.01) on
+BASELINE config[2] packets (fft_len 1024, 16-QAM, 1500 bytes) resident in HBM; value = Msamples/s produced,
+roofline = (payload bytes read + 8 B per sample written) / time against the measured HBM peak, cpu_baseline = the
+oracle TX on all host cores over a bounded sample, parity gate against the oracle on the first packets.
 
 agc2: analog.agc2_cc over `streams` independent streams of `samples` complex samples resident in HBM
 (BASELINE config[1] shape: 4096 streams x 64 frames x 880 samples).  value = Msamples/s (CUDA events on the
@@ -23,9 +29,57 @@ for _p in (os.path.join(ROOT, "gr-ofdm_tools_b200"), os.path.join(ROOT, "tests")
 import numpy as np  # noqa: E402
 
 
+def stage_tx(args, torch, cm, dev, peak):
+    import oracle as O
+    cfg = cm.cfg_c3()
+    cfg["tx_scale"] = 0.01
+    phy = cm.make_phy(cfg, max_pkt_bytes=1504)
+    rng = np.random.default_rng(3)
+    nf = args.frames
+    payload = torch.from_numpy(rng.integers(0, 256, nf * 1500, dtype=np.uint8)).to(dev)
+    off = torch.arange(nf + 1, dtype=torch.int64, device=dev) * 1500
+    for _ in range(args.warmup):
+        s, soff = phy.tx((payload, off))
+    torch.cuda.synchronize()
+    phy.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        s, soff = phy.tx((payload, off))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = phy.profile_read()
+    n = int(soff[-1])
+    # parity gate on the first packets + CPU baseline on a bounded sample
+    k = min(256, nf)
+    pk = [bytes(payload[i * 1500:(i + 1) * 1500].cpu().numpy()) for i in range(k)]
+    orc = O.Oracle(**cfg)
+    t0 = time.perf_counter()
+    ref, roff = orc.tx(pk)
+    cpu_s = time.perf_counter() - t0
+    got = s[: int(roff[-1])].cpu().numpy()
+    err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    assert err < 1e-5, "TX differs from the oracle: %g" % err
+    kern_ms = {kk: v[0] / v[1] * (v[1] / args.steps) for kk, v in prof.items()}
+    dom = max(kern_ms, key=kern_ms.get)
+    ach = (nf * 1500.0 + 8.0 * n) / (kern_ms[dom] * 1e-3) / 1e9
+    print(json.dumps({
+        "stage": "tx", "metric": "OFDM TX Msamples/s (fft_len=1024, 16-QAM)", "value": n / (ms * 1e-3) / 1e6,
+        "unit": "Msamples/s", "ms_per_step": ms, "steps": args.steps,
+        "config": {"workload": "%d packets of 1500 bytes -> %d samples, resident in HBM; step includes the output allocation of the Python wrapper" % (nf, n)},
+        "kernels_ms_per_step": kern_ms,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+        "parity": {"rel_l2_vs_oracle": err, "packets": k},
+        "cpu_baseline": {"value": int(roff[-1]) / cpu_s / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d packets" % k},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stage", default="agc2", choices=["agc2"])
+    ap.add_argument("--stage", default="agc2", choices=["agc2", "tx"])
+    ap.add_argument("--frames", type=int, default=65536)
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--samples", type=int, default=64 * 880)
     ap.add_argument("--steps", type=int, default=10)
@@ -34,6 +88,12 @@ def main():
     import torch
     import common as cm
     dev = torch.device("cuda", 0)
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    if args.stage == "tx":
+        return stage_tx(args, torch, cm, dev, peak)
     phy = cm.make_phy(cm.cfg_c1())
     g = torch.Generator(device=dev).manual_seed(1)
     x = torch.view_as_complex(torch.randn(args.streams, args.samples, 2, device=dev, generator=g))
@@ -50,10 +110,6 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     n = args.streams * args.samples
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        peak = 6650.0
     # parity gate + CPU baseline on a bounded sample
     import oracle as O
     ns = min(8, args.streams)

@@ -201,14 +201,18 @@ class OfdmPhy(object):
         return {L.ofdmx_profile_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n) if calls[i]}
 
     # ------------------------------------------------------------------ TX
-    def tx(self, packets, first_pkt_num=0):
+    def tx(self, packets, first_pkt_num=0, out=None, soff=None):
         """packets: list of bytes-like (or (uint8 cuda tensor, int64 cuda offsets)).
-        Returns (complex64 cuda tensor of samples, int64 cuda tensor of n+1 frame offsets)."""
+        Returns (complex64 cuda tensor of samples, int64 cuda tensor of n+1 frame offsets).
+        With device packets and a pre-allocated `out` (complex64 cuda tensor; `soff`: int64 [n+1], optional) the
+        call only enqueues work: nothing is copied to the host, the whole `out` tensor is returned and
+        soff[-1] tells how much of it was written (packets that would not fit are left out)."""
         torch = self._torch()
         dev = self._dev()
         if isinstance(packets, tuple):
             payload, off = packets
-            lens = (off[1:] - off[:-1]).cpu().numpy()
+            n = int(off.numel()) - 1
+            lens = None if out is not None else (off[1:] - off[:-1]).cpu().numpy()
         else:
             lens = np.array([len(b) for b in packets], np.int64)
             flat = np.frombuffer(b"".join(bytes(bytearray(b)) for b in packets), np.uint8)
@@ -216,18 +220,27 @@ class OfdmPhy(object):
             o = np.zeros(len(lens) + 1, np.int64)
             o[1:] = np.cumsum(lens)
             off = torch.from_numpy(o).to(dev)
-        n = len(lens)
+            n = len(lens)
         extra = 4 if self.crc_mode else 0
-        if n and int(lens.max()) + extra > self.max_pkt_bytes:
-            raise ValueError("packet longer than max_pkt_bytes")
-        uniq = {int(v): self.frame_samples(int(v)) for v in np.unique(lens)}
-        cap = int(sum(uniq[int(v)] for v in lens))
-        out = torch.empty(max(cap, 1), dtype=torch.complex64, device=dev)
-        soff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        if lens is not None:
+            if n and int(lens.max()) + extra > self.max_pkt_bytes:
+                raise ValueError("packet longer than max_pkt_bytes")
+            vals, cnt = np.unique(lens, return_counts=True)
+            need = int(sum(self.frame_samples(int(v)) * int(c) for v, c in zip(vals, cnt)))
+        if out is None:
+            cap = need
+            out = torch.empty(max(cap, 1), dtype=torch.complex64, device=dev)
+        else:
+            assert out.is_cuda and out.dtype == torch.complex64 and out.is_contiguous()
+            cap = int(out.numel())
+            if lens is not None and need > cap:
+                raise BufferError("output tensor too small: %d samples needed, %d given" % (need, cap))
+        if soff is None:
+            soff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         if n:
             _lib.check(_lib.load().ofdmx_tx(self.ctx, payload.data_ptr(), off.data_ptr(), n, int(first_pkt_num),
                                             out.data_ptr(), cap, soff.data_ptr(), self._stream()), self.ctx)
-        return out[:cap], soff
+        return (out[:cap] if lens is not None else out), soff
 
     # ------------------------------------------------------------------ RX
     def default_max_frames(self, n_streams, n):

@@ -38,7 +38,7 @@ static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_frame1024w_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_frame1024w_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_frame1024w_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -74,6 +74,8 @@ struct ofdmx_ctx {
     bool frame1kw = false;          // fft_len 1024 warp-per-frame kernel eligible
     size_t frame1kw_smem = 0;
     int frame1kw_warps = FW_WARPS;
+    int frame1kw_dec_all = 0;       // > 0: bits per OFDM symbol not a byte multiple: decisions of the whole packet kept (capacity)
+    int frame1kw_ctas = 1;          // resident CTAs per SM of the warp-per-frame kernel (fft_len < 1024: several)
     bool tx1kw = false;             // fft_len 1024 warp-per-packet TX kernel usable
     bool no_warp_tx = false;        // OFDMX_NO_WARP_TX=1: generic TX kernel
     size_t tx1kw_smem = 0;
@@ -726,15 +728,22 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                 const int need = (kp.n_occ_u + 7) / 8 + 2;               // float2 slots for n_occ_u bytes
                 if (best_at >= 0 && at + need <= best_at + best) c->frame1kw_dec_off = at;
             }
+            c->frame1kw_dec_all = ((occ_size[0] * kp.bps_p) % 8 == 0) ? 0 : (kp.max_frame_syms + 1) * occ_size[0];
+            if (c->frame1kw_dec_all > 0) c->frame1kw_dec_off = -1;
             c->frame1kw_warps = FW_WARPS;
-            while (c->frame1kw_warps > 4 && frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0) > 227 * 1024)
+            while (c->frame1kw_warps > 4 && framew_smem_bytes(N, kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0, c->frame1kw_dec_all) > 227 * 1024)
                 c->frame1kw_warps--;
-            c->frame1kw_smem = frame1024w_smem_bytes(kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0);
-            c->frame1kw = (N == 1024 && simple && ngc <= 4 && kp.bps_h == 1 && c->hl >= 32 && c->hl <= 1024
-                           && (occ_size[0] * kp.bps_p) % 8 == 0 && c->frame1kw_smem <= 227 * 1024);
+            c->frame1kw_smem = framew_smem_bytes(N, kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0, c->frame1kw_dec_all);
+            // warp-per-frame kernel: fft_len 1024 (register FFT 32x32, <= 4 carrier-offset candidates) and
+            // fft_len 64 / 128 (register FFT + lane-shuffle FFT, any number of candidates)
+            c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128) && simple && kp.bps_h == 1 && c->hl >= 32 && c->hl <= 1024
+                          && c->frame1kw_smem <= 227 * 1024;
             if (c->frame1kw) {
                 cudaError_t e1 = cudaSuccess;
-#define FW_ATTR(B, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_frame1024w_kernel<B, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
+                int occ = 1;
+#define FW_ATTR1(NN, B, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_framew_kernel<NN, B, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1kw_smem); if (e2 != cudaSuccess) e1 = e2; \
+                             if (!Z) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rx_framew_kernel<NN, B, Z>, c->frame1kw_warps * 32, c->frame1kw_smem); }
+#define FW_ATTR(B, Z) { if (N == 1024) FW_ATTR1(1024, B, Z) else if (N == 128) FW_ATTR1(128, B, Z) else FW_ATTR1(64, B, Z) }
                 switch (kp.bps_p) {
                 case 1: FW_ATTR(1, false) FW_ATTR(1, true) break;
                 case 2: FW_ATTR(2, false) FW_ATTR(2, true) break;
@@ -743,6 +752,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                 default: FW_ATTR(6, false) FW_ATTR(6, true) break;
                 }
 #undef FW_ATTR
+#undef FW_ATTR1
+                c->frame1kw_ctas = std::max(1, occ);
                 if (e1 != cudaSuccess) c->frame1kw = false;
             }
         }
@@ -900,14 +911,16 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     ofdmx_ctx *ctx_ = c;
     if (c->frame1kw && !c->force_generic && !c->no_warp_frame) {
         KT(K_FRAME1KW);
+#define FW_GO(NN, B) { if (z_out) rx_framew_kernel<NN, B, true><<<fwgrid, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(        \
+            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,                 \
+            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all);                             \
+        else rx_framew_kernel<NN, B, false><<<fwgrid, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(                         \
+            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,                 \
+            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all); }
 #define FW_LAUNCH(B)                                                                                               \
     do {                                                                                                           \
-        if (z_out) rx_frame1024w_kernel<B, true><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(               \
-            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,         \
-            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off);                                         \
-        else rx_frame1024w_kernel<B, false><<<c->sm_count, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(                    \
-            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,         \
-            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off);                                         \
+        const unsigned fwgrid = (unsigned)(c->sm_count * c->frame1kw_ctas);                                                        \
+        if (c->kp.N == 1024) FW_GO(1024, B) else if (c->kp.N == 128) FW_GO(128, B) else FW_GO(64, B)                                \
     } while (0)
         switch (c->kp.bps_p) {
         case 1: FW_LAUNCH(1); break;
@@ -917,6 +930,7 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
         default: FW_LAUNCH(6); break;
         }
 #undef FW_LAUNCH
+#undef FW_GO
     } else if (c->frame1k_warps > 0 && !c->force_generic) {
         KT(K_FRAME1K);
 #define F1K_LAUNCH3(B, S, Z)                                                                                       \

@@ -14,6 +14,7 @@
 // (max_carr_offset given), bits per OFDM symbol a multiple of 8, <= 1024 occupied carriers.
 #pragma once
 #include "ofdmx_frame1024.cuh"
+#include "ofdmx_symbol_small.cuh"
 
 #define FW_WARPS 16
 #define FW_THREADS (FW_WARPS * 32)
@@ -137,14 +138,14 @@ __device__ __forceinline__ void fw_flush(volatile FwState *fs, ofdmx_frame *dst,
     __syncwarp();
 }
 
-template <int BPS_P, bool WANT_Z>
-__global__ void __launch_bounds__(FW_THREADS, 1)
-rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
+template <int NFFT, int BPS_P, bool WANT_Z>
+__global__ void __launch_bounds__(FW_THREADS, NFFT == 1024 ? 1 : 2)
+rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
                      const long long *__restrict__ trig, const int *__restrict__ trig_stream,
                      const float *__restrict__ cfo, const int *__restrict__ stream_start,
                      const int *__restrict__ n_trig_dev, ofdmx_frame *__restrict__ spec,
                      uint8_t *__restrict__ bytes_out, long long byte_stride, float2 *__restrict__ z_out,
-                     long long z_stride, uint32_t x_2048, int dec_off)
+                     long long z_stride, uint32_t x_2048, int dec_off, int dec_all_arg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NTH = blockDim.x, NWARP = blockDim.x >> 5;
@@ -152,28 +153,33 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     const int hsz = (max(nu, p.y1_span) + 1) & ~1;              // H area also parks the Y1 bins chanest needs
     // ---- CTA-shared tables
     float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024]
-    float2 *ipts = tws + 1024;                                    // [64]
+    float2 *ipts = tws + NFFT;                                    // [64]
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [256] CRC-32 table
     uint32_t *s_pow = s_tab + 256;                                // [32]
     uint16_t *s_occ = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] union bin of carrier u
     uint16_t *s_pos = s_occ + ((nu + 7) & ~7);                    // [nu] position in the serialiser order
     uint8_t *lut = reinterpret_cast<uint8_t *>(s_pos + ((nu + 7) & ~7));   // [64]
     // ---- per-warp buffers
-    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64;
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + (size_t)hsz * 8 + (dec_off >= 0 ? 0 : (size_t)((nu + 15) & ~15)) + 64 + sizeof(FwState);
+    constexpr int YSLOT = (NFFT == 1024) ? F1K_SLOT : NFFT;      // float2 per symbol buffer
+    // fft_len 1024 keeps its steady-state code minimal: configurations whose bits per OFDM symbol are not a byte
+    // multiple (dec_all > 0) go to the CTA-per-frame kernel there
+    const int dec_all = (NFFT == 1024) ? 0 : dec_all_arg;
+    const size_t shared_bytes = (size_t)NFFT * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64;
+    const size_t dec_bytes = (dec_off >= 0) ? 0 : (size_t)(((dec_all > 0 ? dec_all : nu) + 15) & ~15);
+    const size_t per_warp = (size_t)YSLOT * 8 + (size_t)hsz * 8 + dec_bytes + 64 + sizeof(FwState);
     unsigned char *wbase = smem_raw + ((shared_bytes + 15) & ~(size_t)15) + (size_t)wid * per_warp;
     float2 *Y = reinterpret_cast<float2 *>(wbase);                // F1K_SLOT
-    float2 *Hs = Y + F1K_SLOT;                                    // hsz
+    float2 *Hs = Y + YSLOT;                                    // hsz
     // decisions of the current symbol: in the guard band of the symbol buffer when the carrier plan leaves one
     // (bins no equaliser read touches; dead before the next FFT overwrites them), else in their own array
     uint8_t *dec = (dec_off >= 0) ? reinterpret_cast<uint8_t *>(Y + dec_off) : reinterpret_cast<uint8_t *>(Hs + hsz);
-    uint8_t *hb = reinterpret_cast<uint8_t *>(Hs + hsz) + (dec_off >= 0 ? 0 : ((nu + 15) & ~15));   // 64 header items
+    uint8_t *hb = reinterpret_cast<uint8_t *>(Hs + hsz) + dec_bytes;   // 64 header items
     volatile FwState *fs = reinterpret_cast<volatile FwState *>(hb + 64);
 
-    for (int i = tid; i < 1024; i += NTH) {
+    for (int i = tid; i < NFFT; i += NTH) {
         const int k1 = i >> 5, b = i & 31;
         float sn, cs;
-        sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
+        sincospif(-(float)(b * k1) * (2.0f / NFFT), &sn, &cs);
         tws[i] = make_float2(cs, sn);
     }
     for (int i = tid; i < nu; i += NTH) { s_occ[i] = (uint16_t)p.occ_u[i]; s_pos[i] = (uint16_t)p.pos_su[i]; }
@@ -186,7 +192,9 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     __syncthreads();
 
     const int nt = *n_trig_dev;
-    const int N = 1024, D = p.D;
+    constexpr int N = NFFT, HALF = NFFT / 2;
+    const int D = p.D;
+    const LaneTw ltw = lane_twiddles(lane);          // lane-FFT twiddles (fft_len < 1024 only)
     const float al = p.alpha, oma = 1.0f - p.alpha;
     const int size0 = p.occ_size[0];
     const int sym_bytes = size0 * BPS_P / 8;
@@ -205,7 +213,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
             const float cf = cfo[j];
             fs->rec.trigger = t; fs->rec.cfo = cf; fs->rec.stream = st; fs->rec.flags = 0; fs->rec.pkt_len = 0;
             fs->rec.pkt_num = 0; fs->rec.frame_syms = 0; fs->rec.carr_offset = 0; fs->rec.slot = (uint32_t)j;
-            const double kap = (double)cf * (-2.0 / 1024.0) * (1.0 / TWO_PI_D);
+            const double kap = (double)cf * (-2.0 / NFFT) * (1.0 / TWO_PI_D);
             const float2 kst = f1k_step_phasor(kap);
             fs->kappa = kap; fs->stx = kst.x; fs->sty = kst.y;
             fs->tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
@@ -224,53 +232,59 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
         bool dead = false;
         for (int sidx = 0; sidx < fs->nsym; sidx++) {
             const long long i0 = t + (long long)sidx * D + p.cp;
-            f1k_symbol(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
-            {   // pull the next symbol's 8 KB towards L2 while this one is processed
+            if (NFFT == 1024) {
+                f1k_symbol(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
+                // pull the next symbol's 8 KB towards L2 while this one is processed
                 const long long sn = i0 + D - p.D + lane * 32;
                 if (sn >= 0 && sn + 32 <= n) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(r + sn));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(r + sn + 16));
                 }
+            } else {
+                fsmall_symbol<(NFFT == 1024) ? 64 : NFFT>(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + NFFT - 1, j, jend,
+                                                         trig, cfo, Y, tws, lane, ltw);
             }
             __syncwarp();
             if (sidx == 0) {
                 // sync word 1: park the bins chanest needs in the (still unused) H area
-                for (int q = lane; q < p.y1_span; q += 32) Hs[q] = Y[(y1_lo + q) ^ 512];
+                for (int q = lane; q < p.y1_span; q += 32) Hs[q] = Y[(y1_lo + q) ^ HALF];
             } else if (sidx == 1) {
                 // sync word 2: integer carrier offset (ofdm_chanest_vcvc), then the channel taps
-                float2 acc[4];
-#pragma unroll
-                for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
-                for (int c0 = lane; c0 < p.n_cv; c0 += 128) {
-                    // four table entries per lane per trip, loaded together (global, L2-resident)
-                    int kc[4];
-                    float2 cvc[4];
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) {
-                        const int c = c0 + 32 * w4;
-                        kc[w4] = (c < p.n_cv) ? p.cv_k[c] : -1;
-                        cvc[w4] = (c < p.n_cv) ? p.cv_conj[c] : make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) {
-                        if (kc[w4] < 0) continue;
-#pragma unroll
-                        for (int gi = 0; gi < 4; gi++)
-                            if (gi < ng) {
-                                const int k = kc[w4] + p.gneg + 2 * gi;
-                                acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ 512], Hs[k - y1_lo]), cvc[w4]));
-                            }
-                    }
-                }
                 float b = 0.f;
+                for (int g0 = 0; g0 < ng && (NFFT != 1024 || g0 == 0); g0 += 4) {   // candidates in groups of four (one group at fft_len 1024)
+                    float2 acc[4];
 #pragma unroll
-                for (int gi = 0; gi < 4; gi++) {
-                    for (int o = 16; o > 0; o >>= 1) {
-                        acc[gi].x += __shfl_xor_sync(0xffffffffu, acc[gi].x, o);
-                        acc[gi].y += __shfl_xor_sync(0xffffffffu, acc[gi].y, o);
+                    for (int gi = 0; gi < 4; gi++) acc[gi] = make_float2(0.f, 0.f);
+                    for (int c0 = lane; c0 < p.n_cv; c0 += 128) {
+                        // four table entries per lane per trip, loaded together (global, L2-resident)
+                        int kc[4];
+                        float2 cvc[4];
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; w4++) {
+                            const int c = c0 + 32 * w4;
+                            kc[w4] = (c < p.n_cv) ? p.cv_k[c] : -1;
+                            cvc[w4] = (c < p.n_cv) ? p.cv_conj[c] : make_float2(0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; w4++) {
+                            if (kc[w4] < 0) continue;
+#pragma unroll
+                            for (int gi = 0; gi < 4; gi++)
+                                if (g0 + gi < ng) {
+                                    const int k = kc[w4] + p.gneg + 2 * (g0 + gi);
+                                    acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ HALF], Hs[k - y1_lo]), cvc[w4]));
+                                }
+                        }
                     }
-                    const float v = acc[gi].x * acc[gi].x + acc[gi].y * acc[gi].y;
-                    if (gi < ng && v > b) { b = v; off = p.gneg + 2 * gi; }
+#pragma unroll
+                    for (int gi = 0; gi < 4; gi++) {
+                        for (int o = 16; o > 0; o >>= 1) {
+                            acc[gi].x += __shfl_xor_sync(0xffffffffu, acc[gi].x, o);
+                            acc[gi].y += __shfl_xor_sync(0xffffffffu, acc[gi].y, o);
+                        }
+                        const float v = acc[gi].x * acc[gi].x + acc[gi].y * acc[gi].y;
+                        if (g0 + gi < ng && v > b) { b = v; off = p.gneg + 2 * (g0 + gi); }
+                    }
                 }
                 __syncwarp();
                 // H[k] = Y2[k+off] / sw2[k] (overwrites the parked Y1 bins)
@@ -278,7 +292,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     const int k = s_occ[u];
                     const int src = k + off;
                     float2 Hk = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) Hk = cmul(Y[src ^ 512], p.inv_sw2[k]);
+                    if (src >= 0 && src < N) Hk = cmul(Y[src ^ HALF], p.inv_sw2[k]);
                     Hs[u] = Hk;
                 }
             } else if (sidx == 2) {
@@ -294,7 +308,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                 for (int u = lane; u < nu; u += 32) {
                     const int src = (int)s_occ[u] + off;
                     float2 y = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) y = cmul(Y[src ^ 512], pc);
+                    if (src >= 0 && src < N) y = cmul(Y[src ^ HALF], pc);
                     float2 Hk = Hs[u];
                     const float hinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
                     const float2 hn = cmul_conj(y, Hk);
@@ -338,6 +352,8 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                     pc = make_float2(cs, -sn);
                 }
                 const int cb = i * size0;
+                // bits per OFDM symbol not a multiple of 8 (dec_all > 0): keep the decisions of the whole packet, pack at the end
+                uint8_t *decw = dec + (dec_all > 0 ? cb : 0);
                 for (int u0 = lane; u0 < nu; u0 += 32 * FW_DFE_UNROLL) {
                     // several carriers per lane per trip: independent chains for the scheduler to interleave
 #pragma unroll
@@ -347,7 +363,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                             const int src = (int)s_occ[u] + off;
                             float2 y = make_float2(0.f, 0.f);
                             if (src >= 0 && src < N) {
-                                y = Y[src ^ 512];
+                                y = Y[src ^ HALF];
                                 if (off != 0) y = cmul(y, pc);
                             }
                             float2 Hk = Hs[u];
@@ -358,7 +374,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                             const float2 q = cmul(y, ipts[d]);
                             Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                             const int pos = s_pos[u];
-                            dec[pos] = (uint8_t)d;
+                            decw[pos] = (uint8_t)d;
                             if (WANT_Z) {
                                 const int idx = cb + pos;
                                 if (idx < psyms && p.hl + idx < z_stride) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + p.hl + idx] = z;
@@ -369,7 +385,7 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
                 __syncwarp();
                 // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes
                 const int b0 = i * sym_bytes;
-                const int nbytes = fs->nbytes;
+                const int nbytes = (dec_all > 0) ? 0 : fs->nbytes;
                 if ((BPS_P == 4 || BPS_P == 2) && words_ok && (sym_bytes & 3) == 0) {
                     // four bytes per lane: decisions read as words, nibbles / bit pairs squeezed together
                     const uint32_t *dw = reinterpret_cast<const uint32_t *>(dec);
@@ -424,6 +440,20 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
             fw_flush(fs, spec + j, lane);
             continue;
         }
+        if (dec_all > 0) {
+            // repack_bits_bb(bps, 8) + additive_scrambler_bb over the stored decisions of the whole packet
+            const int nb = fs->nbytes;
+            __syncwarp();
+            for (int m = lane; m < nb; m += 32) {
+                unsigned v = 0;
+                for (int b = 0; b < 8; b++) {
+                    const int bi = m * 8 + b;
+                    const int si = bi / BPS_P, sb = bi - si * BPS_P;
+                    v |= ((unsigned)(dec[si] >> sb) & 1u) << b;
+                }
+                bytes_out[(unsigned long long)(unsigned)j * (unsigned long long)byte_stride + m] = (uint8_t)v ^ __ldg(&p.keystream[m]);
+            }
+        }
         bool crc_ok = true;
         if (p.crc_mode) {
             const int nbytes = fs->nbytes;
@@ -444,12 +474,13 @@ rx_frame1024w_kernel(const KP p, const float2 *__restrict__ samples, long long n
     }
 }
 
-static inline size_t frame1024w_smem_bytes(int n_occ_u, int y1_span, int warps, bool dec_in_guard)
+static inline size_t framew_smem_bytes(int nfft, int n_occ_u, int y1_span, int warps, bool dec_in_guard, int dec_all)
 {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t nu8 = (size_t)((n_occ_u + 7) & ~7);
-    const size_t shared_bytes = (size_t)1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64;
+    const size_t yslot = (nfft == 1024) ? (size_t)F1K_SLOT : (size_t)nfft;
+    const size_t shared_bytes = (size_t)nfft * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64;
     const size_t hsz = (size_t)((std::max(n_occ_u, y1_span) + 1) & ~1);
-    const size_t per_warp = (size_t)F1K_SLOT * 8 + hsz * 8 + (dec_in_guard ? 0 : al16(n_occ_u)) + 64 + sizeof(FwState);
+    const size_t per_warp = yslot * 8 + hsz * 8 + (dec_in_guard ? 0 : al16(dec_all > 0 ? dec_all : n_occ_u)) + 64 + sizeof(FwState);
     return al16(shared_bytes) + (size_t)warps * per_warp + 16;
 }

@@ -1,0 +1,104 @@
+// ofdmx_symbol_small.cuh -- one OFDM symbol for the warp-per-frame receiver, fft_len 64 .. 512.
+//
+// A lane owns R = fft_len/32 samples of the symbol (m = 32 a + lane).  With k = k1 + R k2:
+//     X[k1 + R k2] = sum_b [ (sum_a x[32 a + b] W_R^(a k1)) W_N^(b k1) ] W_32^(b k2)
+// pass 1 is an R-point FFT in registers (generated, fft_small_gen.cuh), pass 2 a 32-point FFT ACROSS THE LANES by
+// butterfly shuffles (five stages, decimation in frequency, one per register slot k1).  The result is written to
+// shared memory in natural bin order, like f1k_symbol does for fft_len 1024, so the equaliser code is shared.
+#pragma once
+#include "ofdmx_frame1024.cuh"
+#include "fft_small_gen.cuh"
+
+template <int R> __device__ __forceinline__ void fftR_fwd(float2 (&v)[R]);
+template <> __device__ __forceinline__ void fftR_fwd<2>(float2 (&v)[2]) { fft2_fwd(v); }
+template <> __device__ __forceinline__ void fftR_fwd<4>(float2 (&v)[4]) { fft4_fwd(v); }
+template <> __device__ __forceinline__ void fftR_fwd<8>(float2 (&v)[8]) { fft8_fwd(v); }
+template <> __device__ __forceinline__ void fftR_fwd<16>(float2 (&v)[16]) { fft16_fwd(v); }
+
+template <int R> __device__ __forceinline__ constexpr int brevR(int x)
+{
+    int r = 0;
+    for (int b = 1, o = R >> 1; b < R; b <<= 1, o >>= 1)
+        if (x & b) r |= o;
+    return r;
+}
+
+// per-lane twiddles of the lane-FFT stages with span 16, 8, 4: W_{2 span}^(lane mod span) (spans 2 and 1 are trivial)
+struct LaneTw { float2 w16, w8, w4; };
+
+__device__ __forceinline__ LaneTw lane_twiddles(int lane)
+{
+    LaneTw t;
+    float sn, cs;
+    sincospif(-(float)(lane & 15) * (1.0f / 16.0f), &sn, &cs); t.w16 = make_float2(cs, sn);
+    sincospif(-(float)(lane & 7) * (1.0f / 8.0f), &sn, &cs); t.w8 = make_float2(cs, sn);
+    sincospif(-(float)(lane & 3) * (1.0f / 4.0f), &sn, &cs); t.w4 = make_float2(cs, sn);
+    return t;
+}
+
+// 32-point forward DFT across the lanes: in: z (lane b), out: lane l holds X[brev5(l)]
+__device__ __forceinline__ float2 lane_fft32(float2 z, int lane, const LaneTw &tw)
+{
+#pragma unroll
+    for (int span = 16; span >= 1; span >>= 1) {
+        const float tx = __shfl_xor_sync(0xffffffffu, z.x, span), ty = __shfl_xor_sync(0xffffffffu, z.y, span);
+        const bool up = (lane & span) != 0;
+        // lower lane keeps a + b, upper lane gets (a - b) w, where a is the lower lane's value
+        float2 s = up ? make_float2(tx - z.x, ty - z.y) : make_float2(z.x + tx, z.y + ty);
+        if (span == 16) s = up ? cmul(s, tw.w16) : s;
+        else if (span == 8) s = up ? cmul(s, tw.w8) : s;
+        else if (span == 4) s = up ? cmul(s, tw.w4) : s;
+        else if (span == 2) s = (up && (lane & 1)) ? make_float2(s.y, -s.x) : s;          // W_4^1 = -j
+        z = s;
+    }
+    return z;
+}
+
+// One symbol: load + derotate + NFFT-point FFT.  Result: Y[k] = X[k], natural order, k < NFFT.
+// tws[k1 * 32 + b] = W_NFFT^(b k1), k1 < R.
+template <int NFFT>
+__device__ __forceinline__ void fsmall_symbol(const KP &p, const float2 *__restrict__ r, long long n, long long i0,
+                                              long long t, double kappa, float2 st, bool slow, int j, int jend,
+                                              const long long *__restrict__ trig, const float *__restrict__ cfo,
+                                              float2 *__restrict__ Y, const float2 *__restrict__ tws, int lane,
+                                              const LaneTw &ltw)
+{
+    constexpr int R = NFFT / 32;
+    float2 v[R];
+    const long long sbase = i0 - p.D + lane;
+#pragma unroll
+    for (int a = 0; a < R; a++) {
+        const long long s = sbase + 32 * a;
+        v[a] = (s >= 0 && s < n) ? __ldg(&r[s]) : make_float2(0.f, 0.f);
+    }
+    {
+        double tb = kappa * (double)(i0 + lane - t + 1);
+        tb -= rint(tb);
+        float sn, cs;
+        sincospif(2.0f * (float)tb, &sn, &cs);
+        float2 ph = make_float2(cs, sn);
+        const long long tnx = (slow && j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
+#pragma unroll
+        for (int a = 0; a < R; a++) {
+            const long long i = i0 + lane + 32 * a;
+            float2 pa = ph;
+            if (i >= tnx) {      // sample-and-hold value changed inside the frame: exact piecewise phase
+                double turns = nco_turns(i, j, jend, trig, cfo, NFFT);
+                turns -= rint(turns);
+                float s2, c2;
+                sincospif(2.0f * (float)turns, &s2, &c2);
+                pa = make_float2(c2, s2);
+            }
+            v[a] = cmul(v[a], pa);
+            ph = cmul(ph, st);
+        }
+    }
+    fftR_fwd<R>(v);                                   // v[brevR(k1)] = y_b[k1]
+    const int k2 = brev5(lane);
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+        const int k1 = brevR<R>(q);
+        const float2 z = (k1 == 0) ? v[q] : cmul(v[q], tws[k1 * 32 + lane]);
+        Y[k1 + R * k2] = lane_fft32(z, lane, ltw);
+    }
+}

@@ -8,7 +8,7 @@ ROOT = os.path.normpath(os.path.join(_HERE, "..", ".."))
 CSRC = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
 LIBDIR = os.path.normpath(os.path.join(_HERE, "..", "lib"))
 SOURCES = ["ofdmx_api.cu"]
-HEADERS = ["ofdmx_dev.cuh", "ofdmx_kernels.cuh", "ofdmx_sync.cuh", "ofdmx_frame1024.cuh", "fft32_gen.cuh", "ofdmx_chain.cuh", "ofdmx_sync_tma.cuh", "ofdmx_frame1024w.cuh", "ofdmx_cond.cuh", "ofdmx_sync_warp.cuh", "ofdmx_tx1024w.cuh"]
+HEADERS = ["ofdmx_dev.cuh", "ofdmx_kernels.cuh", "ofdmx_sync.cuh", "ofdmx_frame1024.cuh", "fft32_gen.cuh", "ofdmx_chain.cuh", "ofdmx_sync_tma.cuh", "ofdmx_frame1024w.cuh", "ofdmx_cond.cuh", "ofdmx_sync_warp.cuh", "ofdmx_tx1024w.cuh", "ofdmx_symbol_small.cuh", "fft_small_gen.cuh"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

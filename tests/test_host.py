@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert lib.ofdmx_profile_slots() >= 10
     assert lib.ofdmx_profile_name(0) == b"sync_metric_kernel"
     names = {lib.ofdmx_profile_name(i) for i in range(lib.ofdmx_profile_slots())}
-    assert {b"rx_frame1024w_kernel", b"sync_metric_fast_kernel", b"sync_metric_tma_kernel"} <= names
+    assert {b"rx_framew_kernel", b"sync_metric_fast_kernel", b"sync_metric_tma_kernel"} <= names
 
 
 def test_struct_layouts():

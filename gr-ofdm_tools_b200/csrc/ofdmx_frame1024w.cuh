@@ -183,11 +183,12 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
         tws[i] = make_float2(cs, sn);
     }
     for (int i = tid; i < nu; i += NTH) { s_occ[i] = (uint16_t)p.occ_u[i]; s_pos[i] = (uint16_t)p.pos_su[i]; }
-    if (tid < 256) s_tab[tid] = p.crc_tab[tid];
-    if (tid < 32) s_pow[tid] = p.crc_pow64[tid];
-    if (tid < 64) {
-        lut[tid] = p.lut_p[tid];
-        ipts[tid] = (tid < (1 << BPS_P)) ? p.inv_ppts[tid] : make_float2(0.f, 0.f);
+    // (strided loops: the CTA may have fewer than 256 threads when the per-warp buffers are large)
+    for (int i = tid; i < 256; i += NTH) s_tab[i] = p.crc_tab[i];
+    for (int i = tid; i < 32; i += NTH) s_pow[i] = p.crc_pow64[i];
+    for (int i = tid; i < 64; i += NTH) {
+        lut[i] = p.lut_p[i];
+        ipts[i] = (i < (1 << BPS_P)) ? p.inv_ppts[i] : make_float2(0.f, 0.f);
     }
     __syncthreads();
 

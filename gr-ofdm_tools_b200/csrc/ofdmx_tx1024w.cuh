@@ -50,9 +50,9 @@ tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long
         map[i] = tx_map[i];
         hmask[i] = (i < p.hl) ? p.hdr_mask[i] : 0;
     }
-    if (tid < 256) s_tab[tid] = p.crc_tab[tid];
-    if (tid < 32) s_pow[tid] = p.crc_pow64[tid];
-    if (tid < 64) pts[tid] = (tid < (1 << BPS_P)) ? p.ppts[tid] : make_float2(0.f, 0.f);
+    for (int i = tid; i < 256; i += NTH) s_tab[i] = p.crc_tab[i];
+    for (int i = tid; i < 32; i += NTH) s_pow[i] = p.crc_pow64[i];
+    for (int i = tid; i < 64; i += NTH) pts[i] = (i < (1 << BPS_P)) ? p.ppts[i] : make_float2(0.f, 0.f);
     __syncthreads();
 
     const int N = 1024, D = p.D, cp = p.cp;

@@ -345,7 +345,7 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         // fft_len 1024: warp-autonomous streaming (no block barriers), spans of tiles of 512 samples per warp
         const long long tiles = (n_samples + SW_TILE - 1) / SW_TILE;
         const long long warps = (long long)ctx->sm_count * SW_WARPS;
-        long long span = (tiles * n_streams + 8 * warps - 1) / (8 * warps);
+        long long span = (tiles * n_streams + 4 * warps - 1) / (4 * warps);
         span = std::max<long long>(16, std::min<long long>(span, 1024));
         const long long spans = (tiles + span - 1) / span;
         const long long total = spans * n_streams;

@@ -18,9 +18,6 @@
 
 #define FW_WARPS 16
 #define FW_THREADS (FW_WARPS * 32)
-#ifndef FW_DFE_UNROLL
-#define FW_DFE_UNROLL 1
-#endif
 
 // Per-warp frame state kept in shared memory: these values live across the register-hungry FFT of every
 // symbol, where the compiler would otherwise spill them to local memory (whose reloads miss the small L1
@@ -355,33 +352,34 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                 const int cb = i * size0;
                 // bits per OFDM symbol not a multiple of 8 (dec_all > 0): keep the decisions of the whole packet, pack at the end
                 uint8_t *decw = dec + (dec_all > 0 ? cb : 0);
-                for (int u0 = lane; u0 < nu; u0 += 32 * FW_DFE_UNROLL) {
-                    // several carriers per lane per trip: independent chains for the scheduler to interleave
-#pragma unroll
-                    for (int w4 = 0; w4 < FW_DFE_UNROLL; w4++) {
-                        const int u = u0 + 32 * w4;
-                        if (u < nu) {
-                            const int src = (int)s_occ[u] + off;
-                            float2 y = make_float2(0.f, 0.f);
-                            if (src >= 0 && src < N) {
-                                y = Y[src ^ HALF];
-                                if (off != 0) y = cmul(y, pc);
-                            }
-                            float2 Hk = Hs[u];
-                            const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
-                            const float2 nn = cmul_conj(y, Hk);
-                            const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
-                            const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
-                            const float2 q = cmul(y, ipts[d]);
-                            Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
-                            const int pos = s_pos[u];
-                            decw[pos] = (uint8_t)d;
-                            if (WANT_Z) {
-                                const int idx = cb + pos;
-                                if (idx < psyms && p.hl + idx < z_stride) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + p.hl + idx] = z;
-                            }
-                        }
+                // one carrier per lane per trip; the index look-ups of the NEXT trip are issued before the arithmetic of
+                // this one, so the dependent chain of a trip starts at the data loads (deeper pipelining, also of the Y/H
+                // loads, measured slower: more code and registers)
+                int kc = (lane < nu) ? (int)s_occ[lane] : 0, posc = (lane < nu) ? (int)s_pos[lane] : 0;
+                for (int u = lane; u < nu; u += 32) {
+                    const int un = u + 32;
+                    int kn = 0, posn = 0;
+                    if (un < nu) { kn = (int)s_occ[un]; posn = (int)s_pos[un]; }
+                    const int src = kc + off;
+                    float2 y = make_float2(0.f, 0.f);
+                    if (src >= 0 && src < N) {
+                        y = Y[src ^ HALF];
+                        if (off != 0) y = cmul(y, pc);
                     }
+                    float2 Hk = Hs[u];
+                    const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
+                    const float2 nn = cmul_conj(y, Hk);
+                    const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
+                    const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                    const float2 q = cmul(y, ipts[d]);
+                    Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                    decw[posc] = (uint8_t)d;
+                    if (WANT_Z) {
+                        const int idx = cb + posc;
+                        if (idx < psyms && p.hl + idx < z_stride) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + p.hl + idx] = z;
+                    }
+                    kc = kn;
+                    posc = posn;
                 }
                 __syncwarp();
                 // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes

@@ -1,17 +1,21 @@
-// ofdmx_frame1024w.cuh -- K1+K3+K4, fft_len 1024, ONE WARP PER FRAME.
+// ofdmx_frame1024w.cuh -- K1+K3+K4 with ONE WARP PER FRAME: rx_framew_kernel<fft_len, bps, want_z>,
+// instantiated for fft_len 1024 (the benchmark path) and for fft_len 64 / 128 (the carrier plans of
+// ofdm_tx_rx_hier and ofdm_radio_hier).
 //
-// The CTA-per-frame kernel (ofdmx_frame1024.cuh) spends ~40 % of its instructions on redundancy: ten
-// warps each run the per-frame scalar code, the header/CRC/pack phases and wait at ~10 block barriers
-// per frame.  Here a frame belongs to a single warp, which streams its OFDM symbols one at a time:
-//     load + derotate + 1024-point register FFT (f1k_symbol)  ->  equalise/demap the symbol with the
-//     lanes spread over the carriers  ->  pack + descramble its bytes
-// keeping only one symbol (8.5 KB), the channel state (4.8 KB) and the packet bytes in shared memory.
-// There is no block-level synchronisation after the prologue; 13 independent warps per SM sit in
-// different phases (FP32-heavy FFT, LDS-heavy equaliser, integer CRC) and fill each other's stalls.
+// The CTA-per-frame kernels (ofdmx_frame1024.cuh, rx_frame_kernel) spend a large part of their instructions on
+// redundancy: every warp runs the per-frame scalar code, the header/CRC/pack phases and waits at ~10 block
+// barriers per frame.  Here a frame belongs to a single warp, which streams its OFDM symbols one at a time:
+//     load + derotate + FFT (f1k_symbol: 32x32 in registers; fsmall_symbol: registers + lane shuffles)
+//     ->  equalise/demap the symbol with the lanes spread over the carriers  ->  pack + descramble its bytes
+// keeping only one symbol, the channel state and 80 bytes of frame state in shared memory.  There is no
+// block-level synchronisation after the prologue; the warps of an SM sit in different phases (FP32-heavy FFT,
+// LDS-heavy equaliser, integer CRC) and fill each other's stalls.  Two measured facts shaped the code
+// (profiles/r1_final_summary.md): the steady-state loop has to fit the SM's 32 KB instruction cache, and
+// throughput scales with the number of resident warps (16 at fft_len 1024, where the register file is full).
 //
-// Preconditions checked by the host (otherwise the CTA-per-frame kernel runs): one carrier set, no pilot
-// inside the occupied set, BPSK header with >= 32 items, <= 4 integer-offset candidates
-// (max_carr_offset given), bits per OFDM symbol a multiple of 8, <= 1024 occupied carriers.
+// Preconditions checked by the host (otherwise a CTA-per-frame kernel runs): one carrier set, no pilot inside the
+// occupied set, BPSK header with >= 32 items; at fft_len 1024 also <= 4 integer-offset candidates
+// (max_carr_offset given) and bits per OFDM symbol a multiple of 8.
 #pragma once
 #include "ofdmx_frame1024.cuh"
 #include "ofdmx_symbol_small.cuh"

@@ -38,7 +38,7 @@ static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_frame1024w_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -644,30 +644,30 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64) UP(crc_pow8, crc_pow8)
 #undef UP
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
-    if (N == 1024 && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && prm->n_pilot_sym_sets <= 1 && !kp.pil_in_occ
+    if ((N == 1024 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
         && kp.bps_h == 1 && c->hl >= 32) {
-        std::vector<uint16_t> tx_map(1024, (uint16_t)TXW_EMPTY);
-        for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ 512] = (uint16_t)q;   // later entries win, as in the scatter
-        for (int q = 0; q < (int)pil_bins.size(); q++) tx_map[pil_bins[q] ^ 512] = (uint16_t)(TXW_PILOT | q);
+        std::vector<uint16_t> tx_map((size_t)N, (uint16_t)TXW_EMPTY);
+        for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
+        for (int q = 0; q < (int)pil_bins.size(); q++) tx_map[pil_bins[q] ^ (N / 2)] = (uint16_t)(TXW_PILOT | q);
         std::vector<float2> sync_td((size_t)2 * kp.D);
-        std::vector<double> cs(1024), sn(1024);
-        for (int k = 0; k < 1024; k++) { cs[k] = cos(2.0 * M_PI * k / 1024.0); sn[k] = sin(2.0 * M_PI * k / 1024.0); }
+        std::vector<double> cs((size_t)N), sn((size_t)N);
+        for (int k = 0; k < N; k++) { cs[k] = cos(2.0 * M_PI * k / N); sn[k] = sin(2.0 * M_PI * k / N); }
         for (int o = 0; o < 2; o++) {
             const float *sw = o ? prm->sync_word2 : prm->sync_word1;       // shifted order, (re, im)
-            std::vector<double> xr(1024), xi(1024);
-            for (int t = 0; t < 1024; t++) {
+            std::vector<double> xr((size_t)N), xi((size_t)N);
+            for (int t = 0; t < N; t++) {
                 double ar = 0.0, ai = 0.0;
-                for (int nn = 0; nn < 1024; nn++) {
-                    const double vr = sw[2 * (nn ^ 512)], vi = sw[2 * (nn ^ 512) + 1];
+                for (int nn = 0; nn < N; nn++) {
+                    const double vr = sw[2 * (nn ^ (N / 2))], vi = sw[2 * (nn ^ (N / 2)) + 1];
                     if (vr == 0.0 && vi == 0.0) continue;
-                    const int ph = (nn * t) & 1023;
+                    const int ph = (nn * t) & (N - 1);
                     ar += vr * cs[ph] - vi * sn[ph];
                     ai += vr * sn[ph] + vi * cs[ph];
                 }
                 xr[t] = ar; xi[t] = ai;
             }
             for (int m = 0; m < kp.D; m++) {
-                const int t = (m - kp.cp + 1024) & 1023;
+                const int t = (m - kp.cp + N) & (N - 1);
                 float vr = (float)(xr[t] * (double)kp.tx_scale), vi = (float)(xi[t] * (double)kp.tx_scale);
                 if (kp.tx_clip > 0.f) {
                     vr = vr < -kp.tx_clip ? -kp.tx_clip : (vr > kp.tx_clip ? kp.tx_clip : vr);
@@ -758,9 +758,10 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             }
         }
         if (c->tx1kw) {
-            c->tx1kw_smem = tx1024w_smem_bytes(kp.max_pkt_bytes, TXW_WARPS);
+            c->tx1kw_smem = txw_smem_bytes(N, kp.max_pkt_bytes, TXW_WARPS);
             cudaError_t e1 = cudaSuccess;
-#define TXW_ATTR(B) { cudaError_t e2 = cudaFuncSetAttribute(tx_frame1024w_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
+#define TXW_ATTR1(NN, B) { cudaError_t e2 = cudaFuncSetAttribute(tx_framew_kernel<NN, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
+#define TXW_ATTR(B) { if (N == 1024) TXW_ATTR1(1024, B) else if (N == 128) TXW_ATTR1(128, B) else TXW_ATTR1(64, B) }
             switch (kp.bps_p) {
             case 1: TXW_ATTR(1) break;
             case 2: TXW_ATTR(2) break;
@@ -769,6 +770,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             default: TXW_ATTR(6) break;
             }
 #undef TXW_ATTR
+#undef TXW_ATTR1
             if (e1 != cudaSuccess || c->tx1kw_smem > 227 * 1024) c->tx1kw = false;
         }
         c->sync_tma_smem = sync_tma_smem_bytes(N);
@@ -1012,8 +1014,9 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
         const unsigned grid = (unsigned)std::min<int64_t>((n_pkts + TXW_WARPS - 1) / TXW_WARPS, (int64_t)c->sm_count);
         const int pbb = (int)tx1024w_pb_bytes(c->kp.max_pkt_bytes);
         KT(K_TX1KW);
-#define TXW(B) tx_frame1024w_kernel<B><<<grid, TXW_WARPS * 32, c->tx1kw_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts, \
+#define TXW1(NN, B) tx_framew_kernel<NN, B><<<grid, TXW_WARPS * 32, c->tx1kw_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts, \
             first_pkt_num, (float2 *)samples_out, cap_samples, (const long long *)sample_off_dev, c->tx_map, c->sync_td, c->x_2048, pbb)
+#define TXW(B) { if (c->kp.N == 1024) TXW1(1024, B); else if (c->kp.N == 128) TXW1(128, B); else TXW1(64, B); }
         switch (c->kp.bps_p) {
         case 1: TXW(1); break;
         case 2: TXW(2); break;
@@ -1022,6 +1025,7 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
         default: TXW(6); break;
         }
 #undef TXW
+#undef TXW1
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
         KT(K_TX);

@@ -1,4 +1,5 @@
-// ofdmx_tx1024w.cuh -- K5+K1, fft_len 1024: the TX chain with ONE WARP PER PACKET.
+// ofdmx_tx1024w.cuh -- K5+K1: the TX chain with ONE WARP PER PACKET, tx_framew_kernel<fft_len, bps> for fft_len 1024
+// (register IFFT 32 x 32) and fft_len 64 / 128 (register FFT + lane-shuffle FFT on conjugated data).
 //
 // Mirror image of the warp-per-frame receiver (ofdmx_frame1024w.cuh).  The generic tx_frame_kernel gives a
 // 256-thread CTA to every packet and runs a radix-4 shared-memory IFFT with a block barrier per stage; here a
@@ -13,7 +14,7 @@
 //     transpose through shared memory) and stores the samples with the cyclic prefix, x tx_scale and the clipper
 //     straight from the registers in coalesced 256-byte rows.
 // Preconditions checked by the host (otherwise the generic kernel runs): fft_len 1024, one carrier set, at most
-// one pilot set with one pilot-symbol set, no pilot inside the occupied set, BPSK header.
+// one pilot set (its symbols may cycle over several pilot-symbol sets), no pilot inside the occupied set, BPSK header.
 #pragma once
 #include "ofdmx_frame1024w.cuh"
 
@@ -21,9 +22,69 @@
 #define TXW_EMPTY 0xFFFFu
 #define TXW_PILOT 0x8000u
 
-template <int BPS_P>
+// inverse FFT of the lane-distributed spectrum v (bin 32 a + lane) + ofdm_cyclic_prefixer(rolloff 0) +
+// multiply_const(tx_scale) + clipper, stored to dst[0 .. fft_len + cp)
+template <int NFFT>
+__device__ __forceinline__ void tx_ifft_store(float2 (&v)[NFFT / 32], float2 *__restrict__ Tw, const float2 *__restrict__ tws,
+                                              const LaneTw &ltw, float2 *__restrict__ dst, int cp, float sc, float clip, int lane)
+{
+    auto finish = [&](float2 x) {
+        float2 w = make_float2(x.x * sc, x.y * sc);
+        if (clip > 0.f) {
+            w.x = w.x < -clip ? -clip : (w.x > clip ? clip : w.x);
+            w.y = w.y < -clip ? -clip : (w.y > clip ? clip : w.y);
+        }
+        return w;
+    };
+    if constexpr (NFFT == 1024) {
+        // x[k1 + 32 k2] = sum_b [ (sum_a X[32 a + b] W32^(-a k1)) W1024^(-b k1) ] W32^(-b k2)
+        fft32_inv(v);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+            const int k1 = brev5(q);
+            Tw[k1 * F1K_ROW + lane] = cmul_conj(v[q], tws[k1 * 32 + lane]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(&Tw[lane * F1K_ROW + 2 * q]);
+            v[2 * q] = make_float2(t4.x, t4.y);
+            v[2 * q + 1] = make_float2(t4.z, t4.w);
+        }
+        fft32_inv(v);
+        // straight from the registers: lane = k1, v[q] = x[k1 + 32 brev5(q)]
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+            const int t = lane + 32 * brev5(q);
+            const float2 w = finish(v[q]);
+            dst[cp + t] = w;
+            if (t >= NFFT - cp) dst[t - (NFFT - cp)] = w;
+        }
+    } else {
+        // inverse transform = conj(forward(conj X)): fft_len/32-point FFT in registers, twiddles, 32-point FFT across
+        // the lanes; time samples staged in shared memory so that the global stores are contiguous
+        constexpr int R = NFFT / 32;
+#pragma unroll
+        for (int a = 0; a < R; a++) v[a].y = -v[a].y;
+        fftR_fwd<R>(v);
+        const int k2 = brev5(lane);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            const int k1 = brevR<R>(q);
+            const float2 z = (k1 == 0) ? v[q] : cmul(v[q], tws[k1 * 32 + lane]);
+            const float2 x = lane_fft32(z, lane, ltw);
+            Tw[k1 + R * k2] = make_float2(x.x, -x.y);
+        }
+        __syncwarp();
+        for (int m = lane; m < NFFT + cp; m += 32) dst[m] = finish(Tw[(m - cp + NFFT) & (NFFT - 1)]);
+    }
+}
+
+template <int NFFT, int BPS_P>
 __global__ void __launch_bounds__(TXW_WARPS * 32, 1)
-tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long long *__restrict__ pkt_off,
+tx_framew_kernel(const KP p, const uint8_t *__restrict__ payload, const long long *__restrict__ pkt_off,
                      long long n_pkts, int first_num, float2 *__restrict__ out, long long cap,
                      const long long *__restrict__ sample_off, const uint16_t *__restrict__ tx_map,
                      const float2 *__restrict__ sync_td, uint32_t x_2048, int pb_bytes)
@@ -32,20 +93,21 @@ tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NTH = blockDim.x;
     // ---- CTA-shared tables
     float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024] W1024^(b k1), forward sign
-    float2 *pts = tws + 1024;                                     // [64] payload constellation
+    float2 *pts = tws + NFFT;                                     // [64] payload constellation
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(pts + 64);     // [256] CRC-32 table
     uint32_t *s_pow = s_tab + 256;                                // [32]
     uint16_t *map = reinterpret_cast<uint16_t *>(s_pow + 32);     // [1024] natural bin -> data position / pilot / empty
-    uint8_t *hmask = reinterpret_cast<uint8_t *>(map + 1024);     // [1024] header scrambling mask (zero padded)
-    const size_t shared_bytes = 1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 1024 * 2 + 1024;
-    unsigned char *wbase = smem_raw + shared_bytes + (size_t)wid * ((size_t)F1K_SLOT * 8 + pb_bytes);
-    float2 *Tw = reinterpret_cast<float2 *>(wbase);               // F1K_SLOT
-    uint8_t *pb = reinterpret_cast<uint8_t *>(Tw + F1K_SLOT);     // packet bytes (+ CRC), 16-byte aligned
+    uint8_t *hmask = reinterpret_cast<uint8_t *>(map + NFFT);     // [NFFT] header scrambling mask (zero padded)
+    constexpr int TSLOT = (NFFT == 1024) ? F1K_SLOT : NFFT;       // float2 per warp buffer
+    const size_t shared_bytes = NFFT * 8 + 64 * 8 + 256 * 4 + 32 * 4 + NFFT * 2 + NFFT;
+    unsigned char *wbase = smem_raw + shared_bytes + (size_t)wid * ((size_t)TSLOT * 8 + pb_bytes);
+    float2 *Tw = reinterpret_cast<float2 *>(wbase);               // TSLOT
+    uint8_t *pb = reinterpret_cast<uint8_t *>(Tw + TSLOT);        // packet bytes (+ CRC), 16-byte aligned
 
-    for (int i = tid; i < 1024; i += NTH) {
+    for (int i = tid; i < NFFT; i += NTH) {
         const int k1 = i >> 5, b = i & 31;
         float sn, cs;
-        sincospif(-(float)(b * k1) * (1.0f / 512.0f), &sn, &cs);
+        sincospif(-(float)(b * k1) * (2.0f / NFFT), &sn, &cs);
         tws[i] = make_float2(cs, sn);
         map[i] = tx_map[i];
         hmask[i] = (i < p.hl) ? p.hdr_mask[i] : 0;
@@ -55,7 +117,9 @@ tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long
     for (int i = tid; i < 64; i += NTH) pts[i] = (i < (1 << BPS_P)) ? p.ppts[i] : make_float2(0.f, 0.f);
     __syncthreads();
 
-    const int N = 1024, D = p.D, cp = p.cp;
+    constexpr int N = NFFT;
+    const int D = p.D, cp = p.cp;
+    const LaneTw ltw = lane_twiddles(lane);          // lane-FFT twiddles (fft_len < 1024 only)
     const int size0 = p.occ_size[0];
     const float2 h0 = p.hpts[0], h1 = p.hpts[1];
     const float sc = p.tx_scale, clip = p.tx_clip;
@@ -97,10 +161,12 @@ tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long
         for (int m = lane; m < 2 * D; m += 32) out[base + m] = __ldg(&sync_td[m]);
         // ---- header and payload symbols
         for (int o = 2; o < n_ofdm; o++) {
-            float2 v[32];
+            constexpr int R = NFFT / 32;                       // IFFT inputs per lane: bins 32 a + lane
+            float2 v[R];
             const int sbase = (o - 3) * size0;
+            const int pil0 = (p.n_pil_sym_sets > 1) ? p.pil_sym_base[(o - 2) % p.n_pil_sym_sets] : 0;   // pilot symbols cycle per OFDM symbol
 #pragma unroll
-            for (int a = 0; a < 32; a++) {
+            for (int a = 0; a < R; a++) {
                 const unsigned code = map[32 * a + lane];
                 float2 val = make_float2(0.f, 0.f);
                 if (code < TXW_PILOT) {
@@ -121,45 +187,19 @@ tx_frame1024w_kernel(const KP p, const uint8_t *__restrict__ payload, const long
                         }
                     }
                 } else if (code != TXW_EMPTY) {
-                    val = __ldg(&p.pil_sym[code & 0x7FFFu]);
+                    val = __ldg(&p.pil_sym[pil0 + (code & 0x7FFFu)]);
                 }
                 v[a] = val;
             }
-            // x[k1 + 32 k2] = sum_b [ (sum_a X[32 a + b] W32^(-a k1)) W1024^(-b k1) ] W32^(-b k2)
-            fft32_inv(v);
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 32; q++) {
-                const int k1 = brev5(q);
-                Tw[k1 * F1K_ROW + lane] = cmul_conj(v[q], tws[k1 * 32 + lane]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const float4 t4 = *reinterpret_cast<const float4 *>(&Tw[lane * F1K_ROW + 2 * q]);
-                v[2 * q] = make_float2(t4.x, t4.y);
-                v[2 * q + 1] = make_float2(t4.z, t4.w);
-            }
-            fft32_inv(v);
-            // ---- ofdm_cyclic_prefixer(rolloff 0) + multiply_const(tx_scale) + clipper, from the registers
             float2 *dst = out + base + (long long)o * D;
-#pragma unroll
-            for (int q = 0; q < 32; q++) {
-                const int t = lane + 32 * brev5(q);
-                float2 w = make_float2(v[q].x * sc, v[q].y * sc);
-                if (clip > 0.f) {
-                    w.x = w.x < -clip ? -clip : (w.x > clip ? clip : w.x);
-                    w.y = w.y < -clip ? -clip : (w.y > clip ? clip : w.y);
-                }
-                dst[cp + t] = w;
-                if (t >= N - cp) dst[t - (N - cp)] = w;
-            }
+            tx_ifft_store<NFFT>(v, Tw, tws, ltw, dst, cp, sc, clip, lane);
         }
     }
 }
 
 static inline size_t tx1024w_pb_bytes(int max_pkt_bytes) { return ((size_t)max_pkt_bytes + 8 + 15) & ~(size_t)15; }
-static inline size_t tx1024w_smem_bytes(int max_pkt_bytes, int warps)
+static inline size_t txw_smem_bytes(int nfft, int max_pkt_bytes, int warps)
 {
-    return (size_t)(1024 * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 1024 * 2 + 1024) + (size_t)warps * ((size_t)F1K_SLOT * 8 + tx1024w_pb_bytes(max_pkt_bytes));
+    const size_t tslot = (nfft == 1024) ? (size_t)F1K_SLOT : (size_t)nfft;
+    return (size_t)(nfft * 8 + 64 * 8 + 256 * 4 + 32 * 4 + nfft * 2 + nfft) + (size_t)warps * (tslot * 8 + tx1024w_pb_bytes(max_pkt_bytes));
 }

@@ -449,7 +449,7 @@ def test_tx_warp_kernel_ragged(monkeypatch, bps, crc, scr, clip):
         assert e < 1e-5, "frame %d (len %d): relative error %.3g" % (i, lens[i], e)
     if clip:
         assert np.abs(s.real).max() <= np.float32(clip) and (np.abs(s.real) == np.float32(clip)).sum() > 100
-    assert "tx_frame1024w_kernel" in _kernels_used(phy, lambda: phy.tx(pk))
+    assert "tx_framew_kernel" in _kernels_used(phy, lambda: phy.tx(pk))
     monkeypatch.setenv("OFDMX_NO_WARP_TX", "1")
     gen = cm.make_phy(cfg, tx_clip=clip)
     g, goff = gen.tx(pk, first_pkt_num=4090)
@@ -501,3 +501,34 @@ def test_warp_frame_kernel_small_fft(which, bps, int_off):
     assert np.array_equal(r2.frames, res.frames)
     assert res.payloads() == pk
     assert np.all(res.frames["carr_offset"] == int_off)
+
+
+@pytest.mark.parametrize("which,bps", [("c1", 1), ("c1", 2), ("c1", 3), ("c1", 4), ("c1", 6),
+                                       ("radio128", 1), ("radio128", 2), ("radio128", 3), ("radio128", 4), ("radio128", 6)])
+def test_tx_warp_kernel_small_fft(monkeypatch, which, bps):
+    """Warp-per-packet TX kernel at fft_len 64 and 128 (register FFT + lane-shuffle FFT on conjugated data): every
+    payload modulation, ragged packet lengths, against the oracle and the generic TX kernel; then decoded by the
+    receiver."""
+    cfg = cm.cfg_c1(bps, True, 1) if which == "c1" else cm.cfg_radio128(bps, 1, 1)
+    cfg["tx_scale"] = 0.01
+    rng = np.random.default_rng(300 + bps + len(which))
+    lens = [1, 2, 3, 4, 5, 11, 12, 13, 47, 48, 49, 96, 100, 255, 256, 350, 351, 1000]
+    pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    ref, roff = cm.make_oracle(cfg).tx(pk, first_pkt_num=7)
+    phy = cm.make_phy(cfg)
+    s, soff = phy.tx(pk, first_pkt_num=7)
+    s = s.cpu().numpy()
+    assert "tx_framew_kernel" in _kernels_used(phy, lambda: phy.tx(pk))
+    assert np.array_equal(soff.cpu().numpy(), roff)
+    for i in range(len(pk)):
+        a, b = s[roff[i]:roff[i + 1]], ref[roff[i]:roff[i + 1]]
+        e = np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert e < 1e-5, "frame %d (len %d): relative error %.3g" % (i, lens[i], e)
+    monkeypatch.setenv("OFDMX_NO_WARP_TX", "1")
+    gen = cm.make_phy(cfg)
+    g, goff = gen.tx(pk, first_pkt_num=7)
+    assert "tx_frame_kernel" in _kernels_used(gen, lambda: gen.tx(pk))
+    assert np.linalg.norm(g.cpu().numpy() - s) / np.linalg.norm(s) < 1e-5
+    x = cm.channel(cm.split_frames(s, roff), rng, gaps=(0, 200), lead=400, tail=1500, snr_db=60.0, fft_len=cfg["fft_len"],
+                   scale=100.0)
+    assert cm.make_phy(cfg).rx(_to_dev(x), want_z=False).payloads() == pk

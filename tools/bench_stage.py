@@ -37,14 +37,15 @@ import numpy as np  # noqa: E402
 
 def stage_tx(args, torch, cm, dev, peak):
     import oracle as O
-    cfg = cm.cfg_c3()
+    plen = {"c3": 1500, "c1": 96, "radio128": 350}[args.plan]
+    cfg = {"c3": cm.cfg_c3, "c1": lambda: cm.cfg_c1(2, False, 0), "radio128": lambda: cm.cfg_radio128(4, 1, 1)}[args.plan]()
     cfg["tx_scale"] = 0.01
-    phy = cm.make_phy(cfg, max_pkt_bytes=1504)
+    phy = cm.make_phy(cfg, max_pkt_bytes=plen + 4)
     rng = np.random.default_rng(3)
     nf = args.frames
-    payload = torch.from_numpy(rng.integers(0, 256, nf * 1500, dtype=np.uint8)).to(dev)
-    off = torch.arange(nf + 1, dtype=torch.int64, device=dev) * 1500
-    out = torch.empty(nf * int(phy.frame_samples(1500)), dtype=torch.complex64, device=dev)
+    payload = torch.from_numpy(rng.integers(0, 256, nf * plen, dtype=np.uint8)).to(dev)
+    off = torch.arange(nf + 1, dtype=torch.int64, device=dev) * plen
+    out = torch.empty(nf * int(phy.frame_samples(plen)), dtype=torch.complex64, device=dev)
     soff = torch.zeros(nf + 1, dtype=torch.int64, device=dev)
     for _ in range(args.warmup):
         s, soff = phy.tx((payload, off), out=out, soff=soff)
@@ -61,7 +62,7 @@ def stage_tx(args, torch, cm, dev, peak):
     n = int(soff[-1])
     # parity gate on the first packets + CPU baseline on a bounded sample
     k = min(256, nf)
-    pk = [bytes(payload[i * 1500:(i + 1) * 1500].cpu().numpy()) for i in range(k)]
+    pk = [bytes(payload[i * plen:(i + 1) * plen].cpu().numpy()) for i in range(k)]
     orc = O.Oracle(**cfg)
     t0 = time.perf_counter()
     ref, roff = orc.tx(pk)
@@ -71,11 +72,11 @@ def stage_tx(args, torch, cm, dev, peak):
     assert err < 1e-5, "TX differs from the oracle: %g" % err
     kern_ms = {kk: v[0] / v[1] * (v[1] / args.steps) for kk, v in prof.items()}
     dom = max(kern_ms, key=kern_ms.get)
-    ach = (nf * 1500.0 + 8.0 * n) / (kern_ms[dom] * 1e-3) / 1e9
+    ach = (nf * float(plen) + 8.0 * n) / (kern_ms[dom] * 1e-3) / 1e9
     print(json.dumps({
-        "stage": "tx", "metric": "OFDM TX Msamples/s (fft_len=1024, 16-QAM)", "value": n / (ms * 1e-3) / 1e6,
+        "stage": "tx", "metric": "OFDM TX Msamples/s (fft_len=%d)" % phy.fft_len, "value": n / (ms * 1e-3) / 1e6,
         "unit": "Msamples/s", "ms_per_step": ms, "steps": args.steps,
-        "config": {"workload": "%d packets of 1500 bytes -> %d samples, resident in HBM, output pre-allocated (enqueue-only calls)" % (nf, n)},
+        "config": {"workload": "plan %s: %d packets of %d bytes -> %d samples, resident in HBM, output pre-allocated (enqueue-only calls)" % (args.plan, nf, plen, n)},
         "kernels_ms_per_step": kern_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
         "parity": {"rel_l2_vs_oracle": err, "packets": k},
@@ -153,6 +154,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", default="agc2", choices=["agc2", "tx", "rx_small"])
     ap.add_argument("--frames", type=int, default=65536)
+    ap.add_argument("--plan", default="c3", choices=["c3", "c1", "radio128"], help="tx stage: carrier plan (c3 = BASELINE config[2])")
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--samples", type=int, default=64 * 880)
     ap.add_argument("--steps", type=int, default=10)

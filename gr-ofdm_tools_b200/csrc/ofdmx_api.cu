@@ -734,16 +734,17 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             while (c->frame1kw_warps > 4 && framew_smem_bytes(N, kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0, c->frame1kw_dec_all) > 227 * 1024)
                 c->frame1kw_warps--;
             c->frame1kw_smem = framew_smem_bytes(N, kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0, c->frame1kw_dec_all);
-            // warp-per-frame kernel: fft_len 1024 (register FFT 32x32, <= 4 carrier-offset candidates) and
-            // fft_len 64 / 128 (register FFT + lane-shuffle FFT, any number of candidates)
-            c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128) && simple && kp.bps_h == 1 && c->hl >= 32 && c->hl <= 1024
+            // warp-per-frame kernel: fft_len 1024 (register FFT 32x32, <= 4 carrier-offset candidates), fft_len 2048 (two
+            // interleaved 1024-point transforms) and fft_len 64 / 128 (register FFT + lane-shuffle FFT)
+            c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128 || N == 2048) && simple && kp.bps_h == 1
+                          && c->hl >= 32 && c->hl <= 2048
                           && c->frame1kw_smem <= 227 * 1024;
             if (c->frame1kw) {
                 cudaError_t e1 = cudaSuccess;
                 int occ = 1;
 #define FW_ATTR1(NN, B, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_framew_kernel<NN, B, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1kw_smem); if (e2 != cudaSuccess) e1 = e2; \
                              if (!Z) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rx_framew_kernel<NN, B, Z>, c->frame1kw_warps * 32, c->frame1kw_smem); }
-#define FW_ATTR(B, Z) { if (N == 1024) FW_ATTR1(1024, B, Z) else if (N == 128) FW_ATTR1(128, B, Z) else FW_ATTR1(64, B, Z) }
+#define FW_ATTR(B, Z) { if (N == 1024) FW_ATTR1(1024, B, Z) else if (N == 2048) FW_ATTR1(2048, B, Z) else if (N == 128) FW_ATTR1(128, B, Z) else FW_ATTR1(64, B, Z) }
                 switch (kp.bps_p) {
                 case 1: FW_ATTR(1, false) FW_ATTR(1, true) break;
                 case 2: FW_ATTR(2, false) FW_ATTR(2, true) break;
@@ -922,7 +923,7 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
 #define FW_LAUNCH(B)                                                                                               \
     do {                                                                                                           \
         const unsigned fwgrid = (unsigned)(c->sm_count * c->frame1kw_ctas);                                                        \
-        if (c->kp.N == 1024) FW_GO(1024, B) else if (c->kp.N == 128) FW_GO(128, B) else FW_GO(64, B)                                \
+        if (c->kp.N == 1024) FW_GO(1024, B) else if (c->kp.N == 2048) FW_GO(2048, B) else if (c->kp.N == 128) FW_GO(128, B) else FW_GO(64, B)                                \
     } while (0)
         switch (c->kp.bps_p) {
         case 1: FW_LAUNCH(1); break;

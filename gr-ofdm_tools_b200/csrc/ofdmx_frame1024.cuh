@@ -120,6 +120,70 @@ __device__ __forceinline__ void f1k_symbol(const KP &p, const float2 *__restrict
     for (int q = 0; q < 32; q++) Tw[lane + 32 * brev5(q)] = v[q];
 }
 
+// fft_len 2048 as two interleaved 1024-point transforms (decimation in time): the even samples of the symbol go
+// through the same 32x32 register FFT into Ta, the odd samples into Tb; a bin is read back as
+//     X[k] = Ta[k mod 1024] + W_2048^k Tb[k mod 1024]
+// by the equaliser (rx_framew_kernel's bin accessor), so the combined spectrum is never materialised.
+// st = phasor of 64 samples of NCO advance (the recurrence step between a lane's consecutive inputs).
+__device__ __forceinline__ void f2k_symbol(const KP &p, const float2 *__restrict__ r, long long n, long long i0,
+                                           long long t, double kappa, float2 st, bool slow, int j, int jend,
+                                           const long long *__restrict__ trig, const float *__restrict__ cfo,
+                                           float2 *__restrict__ Ta, float2 *__restrict__ Tb,
+                                           const float2 *__restrict__ tws, int lane)
+{
+    const long long tnx = (slow && j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        float2 *Tw = half ? Tb : Ta;
+        float2 v[32];
+        const long long sbase = i0 - p.D + 2 * lane + half;      // stream index of this lane's first sample
+#pragma unroll
+        for (int a = 0; a < 32; a++) {
+            const long long s = sbase + 64 * a;
+            v[a] = (s >= 0 && s < n) ? __ldg(&r[s]) : make_float2(0.f, 0.f);
+        }
+        {
+            double tb = kappa * (double)(i0 + 2 * lane + half - t + 1);
+            tb -= rint(tb);
+            float sn, cs;
+            sincospif(2.0f * (float)tb, &sn, &cs);
+            float2 ph = make_float2(cs, sn);
+#pragma unroll
+            for (int a = 0; a < 32; a++) {
+                const long long i = i0 + 2 * lane + half + 64 * a;
+                float2 pa = ph;
+                if (i >= tnx) {      // sample-and-hold value changed inside the frame: exact piecewise phase
+                    double turns = nco_turns(i, j, jend, trig, cfo, 2048);
+                    turns -= rint(turns);
+                    float s2, c2;
+                    sincospif(2.0f * (float)turns, &s2, &c2);
+                    pa = make_float2(c2, s2);
+                }
+                v[a] = cmul(v[a], pa);
+                ph = cmul(ph, st);
+            }
+        }
+        fft32_fwd(v);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+            const int k1 = brev5(q);
+            Tw[k1 * F1K_ROW + lane] = cmul(v[q], tws[k1 * 32 + lane]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(&Tw[lane * F1K_ROW + 2 * q]);
+            v[2 * q] = make_float2(t4.x, t4.y);
+            v[2 * q + 1] = make_float2(t4.z, t4.w);
+        }
+        __syncwarp();
+        fft32_fwd(v);
+#pragma unroll
+        for (int q = 0; q < 32; q++) Tw[lane + 32 * brev5(q)] = v[q];
+    }
+}
+
 // decision_maker with the modulation known at compile time
 template <int BPS>
 __device__ __forceinline__ int f1k_decide(float re, float im, const uint8_t *__restrict__ lut)

@@ -140,7 +140,7 @@ __device__ __forceinline__ void fw_flush(volatile FwState *fs, ofdmx_frame *dst,
 }
 
 template <int NFFT, int BPS_P, bool WANT_Z>
-__global__ void __launch_bounds__(FW_THREADS, NFFT == 1024 ? 1 : 2)
+__global__ void __launch_bounds__(FW_THREADS, NFFT >= 1024 ? 1 : 2)
 rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
                      const long long *__restrict__ trig, const int *__restrict__ trig_stream,
                      const float *__restrict__ cfo, const int *__restrict__ stream_start,
@@ -153,36 +153,52 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
     const int nu = p.n_occ_u;
     const int hsz = (max(nu, p.y1_span) + 1) & ~1;              // H area also parks the Y1 bins chanest needs
     // ---- CTA-shared tables
-    float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [1024]
-    float2 *ipts = tws + NFFT;                                    // [64]
+    constexpr int TWN = NFFT;                                     // twiddle entries (fft_len 2048: 32x32 table + W_2048^k, k < 1024)
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw);           // [TWN]
+    float2 *ipts = tws + TWN;                                    // [64]
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [256] CRC-32 table
     uint32_t *s_pow = s_tab + 256;                                // [32]
     uint16_t *s_occ = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] union bin of carrier u
     uint16_t *s_pos = s_occ + ((nu + 7) & ~7);                    // [nu] position in the serialiser order
     uint8_t *lut = reinterpret_cast<uint8_t *>(s_pos + ((nu + 7) & ~7));   // [64]
     // ---- per-warp buffers
-    constexpr int YSLOT = (NFFT == 1024) ? F1K_SLOT : NFFT;      // float2 per symbol buffer
+    constexpr int YSLOT = (NFFT == 2048) ? 2 * F1K_SLOT : (NFFT == 1024) ? F1K_SLOT : NFFT;      // float2 per symbol buffer
     // fft_len 1024 keeps its steady-state code minimal: configurations whose bits per OFDM symbol are not a byte
     // multiple (dec_all > 0) go to the CTA-per-frame kernel there
     const int dec_all = (NFFT == 1024) ? 0 : dec_all_arg;
-    const size_t shared_bytes = (size_t)NFFT * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64;
+    const size_t shared_bytes = (size_t)TWN * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * (size_t)((nu + 7) & ~7) * 2 + 64;
     const size_t dec_bytes = (dec_off >= 0) ? 0 : (size_t)(((dec_all > 0 ? dec_all : nu) + 15) & ~15);
     const size_t per_warp = (size_t)YSLOT * 8 + (size_t)hsz * 8 + dec_bytes + 64 + sizeof(FwState);
     unsigned char *wbase = smem_raw + ((shared_bytes + 15) & ~(size_t)15) + (size_t)wid * per_warp;
     float2 *Y = reinterpret_cast<float2 *>(wbase);                // F1K_SLOT
-    float2 *Hs = Y + YSLOT;                                    // hsz
+    float2 *Hs = Y + YSLOT;
+    // FFT output bin in natural order (fft_len 2048: recombined from the even- and odd-sample transforms)
+    auto ybin = [&](int k) -> float2 {
+        if (NFFT == 2048) {
+            const int kk = k & 1023;
+            const float2 a = Y[kk], b = cmul(tws[1024 + kk], Y[F1K_SLOT + kk]);
+            return (k & 1024) ? make_float2(a.x - b.x, a.y - b.y) : make_float2(a.x + b.x, a.y + b.y);
+        }
+        return Y[k];
+    };                                    // hsz
     // decisions of the current symbol: in the guard band of the symbol buffer when the carrier plan leaves one
     // (bins no equaliser read touches; dead before the next FFT overwrites them), else in their own array
     uint8_t *dec = (dec_off >= 0) ? reinterpret_cast<uint8_t *>(Y + dec_off) : reinterpret_cast<uint8_t *>(Hs + hsz);
     uint8_t *hb = reinterpret_cast<uint8_t *>(Hs + hsz) + dec_bytes;   // 64 header items
     volatile FwState *fs = reinterpret_cast<volatile FwState *>(hb + 64);
 
-    for (int i = tid; i < NFFT; i += NTH) {
+    for (int i = tid; i < (NFFT == 2048 ? 1024 : NFFT); i += NTH) {
         const int k1 = i >> 5, b = i & 31;
         float sn, cs;
-        sincospif(-(float)(b * k1) * (2.0f / NFFT), &sn, &cs);
+        sincospif(-(float)(b * k1) * (2.0f / (NFFT == 2048 ? 1024 : NFFT)), &sn, &cs);
         tws[i] = make_float2(cs, sn);
     }
+    if (NFFT == 2048)
+        for (int i = tid; i < 1024; i += NTH) {      // W_2048^k for the even/odd recombination
+            float sn, cs;
+            sincospif(-(float)i * (1.0f / 1024.0f), &sn, &cs);
+            tws[1024 + i] = make_float2(cs, sn);
+        }
     for (int i = tid; i < nu; i += NTH) { s_occ[i] = (uint16_t)p.occ_u[i]; s_pos[i] = (uint16_t)p.pos_su[i]; }
     // (strided loops: the CTA may have fewer than 256 threads when the per-warp buffers are large)
     for (int i = tid; i < 256; i += NTH) s_tab[i] = p.crc_tab[i];
@@ -196,7 +212,8 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
     const int nt = *n_trig_dev;
     constexpr int N = NFFT, HALF = NFFT / 2;
     const int D = p.D;
-    const LaneTw ltw = lane_twiddles(lane);          // lane-FFT twiddles (fft_len < 1024 only)
+    LaneTw ltw = {};
+    if (NFFT < 1024) ltw = lane_twiddles(lane);      // lane-FFT twiddles
     const float al = p.alpha, oma = 1.0f - p.alpha;
     const int size0 = p.occ_size[0];
     const int sym_bytes = size0 * BPS_P / 8;
@@ -216,7 +233,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
             fs->rec.trigger = t; fs->rec.cfo = cf; fs->rec.stream = st; fs->rec.flags = 0; fs->rec.pkt_len = 0;
             fs->rec.pkt_num = 0; fs->rec.frame_syms = 0; fs->rec.carr_offset = 0; fs->rec.slot = (uint32_t)j;
             const double kap = (double)cf * (-2.0 / NFFT) * (1.0 / TWO_PI_D);
-            const float2 kst = f1k_step_phasor(kap);
+            const float2 kst = f1k_step_phasor(NFFT == 2048 ? 2.0 * kap : kap);
             fs->kappa = kap; fs->stx = kst.x; fs->sty = kst.y;
             fs->tnext = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
             fs->nsym = 3;
@@ -234,7 +251,9 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
         bool dead = false;
         for (int sidx = 0; sidx < fs->nsym; sidx++) {
             const long long i0 = t + (long long)sidx * D + p.cp;
-            if (NFFT == 1024) {
+            if constexpr (NFFT == 2048) {
+                f2k_symbol(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + 2047, j, jend, trig, cfo, Y, Y + F1K_SLOT, tws, lane);
+            } else if constexpr (NFFT == 1024) {
                 f1k_symbol(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + 1023, j, jend, trig, cfo, Y, tws, lane);
                 // pull the next symbol's 8 KB towards L2 while this one is processed
                 const long long sn = i0 + D - p.D + lane * 32;
@@ -243,13 +262,13 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(r + sn + 16));
                 }
             } else {
-                fsmall_symbol<(NFFT == 1024) ? 64 : NFFT>(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + NFFT - 1, j, jend,
-                                                         trig, cfo, Y, tws, lane, ltw);
+                fsmall_symbol<NFFT>(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + NFFT - 1, j, jend,
+                                    trig, cfo, Y, tws, lane, ltw);
             }
             __syncwarp();
             if (sidx == 0) {
                 // sync word 1: park the bins chanest needs in the (still unused) H area
-                for (int q = lane; q < p.y1_span; q += 32) Hs[q] = Y[(y1_lo + q) ^ HALF];
+                for (int q = lane; q < p.y1_span; q += 32) Hs[q] = ybin((y1_lo + q) ^ HALF);
             } else if (sidx == 1) {
                 // sync word 2: integer carrier offset (ofdm_chanest_vcvc), then the channel taps
                 float b = 0.f;
@@ -274,7 +293,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                             for (int gi = 0; gi < 4; gi++)
                                 if (g0 + gi < ng) {
                                     const int k = kc[w4] + p.gneg + 2 * (g0 + gi);
-                                    acc[gi] = cadd(acc[gi], cmul(cmul_conj(Y[k ^ HALF], Hs[k - y1_lo]), cvc[w4]));
+                                    acc[gi] = cadd(acc[gi], cmul(cmul_conj(ybin(k ^ HALF), Hs[k - y1_lo]), cvc[w4]));
                                 }
                         }
                     }
@@ -294,7 +313,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                     const int k = s_occ[u];
                     const int src = k + off;
                     float2 Hk = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) Hk = cmul(Y[src ^ HALF], p.inv_sw2[k]);
+                    if (src >= 0 && src < N) Hk = cmul(ybin(src ^ HALF), p.inv_sw2[k]);
                     Hs[u] = Hk;
                 }
             } else if (sidx == 2) {
@@ -310,7 +329,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                 for (int u = lane; u < nu; u += 32) {
                     const int src = (int)s_occ[u] + off;
                     float2 y = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) y = cmul(Y[src ^ HALF], pc);
+                    if (src >= 0 && src < N) y = cmul(ybin(src ^ HALF), pc);
                     float2 Hk = Hs[u];
                     const float hinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
                     const float2 hn = cmul_conj(y, Hk);
@@ -367,7 +386,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                     const int src = kc + off;
                     float2 y = make_float2(0.f, 0.f);
                     if (src >= 0 && src < N) {
-                        y = Y[src ^ HALF];
+                        y = ybin(src ^ HALF);
                         if (off != 0) y = cmul(y, pc);
                     }
                     float2 Hk = Hs[u];
@@ -481,7 +500,7 @@ static inline size_t framew_smem_bytes(int nfft, int n_occ_u, int y1_span, int w
 {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t nu8 = (size_t)((n_occ_u + 7) & ~7);
-    const size_t yslot = (nfft == 1024) ? (size_t)F1K_SLOT : (size_t)nfft;
+    const size_t yslot = (nfft == 2048) ? 2 * (size_t)F1K_SLOT : (nfft == 1024) ? (size_t)F1K_SLOT : (size_t)nfft;
     const size_t shared_bytes = (size_t)nfft * 8 + 64 * 8 + 256 * 4 + 32 * 4 + 2 * nu8 * 2 + 64;
     const size_t hsz = (size_t)((std::max(n_occ_u, y1_span) + 1) & ~1);
     const size_t per_warp = yslot * 8 + hsz * 8 + (dec_in_guard ? 0 : al16(dec_all > 0 ? dec_all : n_occ_u)) + 64 + sizeof(FwState);

@@ -532,3 +532,22 @@ def test_tx_warp_kernel_small_fft(monkeypatch, which, bps):
     x = cm.channel(cm.split_frames(s, roff), rng, gaps=(0, 200), lead=400, tail=1500, snr_db=60.0, fft_len=cfg["fft_len"],
                    scale=100.0)
     assert cm.make_phy(cfg).rx(_to_dev(x), want_z=False).payloads() == pk
+
+
+@pytest.mark.parametrize("bps,int_off", [(2, 0), (4, 2), (6, -2)])
+def test_warp_frame_kernel_fft2048(bps, int_off):
+    """Warp-per-frame receiver at fft_len 2048 (two interleaved 1024-point register transforms recombined in the bin
+    accessor): ragged lengths, integer carrier offsets, multipath; records, bytes and equalised symbols against the
+    oracle."""
+    cfg = cm.cfg_c4(bps_payload=bps)
+    rng = np.random.default_rng(2048 + bps)
+    lens = [1, 4, 5, 149, 150, 151, 899, 900, 901, 1500, 2999]
+    pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    s, off = cm.make_oracle(cfg).tx(pk)
+    stream = cm.channel(cm.split_frames(s, off), rng, gaps=(0, 700), lead=900, tail=5000, snr_db=50.0, cfo=0.25 + int_off,
+                        fft_len=2048, taps=cm.MULTIPATH)
+    res, ref = _compare_rx(cfg, stream)
+    phy = cm.make_phy(cfg)
+    assert "rx_framew_kernel" in _kernels_used(phy, lambda: phy.rx(_to_dev(stream)))
+    assert res.payloads() == pk
+    assert np.all(res.frames["carr_offset"] == int_off)

@@ -11,7 +11,7 @@ BASELINE config[2] packets (fft_len 1024, 16-QAM, 1500 bytes) resident in HBM; v
 roofline = (payload bytes read + 8 B per sample written) / time against the measured HBM peak, cpu_baseline = the
 oracle TX on all host cores over a bounded sample, parity gate against the oracle on the first packets.
 
-rx_small: the full RX chain on the small-fft configurations of BASELINE.json: configs[1] (fft_len 64, 802.11a carrier
+rx_small: the full RX chain on the other configurations of BASELINE.json (multi-stream, fft_len 64 / 128 / 2048): configs[1] (fft_len 64, 802.11a carrier
 plan of ofdm_tx_rx_hier, QPSK, 96-byte packets, 4096 independent streams x 64 frames) and the ofdm_radio_hier
 default plan (fft_len 128, 103 data carriers, 16-QAM, 350-byte packets + CRC-32, 1024 streams x 64 frames); one JSON
 line per configuration, parity gate = two streams against the oracle (records and bytes bit-exact).
@@ -88,7 +88,8 @@ def stage_tx(args, torch, cm, dev, peak):
 def stage_rx_small(args, torch, cm, dev, peak):
     import oracle as O
     cases = (("configs[1]: fft_len 64, QPSK, 96 B, 4096 streams x 64 frames", cm.cfg_c1(2, False, 0), 96, 4096, 64),
-             ("ofdm_radio_hier defaults: fft_len 128, 16-QAM, 350 B + CRC-32, 1024 streams x 64 frames", cm.cfg_radio128(4, 1, 1), 350, 1024, 64))
+             ("ofdm_radio_hier defaults: fft_len 128, 16-QAM, 350 B + CRC-32, 1024 streams x 64 frames", cm.cfg_radio128(4, 1, 1), 350, 1024, 64),
+             ("configs[3], one GPU's share: fft_len 2048, 64-QAM, 1500 B + CRC-32, 128 streams x 256 frames", cm.cfg_c4(), 1500, 128, 256))
     steps = min(args.steps, 5)
     for name, cfg, plen, n_streams, n_frames in cases:
         phy = cm.make_phy(cfg)

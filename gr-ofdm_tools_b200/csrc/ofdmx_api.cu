@@ -644,7 +644,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64) UP(crc_pow8, crc_pow8)
 #undef UP
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
-    if ((N == 1024 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
+    if ((N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
         && kp.bps_h == 1 && c->hl >= 32) {
         std::vector<uint16_t> tx_map((size_t)N, (uint16_t)TXW_EMPTY);
         for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
@@ -736,7 +736,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             c->frame1kw_smem = framew_smem_bytes(N, kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0, c->frame1kw_dec_all);
             // warp-per-frame kernel: fft_len 1024 (register FFT 32x32, <= 4 carrier-offset candidates), fft_len 2048 (two
             // interleaved 1024-point transforms) and fft_len 64 / 128 (register FFT + lane-shuffle FFT)
-            c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128 || N == 2048) && simple && kp.bps_h == 1
+            c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128 || N == 256 || N == 512 || N == 2048) && simple && kp.bps_h == 1
                           && c->hl >= 32 && c->hl <= 2048
                           && c->frame1kw_smem <= 227 * 1024;
             if (c->frame1kw) {
@@ -744,7 +744,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                 int occ = 1;
 #define FW_ATTR1(NN, B, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_framew_kernel<NN, B, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1kw_smem); if (e2 != cudaSuccess) e1 = e2; \
                              if (!Z) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rx_framew_kernel<NN, B, Z>, c->frame1kw_warps * 32, c->frame1kw_smem); }
-#define FW_ATTR(B, Z) { if (N == 1024) FW_ATTR1(1024, B, Z) else if (N == 2048) FW_ATTR1(2048, B, Z) else if (N == 128) FW_ATTR1(128, B, Z) else FW_ATTR1(64, B, Z) }
+#define FW_ATTR(B, Z) { if (N == 1024) FW_ATTR1(1024, B, Z) else if (N == 2048) FW_ATTR1(2048, B, Z) else if (N == 512) FW_ATTR1(512, B, Z) else if (N == 256) FW_ATTR1(256, B, Z) else if (N == 128) FW_ATTR1(128, B, Z) else FW_ATTR1(64, B, Z) }
                 switch (kp.bps_p) {
                 case 1: FW_ATTR(1, false) FW_ATTR(1, true) break;
                 case 2: FW_ATTR(2, false) FW_ATTR(2, true) break;
@@ -762,7 +762,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             c->tx1kw_smem = txw_smem_bytes(N, kp.max_pkt_bytes, TXW_WARPS);
             cudaError_t e1 = cudaSuccess;
 #define TXW_ATTR1(NN, B) { cudaError_t e2 = cudaFuncSetAttribute(tx_framew_kernel<NN, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
-#define TXW_ATTR(B) { if (N == 1024) TXW_ATTR1(1024, B) else if (N == 128) TXW_ATTR1(128, B) else TXW_ATTR1(64, B) }
+#define TXW_ATTR(B) { if (N == 1024) TXW_ATTR1(1024, B) else if (N == 512) TXW_ATTR1(512, B) else if (N == 256) TXW_ATTR1(256, B) else if (N == 128) TXW_ATTR1(128, B) else TXW_ATTR1(64, B) }
             switch (kp.bps_p) {
             case 1: TXW_ATTR(1) break;
             case 2: TXW_ATTR(2) break;
@@ -923,7 +923,8 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
 #define FW_LAUNCH(B)                                                                                               \
     do {                                                                                                           \
         const unsigned fwgrid = (unsigned)(c->sm_count * c->frame1kw_ctas);                                                        \
-        if (c->kp.N == 1024) FW_GO(1024, B) else if (c->kp.N == 2048) FW_GO(2048, B) else if (c->kp.N == 128) FW_GO(128, B) else FW_GO(64, B)                                \
+        if (c->kp.N == 1024) FW_GO(1024, B) else if (c->kp.N == 2048) FW_GO(2048, B) else if (c->kp.N == 512) FW_GO(512, B) else if (c->kp.N == 256) FW_GO(256, B)  \
+        else if (c->kp.N == 128) FW_GO(128, B) else FW_GO(64, B)                                \
     } while (0)
         switch (c->kp.bps_p) {
         case 1: FW_LAUNCH(1); break;
@@ -1017,7 +1018,7 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
         KT(K_TX1KW);
 #define TXW1(NN, B) tx_framew_kernel<NN, B><<<grid, TXW_WARPS * 32, c->tx1kw_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts, \
             first_pkt_num, (float2 *)samples_out, cap_samples, (const long long *)sample_off_dev, c->tx_map, c->sync_td, c->x_2048, pbb)
-#define TXW(B) { if (c->kp.N == 1024) TXW1(1024, B); else if (c->kp.N == 128) TXW1(128, B); else TXW1(64, B); }
+#define TXW(B) { if (c->kp.N == 1024) TXW1(1024, B); else if (c->kp.N == 512) TXW1(512, B); else if (c->kp.N == 256) TXW1(256, B); else if (c->kp.N == 128) TXW1(128, B); else TXW1(64, B); }
         switch (c->kp.bps_p) {
         case 1: TXW(1); break;
         case 2: TXW(2); break;

@@ -589,3 +589,33 @@ def test_sync_kernel_variants_small_fft(monkeypatch, which, n_streams, n):
         assert np.array_equal(trig, np.array(ref_t, np.int64)), name
         assert np.array_equal(st, np.array(ref_s)), name
         np.testing.assert_allclose(cfo, np.array(ref_c, np.float32), atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("n_fft,bps,int_off", [(256, 2, 0), (256, 4, 2), (512, 3, -2), (512, 6, 0)])
+def test_warp_kernels_fft256_512(monkeypatch, n_fft, bps, int_off):
+    """fft_len 256 and 512 on the carrier plans `spectrum_enforcer` derives (python/ofdm_cr_tools.py:348-378): the
+    warp-per-packet TX kernel against the oracle and the generic kernel, then the warp-per-frame receiver against the
+    oracle (records, bytes, equalised symbols), ragged lengths and integer carrier offsets."""
+    from ofdm_tools import ofdm_cr_tools as T
+    occ, pil, pls, sw1, sw2 = T.spectrum_enforcer(n_fft, [], 10)
+    cfg = dict(fft_len=n_fft, cp_len=n_fft // 4, occupied_carriers=[list(occ[0])], pilot_carriers=[list(pil[0])],
+               pilot_symbols=[list(pls[0])], sync_word1=[complex(v) for v in sw1], sync_word2=[complex(v) for v in sw2],
+               bps_header=1, bps_payload=bps, scramble_bits=True, scramble_header=True, crc_mode=1, max_carr_offset=3,
+               tx_scale=0.01)
+    rng = np.random.default_rng(n_fft + bps)
+    lens = [1, 3, 4, 5, 63, 64, 65, 200, 511, 512, 513, 1000]
+    pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    orc = cm.make_oracle(cfg)
+    ref, roff = orc.tx(pk)
+    phy = cm.make_phy(cfg)
+    s, soff = phy.tx(pk)
+    s = s.cpu().numpy()
+    assert "tx_framew_kernel" in _kernels_used(phy, lambda: phy.tx(pk))
+    assert np.array_equal(soff.cpu().numpy(), roff)
+    assert np.linalg.norm(s - ref) / np.linalg.norm(ref) < 1e-5
+    stream = cm.channel(cm.split_frames(ref, roff), rng, gaps=(0, 500), lead=400, tail=3000, snr_db=45.0, cfo=0.2 + int_off,
+                        fft_len=n_fft, scale=100.0)
+    res, rr = _compare_rx(cfg, stream)
+    assert "rx_framew_kernel" in _kernels_used(phy, lambda: phy.rx(_to_dev(stream)))
+    assert res.payloads() == pk
+    assert np.all(res.frames["carr_offset"] == int_off)

@@ -33,12 +33,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "sync_metric_kernel", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -1084,6 +1084,88 @@ int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_stre
     ofdmx_ctx *ctx_ = c;
     { KT(K_AGC2); agc2_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
                                                       attack, decay, reference, max_gain, gain_io_dev); }
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+int64_t ofdmx_iir_state_doubles(void) { return 4 * (IIR_MAXT - 1); }
+
+int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
+                  const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb, int64_t span,
+                  double *state_io_dev, void *stream)
+{
+    if (!c || !in_dev || !out_dev || !state_io_dev || !fftaps || n_streams < 0 || n < 0 || stride < n ||
+        n_streams > (1 << 24) || n_ff < 1 || n_ff > IIR_MAXT || n_fb < 0 || n_fb > IIR_MAXT || (n_fb > 0 && !fbtaps))
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_iir_ccd arguments (at most 9 feed-forward and 9 feedback taps)");
+    if (n_streams == 0 || n == 0) return OFDMX_OK;
+    if (int rc = check_device(c)) return rc;
+    iir_taps t;
+    for (int i = 0; i < IIR_MAXT; i++) {
+        t.ff[i] = i < n_ff ? fftaps[i] : 0.0;
+        t.fb[i] = (i >= 1 && i < n_fb) ? -fbtaps[i] : 0.0;   // oldstyle=False: a[k] enter with a minus sign
+    }
+    // warm-up length: where the impulse response has decayed below 1e-18 of its peak (host, double)
+    int64_t warm = 0;
+    {
+        double x[IIR_MAXT - 1] = { 0 }, y[IIR_MAXT - 1] = { 0 }, peak = 0.0;
+        const int64_t cap = 1 << 20;
+        int64_t last = 0;
+        for (int64_t k = 0; k < cap; k++) {
+            const double in = k == 0 ? 1.0 : 0.0;
+            double acc = t.ff[0] * in;
+            for (int i = 1; i < IIR_MAXT; i++) acc += t.ff[i] * x[i - 1];
+            for (int i = 1; i < IIR_MAXT; i++) acc += t.fb[i] * y[i - 1];
+            for (int i = IIR_MAXT - 2; i > 0; i--) { x[i] = x[i - 1]; y[i] = y[i - 1]; }
+            x[0] = in; y[0] = acc;
+            const double a = std::fabs(acc);
+            if (!(a < 1e300)) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: unstable filter");
+            if (a > peak) peak = a;
+            if (a > 1e-18 * peak) last = k;
+            if (k - last > 64) break;
+        }
+        if (last >= cap - 65) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: impulse response does not decay");
+        warm = last + 1 + (IIR_MAXT - 1);
+    }
+    // span: caller's choice, else one full wave of lanes (12 resident warps per SM; the recurrence is a chain of
+    // dependent double additions ~350 cycles per sample long, so more lanes is the only way to go faster until
+    // the FP64 pipe is full), in several waves once a span would exceed 16 warm-up lengths
+    if (span <= 0) {
+        const int64_t capacity = (int64_t)c->sm_count * 12 * 32;
+        int64_t sps = std::max<int64_t>(1, capacity / n_streams);
+        span = (n + sps - 1) / sps;
+        if (span > 16 * warm) {
+            sps *= (span + 16 * warm - 1) / (16 * warm);
+            span = (n + sps - 1) / sps;
+        }
+        span = std::max<int64_t>((span + 31) / 32 * 32, 1024);
+    }
+    if (out_dev == in_dev && span < n) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: in-place needs span >= n");
+    span = std::min<int64_t>(span, std::max<int64_t>(n, 1));
+    if (span + warm >= (1ll << 31)) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: span too long (2^31 samples with the warm-up)");
+    const int64_t sps = (n + span - 1) / span;
+    if (sps > (1 << 30)) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: too many spans");
+    const int64_t lanes = n_streams * sps;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((lanes + 32 * IIR_WARPS - 1) / (32 * IIR_WARPS));
+    ofdmx_ctx *ctx_ = c;
+    { KT(K_IIR); iir_ccd_kernel<<<grid, IIR_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
+                                                        (int)sps, span, warm, t, state_io_dev); }
+    CUDA_TRY(c, cudaGetLastError());
+    return OFDMX_OK;
+}
+
+int ofdmx_papr(ofdmx_ctx *c, const float *in_dev, int64_t n, float *out3_dev, void *stream)
+{
+    if (!c || !in_dev || !out3_dev || n <= 0) return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_papr arguments");
+    if (int rc = check_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int parts = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+    if (int rc = grow(c, c->ws, (size_t)parts * 16)) return rc;
+    double *ps = (double *)c->ws.p;
+    float *pp = (float *)(ps + parts);
+    ofdmx_ctx *ctx_ = c;
+    { KT(K_PAPR); papr_kernel<<<parts, 256, 0, st>>>((const float2 *)in_dev, n, ps, pp); }
+    papr_final_kernel<<<1, 32, 0, st>>>(ps, pp, parts, n, out3_dev);
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }

@@ -63,3 +63,173 @@ agc2_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n
     }
     if (lane < ns) gain_io[s0 + lane] = g;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False): the out-of-band TX filter of ofdm_radio_hier
+// (python/ofdm_radio_hier.py:83-84,93,232-237; python/sync_radio_hier.py:73,165) -- SURVEY.md 8(f) rank 2.
+// [UPSTREAM gr-filter iir_filter<gr_complex, gr_complex, double, gr_complexd>::filter]:
+//     acc  = ff[0]*x[n];  acc += ff[i]*x[n-i] (i = 1..);  acc += (-fb[j])*y[n-j] (j = 1..);  y[n] = acc
+// accumulated in complex double (real taps: the two components are independent real recurrences), output
+// rounded to complex float.  A linear recurrence, so unlike the AGC it CAN be cut in time: a lane that starts
+// from a zero state `warm` samples before its span reproduces the sequential result up to the impulse
+// response left after `warm` samples; the host picks `warm` where that tail is below 1e-18 of its peak, i.e.
+// below the rounding of the double accumulator.  Lane (s, c) owns span c of `span` samples of stream s, runs
+// the recurrence from max(0, c*span - warm) (from the carried state when that is sample 0) and stores only its
+// own span.  The first span of a stream is therefore bit-exact against the sequential filter; the others
+// agree to the round-off noise floor of the direct-form recurrence itself (the reference taps cluster eight
+// poles at radius <= 0.985 next to z = -1: ~1e-10 relative in the double accumulator, measured: every float
+// within one ulp, 99.4 % identical).  Same 32 x 32 shared-memory
+// transpose as the AGC: rows are lanes, coalesced 256-byte row segments on the global side.
+// state_io[n_streams][4*(IIR_MAXT-1)] doubles: x[n-1..n-8] (re,im) then y[n-1..n-8] (re,im).
+#define IIR_MAXT 9
+#define IIR_WARPS 2
+struct iir_taps { double ff[IIR_MAXT]; double fb[IIR_MAXT]; };  // fb already negated, fb[0] unused; zero padded
+
+// Tiles travel global -> shared with 8-byte cp.async (no staging registers: the 32 history doubles and the
+// accumulators fill the register file), double buffered so the next tile is in flight while the recurrence
+// walks the current one.
+__global__ void __launch_bounds__(IIR_WARPS * 32)
+iir_ccd_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, long long stride, int n_streams,
+               int spans_per_stream, long long span, long long warm, const iir_taps taps,
+               double *__restrict__ state_io)
+{
+    __shared__ float2 tile[IIR_WARPS][2][32][33];
+    __shared__ long long row_off[IIR_WARPS][32];      // element offset of the first sample a row filters
+    __shared__ int row_len[IIR_WARPS][32], row_skip[IIR_WARPS][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)n_streams * spans_per_stream;
+    const long long l0 = ((long long)blockIdx.x * IIR_WARPS + w) * 32;
+    if (l0 >= total) return;
+    const int nl = (int)min((long long)32, total - l0);
+    const long long me = l0 + min(lane, nl - 1);
+    const int ms = (int)(me / spans_per_stream);
+    const int mc = (int)(me - (long long)ms * spans_per_stream);
+    const long long own0 = (long long)mc * span;                 // first sample I store
+    const long long beg = max((long long)0, own0 - warm);        // first sample I filter
+    const long long end = min(n, own0 + span);                   // one past my last sample
+    const int len = (int)(end - beg);
+    row_off[w][lane] = (long long)ms * stride + beg;
+    row_len[w][lane] = lane < nl ? len : 0;
+    row_skip[w][lane] = (int)(own0 - beg);
+    double xr[IIR_MAXT - 1], xi[IIR_MAXT - 1], yr[IIR_MAXT - 1], yi[IIR_MAXT - 1];
+#pragma unroll
+    for (int k = 0; k < IIR_MAXT - 1; k++) { xr[k] = xi[k] = yr[k] = yi[k] = 0.0; }
+    if (beg == 0) {
+        const double *st = state_io + (long long)ms * (4 * (IIR_MAXT - 1));
+#pragma unroll
+        for (int k = 0; k < IIR_MAXT - 1; k++) {
+            xr[k] = st[2 * k]; xi[k] = st[2 * k + 1];
+            yr[k] = st[2 * (IIR_MAXT - 1) + 2 * k]; yi[k] = st[2 * (IIR_MAXT - 1) + 2 * k + 1];
+        }
+    }
+    int maxlen = lane < nl ? len : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    __syncwarp();
+    const uint32_t tile0 = (uint32_t)__cvta_generic_to_shared(&tile[w][0][0][0]);
+    auto fill = [&](int buf, int i0) {
+        if (i0 < maxlen) {
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                if (i0 + lane < row_len[w][r])
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile0 + (uint32_t)(((buf * 32 + r) * 33 + lane) * 8)),
+                                 "l"(in + row_off[w][r] + i0 + lane) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fill(0, 0);
+    for (int i0 = 0, buf = 0; i0 < maxlen; i0 += 32, buf ^= 1) {
+        fill(buf ^ 1, i0 + 32);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const int nc = max(0, min(32, row_len[w][lane] - i0));
+#pragma unroll 8
+        for (int k = 0; k < nc; k++) {
+            const float2 x = tile[w][buf][lane][k];
+            const double dx = (double)x.x, dy = (double)x.y;
+            double ar = __dmul_rn(taps.ff[0], dx), ai = __dmul_rn(taps.ff[0], dy);
+#pragma unroll
+            for (int t = 1; t < IIR_MAXT; t++) {
+                ar = __dadd_rn(ar, __dmul_rn(taps.ff[t], xr[t - 1]));
+                ai = __dadd_rn(ai, __dmul_rn(taps.ff[t], xi[t - 1]));
+            }
+#pragma unroll
+            for (int t = 1; t < IIR_MAXT; t++) {
+                ar = __dadd_rn(ar, __dmul_rn(taps.fb[t], yr[t - 1]));
+                ai = __dadd_rn(ai, __dmul_rn(taps.fb[t], yi[t - 1]));
+            }
+#pragma unroll
+            for (int t = IIR_MAXT - 2; t > 0; t--) {
+                xr[t] = xr[t - 1]; xi[t] = xi[t - 1]; yr[t] = yr[t - 1]; yi[t] = yi[t - 1];
+            }
+            xr[0] = dx; xi[0] = dy; yr[0] = ar; yi[0] = ai;
+            tile[w][buf][lane][k] = make_float2((float)ar, (float)ai);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            if (i0 + lane < row_len[w][r] && i0 + lane >= row_skip[w][r])
+                __stcs(out + row_off[w][r] + i0 + lane, tile[w][buf][r][lane]);
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // the lane that filtered the last sample of a stream leaves the history for the next call
+    if (lane < nl && end == n) {
+        double *st = state_io + (long long)ms * (4 * (IIR_MAXT - 1));
+#pragma unroll
+        for (int k = 0; k < IIR_MAXT - 1; k++) {
+            st[2 * k] = xr[k]; st[2 * k + 1] = xi[k];
+            st[2 * (IIR_MAXT - 1) + 2 * k] = yr[k]; st[2 * (IIR_MAXT - 1) + 2 * k + 1] = yi[k];
+        }
+    }
+}
+
+// PAPR probe of python/papr_sink.py:46-50: peak |x|^2 and sum |x|^2 of a block.
+// One partial {sum (double), peak (float)} per CTA; the host wrapper divides.  Grid-stride float4 loads.
+__global__ void __launch_bounds__(256)
+papr_kernel(const float2 *__restrict__ in, long long n, double *__restrict__ part_sum, float *__restrict__ part_peak)
+{
+    double s = 0.0;
+    float pk = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = __ldcs(in + i);
+        const float p = v.x * v.x + v.y * v.y;
+        s += (double)p;
+        pk = fmaxf(pk, p);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+    }
+    __shared__ double ss[8];
+    __shared__ float sp[8];
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sp[threadIdx.x >> 5] = pk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) { s += ss[k]; pk = fmaxf(pk, sp[k]); }
+        part_sum[blockIdx.x] = s;
+        part_peak[blockIdx.x] = pk;
+    }
+}
+
+// out[0] = peak / (sum / n) (the value papr_sink.level() returns), out[1] = peak, out[2] = mean square
+__global__ void __launch_bounds__(32)
+papr_final_kernel(const double *__restrict__ part_sum, const float *__restrict__ part_peak, int n_parts, long long n,
+                  float *__restrict__ out)
+{
+    double s = 0.0;
+    float pk = 0.f;
+    for (int i = threadIdx.x; i < n_parts; i += 32) { s += part_sum[i]; pk = fmaxf(pk, part_peak[i]); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+    }
+    if (threadIdx.x == 0) {
+        const double ms = s / (double)n;
+        out[0] = (float)((double)pk / ms);
+        out[1] = pk;
+        out[2] = (float)ms;
+    }
+}

@@ -3,7 +3,7 @@
 Mirrors the export names of the reference package for the hot path only
 (python/__init__.py:49-84 of the reference): ofdm_tx_rx_hier, ofdm_radio_hier,
 ofdm_txrx_modules.{ofdm_tx, ofdm_rx}, payload_source, payload_sink, and the next rows of SURVEY.md 8(f):
-clipper, payload_source_pdu, payload_sink_pdu, ofdm_cr_tools.{make_packet, unmake_packet}, crc (the MAC-level
+clipper, papr_sink, payload_source_pdu, payload_sink_pdu, ofdm_cr_tools.{make_packet, unmake_packet}, crc (the MAC-level
 CRC-32 of gnuradio.digital.crc).
 """
 from .phy import OfdmPhy, RxResult, FRAME_DTYPE  # noqa: F401
@@ -17,4 +17,5 @@ from . import ofdm_cr_tools  # noqa: F401
 from .payload_source_pdu import payload_source_pdu  # noqa: F401
 from .payload_sink_pdu import payload_sink_pdu  # noqa: F401
 from .clipper import clipper  # noqa: F401
+from .papr_sink import papr_sink  # noqa: F401
 from . import crc  # noqa: F401

@@ -57,6 +57,9 @@ SYMBOLS = {
     "ofdmx_fft": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P]),
     "ofdmx_crc32": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
     "ofdmx_agc2": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "ofdmx_iir_state_doubles": (_I64, []),
+    "ofdmx_iir_ccd": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P, _I32, _I64, _P, _P]),
+    "ofdmx_papr": (C.c_int, [_P, _P, _I64, _P, _P]),
 }
 
 _lib = None

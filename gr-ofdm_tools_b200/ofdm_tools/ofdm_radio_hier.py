@@ -12,8 +12,9 @@ crc32_bb on both paths), clipper_mode (ofdm_tools.clipper(clipping_factor) after
 max gain 65536, :180-181) runs in front of the receiver as in the reference; its loop gain is carried from
 one rx() call to the next.  It is a per-sample non-linear recurrence: streams are processed in parallel,
 the samples of one stream sequentially, so pass agc=False to rx() for long single streams whose level is
-already normalised.  filter_mode (8th-order iir_filter_ccd out-of-band filter) is
-not built: the flag is stored and the TX output is the unfiltered signal.
+already normalised.  filter_mode=1 (the default) runs the TX burst stream through the 8th-order
+iir_filter_ccd(forward_OOB, feedback_OOB) out-of-band filter (:83-84,:93,:232-237) on the GPU
+(OfdmPhy.iir_ccd -> ofdmx_iir_ccd), its history carried across tx() calls; filter_mode=0 bypasses it.
 """
 from .phy import OfdmPhy
 
@@ -67,14 +68,26 @@ class ofdm_radio_hier(object):
                            scramble_bits=bool(scramble_mode), scramble_header=True, crc_mode=int(crc_mode),
                            max_carr_offset=3, tx_scale=0.01,
                            tx_clip=float(clipping_factor) if int(clipper_mode) else 0.0, **phy_kwargs)
+        # python/ofdm_radio_hier.py:83-84: taps of the 8th-order out-of-band filter (iir_filter_ccd, :93)
+        self.forward_OOB = [0.40789374966665903, 3.2351160543115207, 11.253435139165413, 22.423991613997735,
+                            27.99555756436666, 22.423991613997735, 11.253435139165425, 3.235116054311531,
+                            0.40789374966666014]
+        self.feedback_OOB = [1.0, 6.170110168740749, 16.888669609673336, 26.73762881119027, 26.75444043101795,
+                             17.322358010203928, 7.091659316015212, 1.682084643429639, 0.17795354282083842]
         self._pkt_num = 0
         self._agc_gain = None
+        self._iir_state = None
 
     # port 0 (bytes) in -> port 1 (samples) out
     def tx(self, packets):
-        out = self.phy.tx(packets, first_pkt_num=self._pkt_num)
+        """-> (samples, sample offsets).  With filter_mode=1 (the reference default, :39) the burst stream runs
+        through iir_filter_ccd(forward_OOB, feedback_OOB) (:93,:232-237); the filter history is carried from
+        call to call like the GNU Radio block carries it from burst to burst."""
+        out, soff = self.phy.tx(packets, first_pkt_num=self._pkt_num)
         self._pkt_num = (self._pkt_num + len(packets)) & 0xFFF
-        return out
+        if int(self.filter_mode) and out.numel():
+            out, self._iir_state = self.phy.iir_ccd(out, self.forward_OOB, self.feedback_OOB, self._iir_state)
+        return out, soff
 
     # port 1 (samples) in -> port 0 (bytes) out
     def rx(self, samples, agc=True, **kw):

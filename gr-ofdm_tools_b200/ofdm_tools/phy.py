@@ -380,3 +380,43 @@ class OfdmPhy(object):
                                           samples.stride(0) if n_streams > 1 else max(n, 1), attack, decay, reference,
                                           max_gain, gain.data_ptr(), self._stream()), self.ctx)
         return out, gain
+
+    def iir_ccd(self, samples, fftaps, fbtaps, state=None, span=0, out=None):
+        """filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False): the out-of-band filter behind the TX chain of
+        ofdm_radio_hier when filter_mode=1 (python/ofdm_radio_hier.py:83-84,93,232-237).  samples: cuda complex64
+        [n] or [n_streams, n]; state: None (a fresh block) or the cuda float64 [n_streams, 32] tensor a previous
+        call returned -- updated in place, so consecutive calls continue each stream.  Returns (out, state).
+        Each stream is cut into spans that run in parallel (ofdmx_iir_ccd in include/ofdmx.h)."""
+        import ctypes as C
+        torch = self._torch()
+        one = samples.dim() == 1
+        if one:
+            samples = samples.unsqueeze(0)
+        assert samples.is_cuda and samples.dtype == torch.complex64 and samples.stride(1) == 1
+        n_streams, n = samples.shape
+        lib = _lib.load()
+        nd = int(lib.ofdmx_iir_state_doubles())
+        if state is None:
+            state = torch.zeros((n_streams, nd), dtype=torch.float64, device=samples.device)
+        assert state.is_cuda and state.dtype == torch.float64 and state.numel() == n_streams * nd and state.is_contiguous()
+        if out is None:
+            out = torch.empty_strided(samples.shape, samples.stride(), dtype=samples.dtype, device=samples.device)
+        elif out.dim() == 1:
+            out = out.unsqueeze(0)
+        assert out.shape == samples.shape and (n_streams == 1 or out.stride() == samples.stride())
+        ff = (C.c_double * len(fftaps))(*[float(t) for t in fftaps])
+        fb = (C.c_double * max(len(fbtaps), 1))(*[float(t) for t in fbtaps])
+        _lib.check(lib.ofdmx_iir_ccd(self.ctx, samples.data_ptr(), out.data_ptr(), n_streams, n,
+                                     samples.stride(0) if n_streams > 1 else max(n, 1), ff, len(fftaps), fb,
+                                     len(fbtaps), int(span), state.data_ptr(), self._stream()), self.ctx)
+        return (out[0] if one else out), state
+
+    def papr(self, block):
+        """papr_sink.level() (python/papr_sink.py:46-54) of a cuda complex64 block: peak |x|^2 over mean |x|^2.
+        Returns a cuda float32 [3] tensor {papr, peak, mean square} (no host synchronisation)."""
+        torch = self._torch()
+        assert block.is_cuda and block.dtype == torch.complex64 and block.is_contiguous() and block.numel() > 0
+        out = torch.empty(3, dtype=torch.float32, device=block.device)
+        _lib.check(_lib.load().ofdmx_papr(self.ctx, block.data_ptr(), block.numel(), out.data_ptr(), self._stream()),
+                   self.ctx)
+        return out

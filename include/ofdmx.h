@@ -180,6 +180,26 @@ int ofdmx_agc2(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_st
                int64_t stride, float attack, float decay, float reference, float max_gain,
                float *gain_io_dev, void *cuda_stream);
 
+/* ---- TX conditioning and the PAPR probe (rank 4) ---- */
+/* filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False), the out-of-band filter ofdm_radio_hier puts behind the
+ * TX chain when filter_mode=1 (python/ofdm_radio_hier.py:83-84,93,232-237; python/sync_radio_hier.py:73,165):
+ * complex float in/out, double taps, complex double accumulator, y[n] = sum ff[i] x[n-i] - sum_{j>=1} fb[j] y[n-j]
+ * (fb[0] is not used, as in GNU Radio).  At most 9 + 9 taps (the reference filter is 8th order).  Each stream is
+ * cut into spans of `span` samples (<= 0: chosen by the library) that run in parallel, each warmed up from a
+ * zero state over the length the impulse response needs to fall below 1e-18 of its peak; the first span starts
+ * from state_io and is bit-exact against the sequential filter, later spans agree to the round-off noise of the
+ * direct-form recurrence (~1e-10 relative in the accumulator for the reference taps).  state_io_dev[n_streams][ofdmx_iir_state_doubles()] doubles (zeros = a fresh block) holds the
+ * filter history before the first sample on entry and after the last one on return.  In place only when
+ * span >= n.  stride in complex samples. */
+int64_t ofdmx_iir_state_doubles(void);
+int ofdmx_iir_ccd(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n,
+                  int64_t stride, const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb,
+                  int64_t span, double *state_io_dev, void *cuda_stream);
+
+/* papr_sink.level() (python/papr_sink.py:46-54) of one block of n complex samples:
+ * out3_dev[0] = max|x|^2 / mean|x|^2, out3_dev[1] = max|x|^2, out3_dev[2] = mean|x|^2. */
+int ofdmx_papr(ofdmx_ctx *ctx, const float *in_dev, int64_t n, float *out3_dev, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

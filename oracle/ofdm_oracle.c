@@ -930,3 +930,40 @@ uint32_t orc_crc32_mac(const uint8_t *buf, int64_t len)
     }
     return crc ^ 0xFFFFFFFFu;
 }
+
+/* filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False) -- python/ofdm_radio_hier.py:83-84,93 (8th-order
+ * out-of-band TX filter), python/sync_radio_hier.py:73.  [UPSTREAM gr-filter include/gnuradio/filter/iir_filter.h,
+ * iir_filter<gr_complex, gr_complex, double, gr_complexd>::filter and set_taps(), restated from memory --
+ * parity unpinned:]
+ *     set_taps (oldstyle == false): d_fbtaps[i] = -fbtaps[i] for i >= 1 (fbtaps[0] is never used)
+ *     acc = d_fftaps[0] * (gr_complexd)in
+ *     for i = 1 .. n-1:  acc += d_fftaps[i] * (gr_complexd)prev_input[i]      (prev_input[1] = x[n-1], ...)
+ *     for i = 1 .. m-1:  acc += d_fbtaps[i] * prev_output[i]                  (complex double history)
+ *     out = (gr_complex)acc
+ * real tap x complex double = component-wise products; one rounding per operation (-ffp-contract=off).
+ * state[2*(n_ff-1) + 2*(n_fb-1)] doubles: x history (re,im pairs, newest first) then y history. */
+void orc_iir_ccd(const float *in, float *out, int64_t n, const double *ff, int n_ff, const double *fb, int n_fb,
+                 double *state)
+{
+    double *xh = state, *yh = state + 2 * (n_ff - 1);
+    const int nx = n_ff - 1, ny = n_fb > 0 ? n_fb - 1 : 0;
+    for (int64_t k = 0; k < n; k++) {
+        const double xr = (double)in[2 * k], xi = (double)in[2 * k + 1];
+        double ar = ff[0] * xr, ai = ff[0] * xi;
+        for (int i = 1; i < n_ff; i++) {
+            ar += ff[i] * xh[2 * (i - 1)];
+            ai += ff[i] * xh[2 * (i - 1) + 1];
+        }
+        for (int i = 1; i < n_fb; i++) {
+            const double t = -fb[i];
+            ar += t * yh[2 * (i - 1)];
+            ai += t * yh[2 * (i - 1) + 1];
+        }
+        for (int i = nx - 1; i > 0; i--) { xh[2 * i] = xh[2 * i - 2]; xh[2 * i + 1] = xh[2 * i - 1]; }
+        for (int i = ny - 1; i > 0; i--) { yh[2 * i] = yh[2 * i - 2]; yh[2 * i + 1] = yh[2 * i - 1]; }
+        if (nx > 0) { xh[0] = xr; xh[1] = xi; }
+        if (ny > 0) { yh[0] = ar; yh[1] = ai; }
+        out[2 * k] = (float)ar;
+        out[2 * k + 1] = (float)ai;
+    }
+}

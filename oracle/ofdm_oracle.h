@@ -126,6 +126,8 @@ void orc_agc2(const float *in, float *out, int64_t n, float attack, float decay,
 /* digital.crc32() of gr-digital/lib/crc32.cc as used by digital.crc.gen_and_append_crc32
  * (examples/benchmarks.py:347, python/ofdm_cr_tools.py:1760): MSB-first, poly 0x04C11DB7,
  * init and final XOR 0xFFFFFFFF; check value 0xFC891918. */
+void orc_iir_ccd(const float *in, float *out, int64_t n, const double *ff, int n_ff, const double *fb, int n_fb,
+                 double *state);
 uint32_t orc_crc32_mac(const uint8_t *buf, int64_t len);
 
 #ifdef __cplusplus

@@ -73,6 +73,9 @@ def lib():
                              C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_agc2.restype = None
         L.orc_agc2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orc_iir_ccd.restype = None
+        L.orc_iir_ccd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                  C.c_void_p]
         L.orc_crc32_mac.restype = C.c_uint32
         L.orc_crc32_mac.argtypes = [C.c_void_p, C.c_int64]
         L.orc_tx_frame_samples.restype = C.c_int64
@@ -328,6 +331,27 @@ def agc2(samples, gain=1.0, attack=1e-1, decay=1e-2, reference=1.0, max_gain=655
         lib().orc_agc2(_ptr(x2[s]), _ptr(out[s]), x2.shape[1], attack, decay, reference, max_gain, _ptr(gs))
         g[s] = gs[0]
     return (out[0], float(g[0])) if one else (out, g)
+
+
+def iir_ccd(samples, fftaps, fbtaps, state=None):
+    """filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False) over one stream.  state: None (fresh block) or the
+    float64 array a previous call returned.  Returns (out complex64, state)."""
+    x = np.ascontiguousarray(samples, np.complex64)
+    ff = np.ascontiguousarray(fftaps, np.float64)
+    fb = np.ascontiguousarray(fbtaps, np.float64)
+    ns = 2 * (len(ff) - 1) + 2 * max(len(fb) - 1, 0)
+    st = np.zeros(max(ns, 1), np.float64) if state is None else np.array(state, np.float64)
+    out = np.empty_like(x)
+    lib().orc_iir_ccd(_ptr(x), _ptr(out), len(x), _ptr(ff), len(ff), _ptr(fb), len(fb), _ptr(st))
+    return out, st
+
+
+def papr(block):
+    """papr_sink.set_papr (python/papr_sink.py:46-50): max(x * conj(x)) / (vdot(x, x) / len(x)), real part."""
+    m = np.asarray(block, np.complex64)
+    mean_square = np.vdot(m, np.transpose(m)) / len(m)
+    peak = max(m * np.conjugate(m))
+    return float((peak / mean_square).real)
 
 
 def lfsr_bits(mask, seed, reg_len, n):

@@ -10,7 +10,59 @@ import pytest
 import common as cm
 
 
+# python/ofdm_radio_hier.py:83-84
+FORWARD_OOB = [0.40789374966665903, 3.2351160543115207, 11.253435139165413, 22.423991613997735, 27.99555756436666,
+               22.423991613997735, 11.253435139165425, 3.235116054311531, 0.40789374966666014]
+FEEDBACK_OOB = [1.0, 6.170110168740749, 16.888669609673336, 26.73762881119027, 26.75444043101795,
+                17.322358010203928, 7.091659316015212, 1.682084643429639, 0.17795354282083842]
+
+
+def _cnoise(rng, *shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+
 # ------------------------------------------------------------------------------------------- CPU
+def test_oracle_iir_ccd_against_direct_form():
+    """orc_iir_ccd (iir_filter_ccd, oldstyle=False) against scipy's direct-form filter in complex128 and against
+    a pure-Python loop of the GNU Radio recurrence; history carried across calls; FIR-only taps."""
+    import oracle as O
+    from scipy.signal import lfilter
+    rng = np.random.default_rng(11)
+    x = _cnoise(rng, 3000)
+    y, st = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB)
+    ref = lfilter(FORWARD_OOB, FEEDBACK_OOB, x.astype(np.complex128))
+    assert np.abs(y - ref).max() <= 2e-7 * np.abs(ref).max()
+    # GNU Radio's own order of operations, 40 samples, by hand
+    xs, ys, want = [0j] * 8, [0j] * 8, []
+    for v in x[:40]:
+        v = complex(v)
+        acc = complex(FORWARD_OOB[0] * v.real, FORWARD_OOB[0] * v.imag)
+        for i in range(1, 9):
+            acc = complex(acc.real + FORWARD_OOB[i] * xs[i - 1].real, acc.imag + FORWARD_OOB[i] * xs[i - 1].imag)
+        for i in range(1, 9):
+            acc = complex(acc.real + (-FEEDBACK_OOB[i]) * ys[i - 1].real, acc.imag + (-FEEDBACK_OOB[i]) * ys[i - 1].imag)
+        xs = [v] + xs[:-1]
+        ys = [acc] + ys[:-1]
+        want.append(np.complex64(acc))
+    assert np.array_equal(y[:40], np.array(want, np.complex64))
+    y1, s1 = O.iir_ccd(x[:777], FORWARD_OOB, FEEDBACK_OOB)
+    y2, s2 = O.iir_ccd(x[777:], FORWARD_OOB, FEEDBACK_OOB, s1)
+    assert np.array_equal(np.concatenate([y1, y2]), y) and np.array_equal(s2, st)
+    taps = [0.25, 0.5, 0.25]
+    yf, _ = O.iir_ccd(x, taps, [1.0])
+    assert np.allclose(yf, lfilter(taps, [1.0], x.astype(np.complex128)), rtol=0, atol=1e-6)
+
+
+def test_oracle_papr():
+    """python/papr_sink.py:46-50 on a constant-envelope block (PAPR 1) and on a single peak."""
+    import oracle as O
+    x = np.exp(1j * np.arange(512)).astype(np.complex64)
+    assert abs(O.papr(x) - 1.0) < 1e-5
+    x = np.ones(100, np.complex64)
+    x[7] = 3 + 4j
+    assert abs(O.papr(x) - 25.0 / ((99 + 25) / 100.0)) < 1e-4
+
+
 def test_mac_crc32_check_values():
     """MSB-first CRC-32 of digital.crc (SURVEY.md A.13 check value) in the oracle and in the host module."""
     import oracle as O
@@ -195,7 +247,8 @@ def test_hier_facades_with_agc_and_clipper():
     import oracle as O
     from ofdm_tools import ofdm_radio_hier, ofdm_tx_rx_hier
     rng = np.random.default_rng(77)
-    radio = ofdm_radio_hier(payload_mod='qam16', scramble_mode=1, crc_mode=1, clipper_mode=1, clipping_factor=0.3)
+    radio = ofdm_radio_hier(payload_mod='qam16', scramble_mode=1, crc_mode=1, clipper_mode=1, clipping_factor=0.3,
+                            filter_mode=0)
     pk = cm.rand_packets(rng, 6, 200)
     s, off = radio.tx(pk)
     s = s.cpu().numpy()
@@ -249,3 +302,99 @@ def test_pdu_adaptors_gpu_crc():
     snk = payload_sink_pdu(lambda a, t, n, p: got.append(p), phy=phy)
     snk.deliver(pk[:2] + [pk[2][:-1] + bytes([pk[2][-1] ^ 0x80])] + pk[3:])
     assert [len(p) for p in got] == [0, 1, 100, 1500]
+
+
+@pytest.mark.gpu
+def test_iir_ccd_parity():
+    """ofdmx_iir_ccd against the oracle: one span = the sequential recurrence, bit for bit, history included;
+    many parallel spans agree to the round-off noise floor of the direct-form recurrence itself (the reference
+    taps put eight poles at radius <= 0.985 next to z = -1, so the double accumulator carries ~1e-10 of relative
+    round-off noise whatever the order of evaluation): every float within one ulp of the peak, > 98 % identical;
+    strided multi-stream input; FIR-only taps; error paths."""
+    import torch
+    import oracle as O
+    phy = cm.make_phy(cm.cfg_c1())
+    rng = np.random.default_rng(21)
+    x = _cnoise(rng, 5000)
+    xd = torch.from_numpy(x).to(_dev())
+    y, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, span=1 << 20)
+    ref, rst = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    assert np.array_equal(st.cpu().numpy().ravel(), rst)
+    y2, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, state=st, span=1 << 20)     # continues the stream
+    ref2, rst2 = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB, rst)
+    assert np.array_equal(y2.cpu().numpy(), ref2) and np.array_equal(st.cpu().numpy().ravel(), rst2)
+    # parallel spans (explicit and library-chosen), ragged tail, carried state
+    x = _cnoise(rng, 300001)
+    xd = torch.from_numpy(x).to(_dev())
+    ref, rst = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB)
+    refb, rstb = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB, rst)
+    for span in (1024, 4096, 0):
+        y, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, span=span)
+        y = y.cpu().numpy()
+        assert np.abs(y - ref).max() <= 2.4e-7 * np.abs(ref).max()
+        assert np.mean(y == ref) > 0.98
+        assert np.array_equal(y[:1024], ref[:1024])                 # the first span is the sequential filter
+        assert np.abs(st.cpu().numpy().ravel() - rst).max() <= 1e-8 * np.abs(rst).max()
+        yb, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, state=st, span=span)
+        assert np.abs(yb.cpu().numpy() - refb).max() <= 2.4e-7 * np.abs(refb).max()
+    # streams = rows of a wider matrix
+    m = _cnoise(rng, 37, 6000)
+    md = torch.from_numpy(m).to(_dev())
+    y, st = phy.iir_ccd(md[:, :5555], FORWARD_OOB, FEEDBACK_OOB, span=1 << 20)
+    for r in range(37):
+        rr, rs = O.iir_ccd(m[r, :5555], FORWARD_OOB, FEEDBACK_OOB)
+        assert np.array_equal(y[r].cpu().numpy(), rr) and np.array_equal(st[r].cpu().numpy(), rs)
+    y, _ = phy.iir_ccd(md[:, :5555], FORWARD_OOB, FEEDBACK_OOB, span=2048)
+    assert np.abs(y.cpu().numpy() - np.stack([O.iir_ccd(m[r, :5555], FORWARD_OOB, FEEDBACK_OOB)[0] for r in range(37)])).max() < 1e-5
+    # FIR only
+    yf, _ = phy.iir_ccd(xd, [0.25, 0.5, 0.25], [1.0], span=0)
+    assert np.array_equal(yf.cpu().numpy(), O.iir_ccd(x, [0.25, 0.5, 0.25], [1.0])[0])
+    with pytest.raises(Exception):
+        phy.iir_ccd(xd, [1.0] * 10, FEEDBACK_OOB)
+    with pytest.raises(Exception):
+        phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, span=1024, out=xd)
+    with pytest.raises(Exception):
+        phy.iir_ccd(xd, [1.0], [1.0, -1.5])                        # pole outside the unit circle
+
+
+@pytest.mark.gpu
+def test_papr_sink_gpu():
+    """papr_sink.level() on the GPU against python/papr_sink.py:46-50 restated in the oracle."""
+    import torch
+    import oracle as O
+    from ofdm_tools import papr_sink
+    phy = cm.make_phy(cm.cfg_c1())
+    rng = np.random.default_rng(4)
+    for n, bl in ((1, 512), (511, 512), (100000, 4096), (300000, 300000)):
+        x = _cnoise(rng, n)
+        snk = papr_sink(bl, phy=phy)
+        assert snk.work(torch.from_numpy(x).to(_dev())) == min(n, bl)
+        assert abs(snk.level() - O.papr(x[:bl])) <= 1e-5 * O.papr(x[:bl])
+
+
+@pytest.mark.gpu
+def test_radio_hier_filter_mode():
+    """ofdm_radio_hier(filter_mode=1), the reference default: the TX burst stream equals oracle TX -> oracle
+    iir_filter_ccd (history carried across tx() calls), and the filtered bursts still decode."""
+    import torch
+    import oracle as O
+    from ofdm_tools import ofdm_radio_hier
+    rng = np.random.default_rng(9)
+    radio = ofdm_radio_hier(payload_mod='qpsk', scramble_mode=1, crc_mode=1)
+    assert radio.filter_mode == 1
+    cfg = cm.cfg_radio128(2, 1, 1)
+    cfg.update(tx_scale=0.01, max_carr_offset=3, scramble_header=True)
+    orc = O.Oracle(**cfg)
+    st, n0 = None, 0
+    for call in range(2):
+        pk = cm.rand_packets(rng, 5, 180)
+        s, off = radio.tx(pk)
+        so, oo = orc.tx(pk, first_pkt_num=n0)
+        n0 += len(pk)
+        assert np.array_equal(off.cpu().numpy(), oo)
+        ref, st = O.iir_ccd(so, radio.forward_OOB, radio.feedback_OOB, st)
+        s = s.cpu().numpy()
+        assert np.abs(s - ref).max() <= 1e-5 * np.abs(ref).max()
+        x = cm.channel(cm.split_frames(s, oo), rng, gaps=(400, 900), tail=2000, snr_db=40.0, fft_len=128, scale=100.0)
+        assert radio.rx(torch.from_numpy(x).to(_dev()), agc=False).payloads() == pk

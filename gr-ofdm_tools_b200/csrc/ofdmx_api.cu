@@ -410,6 +410,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     const int N = prm->fft_len;
     if (N < 16 || N > 4096 || (N & (N - 1))) return fail(nullptr, OFDMX_ERR_PARAM, "fft_len must be a power of two in 16..4096");
     if (prm->cp_len < 0 || prm->cp_len > N) return fail(nullptr, OFDMX_ERR_PARAM, "cp_len out of range");
+    if (prm->rolloff < 0 || prm->rolloff > prm->cp_len)
+        return fail(nullptr, OFDMX_ERR_PARAM, "cyclic prefixer: rolloff len must smaller than the cyclic prefix.");
     if (prm->n_occ_sets < 1 || !prm->occ_sizes || !prm->occ_carriers) return fail(nullptr, OFDMX_ERR_PARAM, "occupied_carriers missing");
     if (!prm->sync_word1 || !prm->sync_word2) return fail(nullptr, OFDMX_ERR_PARAM, "Length of sync sequence(s) must be FFT length.");
     std::vector<float2> hpts, ppts;
@@ -448,6 +450,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     kp.alpha = prm->alpha;
     kp.tx_scale = prm->tx_scale;
     kp.tx_clip = prm->tx_clip;
+    kp.roll = prm->rolloff > 1 ? prm->rolloff : 0;      // a flank of length 1 would just be rectangular
+    kp.roll_flank = nullptr;
 
     int rc = 0;
     auto bail = [&](int code) { ofdmx_destroy(c); return code; };
@@ -643,8 +647,18 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     UP(crc_tab, crc_tab) UP(crc_pow, crc_pow) UP(hpts, hpts) UP(ppts, ppts) UP(lut_h, lut_h) UP(lut_p, lut_p)
     UP(inv_hpts, inv_hpts) UP(inv_ppts, inv_ppts) UP(pos_su, pos_su) UP(crc8_bit, crc8_bit) UP(crc_pow64, crc_pow64) UP(crc_pow8, crc_pow8)
 #undef UP
+    if (kp.roll) {
+        // [UPSTREAM ofdm_cyclic_prefixer_impl.cc ctor]: flanks are one sample shorter than rolloff_len
+        // (the first sample of the up / down flank is always zero / one), float vectors
+        std::vector<float> fl((size_t)2 * (kp.roll - 1));
+        for (int i = 1; i < kp.roll; i++) {
+            fl[i - 1] = (float)(0.5 * (1 + cos(M_PI * i / kp.roll - M_PI)));
+            fl[kp.roll - 1 + i - 1] = (float)(0.5 * (1 + cos(M_PI * (kp.roll - i) / kp.roll - M_PI)));
+        }
+        if ((rc = upload(c, fl, &kp.roll_flank)) != 0) return bail(rc);
+    }
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
-    if ((N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
+    if (!kp.roll && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
         && kp.bps_h == 1 && c->hl >= 32) {
         std::vector<uint16_t> tx_map((size_t)N, (uint16_t)TXW_EMPTY);
         for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
@@ -687,7 +701,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         c->sync_smem = (size_t)Lp * 32;
         c->frame_smem = (size_t)N * 8 * 4 + 64 + N + align_up(c->hl, 16) + align_up(kp.max_pkt_syms, 16)
                         + align_up(kp.max_pkt_bytes, 16) + 16;
-        c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16;
+        c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16 + (size_t)kp.roll * 8;
         if (N == 1024) {
             c->frame1k_warps = std::max(4, std::min(F1K_MAXW, 3 + kp.max_frame_syms));
             c->frame1k_smem = frame1024_smem_bytes(c->frame1k_warps, kp.n_occ_u, c->hl, kp.max_pkt_syms, kp.max_pkt_bytes);
@@ -864,7 +878,7 @@ int64_t ofdmx_tx_frame_samples(const ofdmx_ctx *c, int64_t payload_bytes)
     if (!c || payload_bytes < 0) return -1;
     const int64_t lp = payload_bytes + (c->kp.crc_mode ? 4 : 0);
     const int64_t ns = (lp * 8 + c->kp.bps_p - 1) / c->kp.bps_p;
-    return (int64_t)(3 + payload_ofdm_syms(c, (int)ns)) * c->kp.D;
+    return (int64_t)(3 + payload_ofdm_syms(c, (int)ns)) * c->kp.D + (c->kp.roll ? c->kp.roll - 1 : 0);
 }
 
 int ofdmx_reserve(ofdmx_ctx *c, int64_t n_streams, int64_t n_samples, int64_t max_frames)

@@ -17,6 +17,8 @@ struct KP {
     int max_pkt_bytes, max_pkt_syms;
     double thr;
     float alpha, tx_scale, tx_clip;
+    int roll;                    // ofdm_cyclic_prefixer rolloff_len (0 = rectangular, else >= 2)
+    const float *roll_flank;     // [2 * (roll - 1)]: up flank, then down flank
     const float2 *tw;            // [N] exp(-2 pi i k / N)
     const int *occ_bins;         // flat, set-major, list order, shifted bins
     const int *occ_base;         // [n_occ_sets]

@@ -631,11 +631,12 @@ tx_offsets_kernel(const KP p, const long long *__restrict__ pkt_off, long long n
         }
         int total;
         const int ex = block_excl_scan(v, wt, total);
-        if (idx < n_pkts) sample_off[idx] = (carry + ex) * (long long)p.D;
+        // with rolloff every burst carries roll-1 extra samples (the flushed down flank of its last symbol)
+        if (idx < n_pkts) sample_off[idx] = (carry + ex) * (long long)p.D + idx * (long long)(p.roll ? p.roll - 1 : 0);
         carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) sample_off[n_pkts] = carry * (long long)p.D;
+    if (threadIdx.x == 0) sample_off[n_pkts] = carry * (long long)p.D + n_pkts * (long long)(p.roll ? p.roll - 1 : 0);
 }
 
 __global__ void __launch_bounds__(OFDMX_THREADS)
@@ -648,10 +649,13 @@ tx_frame_kernel(const KP p, const uint8_t *__restrict__ payload, const long long
     uint32_t *scratch = reinterpret_cast<uint32_t *>(buf + p.N);
     uint8_t *pb = reinterpret_cast<uint8_t *>(scratch + 16);
     uint8_t *hdr = pb + ((p.max_pkt_bytes + 8 + 15) & ~15);
+    float2 *tail = reinterpret_cast<float2 *>(hdr + ((p.hl + 15) & ~15));   // delay line of the prefixer [roll-1]
     const int tid = threadIdx.x, N = p.N;
+    const int nfl = p.roll ? p.roll - 1 : 0;
 
     for (long long pk = blockIdx.x; pk < n_pkts; pk += gridDim.x) {
         __syncthreads();
+        for (int m = tid; m < nfl; m += blockDim.x) tail[m] = make_float2(0.f, 0.f);
         const long long o0 = pkt_off[pk];
         const int len = (int)(pkt_off[pk + 1] - o0);
         const int lp = len + (p.crc_mode ? 4 : 0);
@@ -680,7 +684,7 @@ tx_frame_kernel(const KP p, const uint8_t *__restrict__ payload, const long long
         const int ns = (lp * 8 + p.bps_p - 1) / p.bps_p;       // repack_bits_bb(8, bps, key, False)
         const int n_ofdm = 3 + tx_payload_ofdm_syms(p, ns);
         const long long base = sample_off[pk];
-        if (base + (long long)n_ofdm * p.D > cap) continue;
+        if (base + (long long)n_ofdm * p.D + nfl > cap) continue;
         int sym_base = 0, set = 0;
         for (int o = 0; o < n_ofdm; o++) {
             // ofdm_carrier_allocator_cvc: sync words, then data on occupied bins, pilots on top
@@ -722,7 +726,15 @@ tx_frame_kernel(const KP p, const uint8_t *__restrict__ payload, const long long
             fft_smem<true>(buf, N, p.logN, p.tw);
             float2 *dst = out + base + (long long)o * p.D;
             for (int m = tid; m < p.D; m += blockDim.x) {
-                const float2 v = buf[(m - p.cp + N) & (N - 1)];
+                float2 v = buf[(m - p.cp + N) & (N - 1)];
+                if (m < nfl) {
+                    // ofdm_cyclic_prefixer with rolloff: out[i] = out[i]*up[i] + delay[i]; delay[i] = in[i]*down[i]
+                    // (nfl <= cp, so thread m owns tail[m] and only reads buf)
+                    const float up = p.roll_flank[m], dn = p.roll_flank[nfl + m];
+                    const float2 t = tail[m], h = buf[m];
+                    v = make_float2(__fadd_rn(__fmul_rn(v.x, up), t.x), __fadd_rn(__fmul_rn(v.y, up), t.y));
+                    tail[m] = make_float2(__fmul_rn(h.x, dn), __fmul_rn(h.y, dn));
+                }
                 float2 o = make_float2(v.x * p.tx_scale, v.y * p.tx_scale);
                 if (p.tx_clip > 0.f) {      // clipper: analog.rail_ff(-c, c) on re and im
                     o.x = o.x < -p.tx_clip ? -p.tx_clip : (o.x > p.tx_clip ? p.tx_clip : o.x);
@@ -731,6 +743,16 @@ tx_frame_kernel(const KP p, const uint8_t *__restrict__ payload, const long long
                 dst[m] = o;
             }
             __syncthreads();
+        }
+        // packet mode: the delay line is flushed behind the last symbol (and cleared for the next packet)
+        for (int m = tid; m < nfl; m += blockDim.x) {
+            const float2 t = tail[m];
+            float2 o = make_float2(t.x * p.tx_scale, t.y * p.tx_scale);
+            if (p.tx_clip > 0.f) {
+                o.x = o.x < -p.tx_clip ? -p.tx_clip : (o.x > p.tx_clip ? p.tx_clip : o.x);
+                o.y = o.y < -p.tx_clip ? -p.tx_clip : (o.y > p.tx_clip ? p.tx_clip : o.y);
+            }
+            out[base + (long long)n_ofdm * p.D + m] = o;
         }
     }
 }

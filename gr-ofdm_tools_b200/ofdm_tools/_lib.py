@@ -25,7 +25,7 @@ class Params(C.Structure):
         ("scramble_header", C.c_int32), ("scramble_seed", C.c_int32),
         ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
         ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32),
-        ("max_pkt_bytes", C.c_int32), ("tx_clip", C.c_float),
+        ("max_pkt_bytes", C.c_int32), ("tx_clip", C.c_float), ("rolloff", C.c_int32),
     ]
 
 

@@ -106,8 +106,9 @@ class _ofdm_base(object):
 class ofdm_tx(_ofdm_base):
     """OFDM modulation: byte packets in, complex baseband out.
 
-    Args: as python/ofdm_txrx_modules.py:126-142 of the reference.  `rolloff` > 0 (cyclic-prefix
-    windowing) is not built; `debug_log` is accepted and ignored as in the reference (:153)."""
+    Args: as python/ofdm_txrx_modules.py:126-142 of the reference.  `rolloff` is the
+    rolloff_len of digital.ofdm_cyclic_prefixer (:247-253): raised-cosine flanks, each burst rolloff-1 samples
+    longer; `debug_log` is accepted and ignored as in the reference (:153)."""
 
     def __init__(self, fft_len=_def_fft_len, cp_len=_def_cp_len,
                  packet_length_tag_key=_def_packet_length_tag_key,
@@ -116,11 +117,10 @@ class ofdm_tx(_ofdm_base):
                  pilot_symbols=_def_pilot_symbols,
                  bps_header=1, bps_payload=1, sync_word1=None, sync_word2=None,
                  rolloff=0, debug_log=False, scramble_bits=False, **phy_kwargs):
-        if rolloff:
-            raise NotImplementedError("rolloff > 0 is not built (all reference surfaces use 0)")
         self.packet_length_tag_key = packet_length_tag_key
+        self.rolloff = rolloff
         self._setup(fft_len, cp_len, occupied_carriers, pilot_carriers, pilot_symbols, bps_header,
-                    bps_payload, sync_word1, sync_word2, scramble_bits, **phy_kwargs)
+                    bps_payload, sync_word1, sync_word2, scramble_bits, rolloff=int(rolloff), **phy_kwargs)
         self.sync_words = [self.sync_word1, self.sync_word2]
         self._pkt_num = 0
 

@@ -94,7 +94,7 @@ class OfdmPhy(object):
                  pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
                  max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None,
-                 max_pkt_bytes=4095, device=0, tx_clip=0.0):
+                 max_pkt_bytes=4095, device=0, tx_clip=0.0, rolloff=0):
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occupied_carriers = [list(map(int, s)) for s in occupied_carriers]
         self.pilot_carriers = [list(map(int, s)) for s in pilot_carriers]
@@ -140,6 +140,8 @@ class OfdmPhy(object):
         p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
         p.max_pkt_bytes = self.max_pkt_bytes
         p.tx_clip = float(tx_clip)
+        p.rolloff = int(rolloff)
+        self.rolloff = int(rolloff)
         self.params = p
         self._ctx = None
 

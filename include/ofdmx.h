@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OFDMX_ABI_VERSION 2
+#define OFDMX_ABI_VERSION 3
 
 typedef enum {
     OFDMX_OK = 0,
@@ -78,6 +78,11 @@ typedef struct {
     float   tx_clip;                /* ofdm_tools.clipper(clipping_factor) fused after the scaling: re and im
                                        railed to +-tx_clip (python/clipper.py:45-58,
                                        python/ofdm_radio_hier.py:92,229,239); 0 = no clipper */
+    int32_t rolloff;                /* ofdm_cyclic_prefixer(fft_len, fft_len+cp_len, rolloff, key)
+                                       (python/ofdm_txrx_modules.py:247-253; cp_len/4 in python/ofdm_cr_tools.py:1093):
+                                       raised-cosine flanks of rolloff-1 samples; every burst grows by rolloff-1
+                                       samples (the flushed down flank of its last symbol).  0 or 1 = rectangular;
+                                       must not exceed cp_len */
 } ofdmx_params;
 
 /* Per-frame record (replaces the stream tags / PMT header dict of the reference). 32 bytes. */

@@ -366,7 +366,8 @@ int64_t orc_tx_frame_samples(const orc_params *p, int64_t payload_bytes)
 {
     int64_t lp = payload_bytes + (p->crc_mode ? 4 : 0);
     int64_t ns = (lp * 8 + p->bps_payload - 1) / p->bps_payload;
-    return (int64_t)(3 + alloc_payload_ofdm_syms(p, (int)ns)) * (p->fft_len + p->cp_len);
+    return (int64_t)(3 + alloc_payload_ofdm_syms(p, (int)ns)) * (p->fft_len + p->cp_len)
+           + (p->rolloff > 1 ? p->rolloff - 1 : 0);
 }
 
 /* TX chain: python/ofdm_txrx_modules.py:189-254 (ofdm_tx), python/ofdm_radio_hier.py:212-231
@@ -388,6 +389,18 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
     for (int s = 0, a = 0; s < p->n_pilot_sets; s++) { pil_base[s] = a; a += p->pilot_sizes[s]; }
     int *pls_base = (int *)malloc(sizeof(int) * (size_t)(p->n_pilot_sym_sets + 1));
     for (int s = 0, a = 0; s < p->n_pilot_sym_sets; s++) { pls_base[s] = a; a += p->pilot_sym_sizes[s]; }
+
+    /* [UPSTREAM ofdm_cyclic_prefixer_impl.cc ctor]: rolloff_len 1 is rectangular; the flanks (float vectors)
+     * are rolloff_len-1 long because the first sample of the up / down flank is always zero / one */
+    const int roll = p->rolloff > 1 ? p->rolloff : 0, nfl = roll ? roll - 1 : 0;
+    if (roll > cp) return -1;
+    float up_flank[4096], down_flank[4096];
+    cd delay_line[4096];
+    for (int i = 1; i < roll; i++) {
+        up_flank[i - 1] = (float)(0.5 * (1 + cos(M_PI * i / roll - M_PI)));
+        down_flank[i - 1] = (float)(0.5 * (1 + cos(M_PI * (roll - i) / roll - M_PI)));
+        delay_line[i - 1] = 0.0;
+    }
 
     int64_t pos = 0;
     int rc = 0;
@@ -412,7 +425,7 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
         int n_pay = alloc_payload_ofdm_syms(p, (int)ns);
         int n_ofdm = 3 + n_pay;
         sample_off[pk] = pos;
-        if (pos + (int64_t)n_ofdm * (n + cp) > cap_samples) { rc = -2; }
+        if (pos + (int64_t)n_ofdm * (n + cp) + nfl > cap_samples) { rc = -2; }
         int64_t sym_idx = 0; /* index into concatenated header+payload symbols */
         int set = 0;
         for (int o = 0; o < n_ofdm && !rc; o++) {
@@ -451,7 +464,15 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
             fft_cd(n, 0, sw, td);
             float *o_ = samples_out + 2 * (pos + (int64_t)o * (n + cp));
             for (int m = 0; m < n + cp; m++) {
-                cd v = td[(m - cp + n) % n] * (double)p->tx_scale;
+                cd v = td[(m - cp + n) % n];
+                if (m < nfl) {
+                    /* [UPSTREAM ofdm_cyclic_prefixer_impl.cc work(), restated from memory -- parity unpinned]:
+                     *   out[i] = out[i] * d_up_flank[i] + d_delay_line[i];  d_delay_line[i] = in[i] * d_down_flank[i]
+                     * for i < rolloff_len-1, flanks 0.5*(1+cos(pi*i/rolloff_len - pi)) and its mirror, i = 1.. */
+                    v = v * up_flank[m] + delay_line[m];
+                    delay_line[m] = td[m] * down_flank[m];
+                }
+                v *= (double)p->tx_scale;
                 float vr = (float)creal(v), vi = (float)cimag(v);
                 if (p->tx_clip > 0.0f) {   /* analog.rail_ff(-c, c) on re and im (python/clipper.py:45-58) */
                     vr = vr < -p->tx_clip ? -p->tx_clip : (vr > p->tx_clip ? p->tx_clip : vr);
@@ -461,7 +482,19 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
                 o_[2 * m + 1] = vi;
             }
         }
-        pos += (int64_t)n_ofdm * (n + cp);
+        /* tagged-stream mode: the delay line is flushed behind the last symbol and cleared */
+        for (int m = 0; m < nfl; m++) {
+            cd v = delay_line[m] * (double)p->tx_scale;
+            float vr = (float)creal(v), vi = (float)cimag(v);
+            if (p->tx_clip > 0.0f) {
+                vr = vr < -p->tx_clip ? -p->tx_clip : (vr > p->tx_clip ? p->tx_clip : vr);
+                vi = vi < -p->tx_clip ? -p->tx_clip : (vi > p->tx_clip ? p->tx_clip : vi);
+            }
+            samples_out[2 * (pos + (int64_t)n_ofdm * (n + cp) + m)] = vr;
+            samples_out[2 * (pos + (int64_t)n_ofdm * (n + cp) + m) + 1] = vi;
+            delay_line[m] = 0.0;
+        }
+        pos += (int64_t)n_ofdm * (n + cp) + nfl;
         free(buf); free(hdr); free(chunks);
     }
     sample_off[n_pkts] = pos;

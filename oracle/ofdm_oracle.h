@@ -57,6 +57,8 @@ typedef struct {
                                        fft_len+cp_len (GNU Radio < 3.7.10) or 1 (>= 3.7.10) */
     float   tx_clip;                /* ofdm_tools.clipper(clipping_factor) after the scaling: re and im railed to
                                        +-tx_clip (python/clipper.py:45-58, ofdm_radio_hier.py:92,229); 0 = off */
+    int32_t rolloff;                /* ofdm_cyclic_prefixer rolloff_len (python/ofdm_txrx_modules.py:247-253);
+                                       0 or 1 = rectangular */
 } orc_params;
 
 typedef struct {

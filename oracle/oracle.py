@@ -38,7 +38,7 @@ class _Params(C.Structure):
         ("bps_header", C.c_int32), ("bps_payload", C.c_int32),
         ("scramble_header", C.c_int32), ("scramble_seed", C.c_int32),
         ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
-        ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32), ("tx_clip", C.c_float),
+        ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32), ("tx_clip", C.c_float), ("rolloff", C.c_int32),
     ]
 
 
@@ -156,7 +156,7 @@ class Oracle:
     def __init__(self, fft_len=64, cp_len=16, occupied_carriers=None, pilot_carriers=None,
                  pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
-                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None, tx_clip=0.0):
+                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None, tx_clip=0.0, rolloff=0):
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occ = [list(map(int, s)) for s in occupied_carriers]
         self.pil = [list(map(int, s)) for s in pilot_carriers]
@@ -191,6 +191,7 @@ class Oracle:
         p.threshold, p.max_carr_offset, p.alpha, p.tx_scale = threshold, max_carr_offset, alpha, tx_scale
         p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
         p.tx_clip = float(tx_clip)
+        p.rolloff = int(rolloff)
         self.p = p
         self.L = lib()
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.ofdmx_abi_version() == 2
+    assert lib.ofdmx_abi_version() == 3
     assert lib.ofdmx_profile_slots() >= 10
     assert lib.ofdmx_profile_name(0) == b"sync_metric_kernel"
     names = {lib.ofdmx_profile_name(i) for i in range(lib.ofdmx_profile_slots())}

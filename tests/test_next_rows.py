@@ -53,6 +53,48 @@ def test_oracle_iir_ccd_against_direct_form():
     assert np.allclose(yf, lfilter(taps, [1.0], x.astype(np.complex128)), rtol=0, atol=1e-6)
 
 
+def _prefixer_numpy(td_syms, cp, roll):
+    """Independent numpy restatement of ofdm_cyclic_prefixer in packet mode: td_syms [n_sym, N] -> burst."""
+    n_sym, N = td_syms.shape
+    nfl = roll - 1 if roll > 1 else 0
+    i = np.arange(1, nfl + 1)
+    up = (0.5 * (1 + np.cos(np.pi * i / max(roll, 1) - np.pi))).astype(np.float32)
+    down = (0.5 * (1 + np.cos(np.pi * (max(roll, 1) - i) / max(roll, 1) - np.pi))).astype(np.float32)
+    out = np.zeros(n_sym * (N + cp) + nfl, np.complex128)
+    for s_ in range(n_sym):
+        sym = np.concatenate([td_syms[s_, N - cp:], td_syms[s_]])
+        sym[:nfl] *= up
+        out[s_ * (N + cp): (s_ + 1) * (N + cp)] += sym
+        out[(s_ + 1) * (N + cp): (s_ + 1) * (N + cp) + nfl] += td_syms[s_, :nfl] * down
+    return out
+
+
+def test_oracle_tx_rolloff():
+    """orc_tx with rolloff > 0 against the rolloff-0 burst re-windowed by an independent numpy restatement of
+    ofdm_cyclic_prefixer (flanks sum to one; each burst rolloff-1 samples longer; rolloff 1 == rolloff 0)."""
+    import oracle as O
+    rng = np.random.default_rng(3)
+    pk = cm.rand_packets(rng, 3, 60) + [b""]
+    cfg = cm.cfg_c1()
+    base = O.Oracle(**cfg)
+    s0, off0 = base.tx(pk)
+    N, cp = cfg["fft_len"], cfg["cp_len"]
+    for roll in (1, 2, 4, 7, 16):
+        orc = O.Oracle(rolloff=roll, **cfg)
+        s, off = orc.tx(pk)
+        nfl = roll - 1 if roll > 1 else 0
+        assert np.array_equal(off, off0 + nfl * np.arange(len(pk) + 1))
+        assert orc.frame_samples(60) == base.frame_samples(60) + nfl
+        for k in range(len(pk)):
+            burst0 = s0[off0[k]:off0[k + 1]].astype(np.complex128).reshape(-1, N + cp)
+            want = _prefixer_numpy(burst0[:, cp:], cp, roll)
+            got = s[off[k]:off[k + 1]]
+            assert len(got) == len(want)
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    with pytest.raises(Exception):
+        O.Oracle(rolloff=cp + 1, **cfg).tx(pk)
+
+
 def test_oracle_papr():
     """python/papr_sink.py:46-50 on a constant-envelope block (PAPR 1) and on a single peak."""
     import oracle as O
@@ -398,3 +440,35 @@ def test_radio_hier_filter_mode():
         assert np.abs(s - ref).max() <= 1e-5 * np.abs(ref).max()
         x = cm.channel(cm.split_frames(s, oo), rng, gaps=(400, 900), tail=2000, snr_db=40.0, fft_len=128, scale=100.0)
         assert radio.rx(torch.from_numpy(x).to(_dev()), agc=False).payloads() == pk
+
+
+@pytest.mark.gpu
+def test_tx_rolloff_parity_and_loopback():
+    """ofdm_tx(rolloff=r): CUDA TX against the oracle (offsets exact, samples within 1e-5) for the
+    sync_transmit_path setting rolloff = cp_len/4 (python/ofdm_cr_tools.py:1093) and others, with the clipper
+    behind it; the windowed bursts decode on the RX chain; rolloff > cp_len is refused as in GNU Radio."""
+    import torch
+    import oracle as O
+    from ofdm_tools import ofdm_tx
+    rng = np.random.default_rng(13)
+    for cfg, rolls, plen in ((cm.cfg_c1(), (4, 2, 16, 1), 96), (cm.cfg_radio128(4, 1, 1), (8,), 200)):
+        for roll in rolls:
+            kw = dict(cfg, rolloff=roll, tx_scale=0.01, tx_clip=0.3)
+            phy = cm.make_phy(kw)
+            orc = O.Oracle(**kw)
+            pk = cm.rand_packets(rng, 7, plen) + [b"", b"x"]
+            s, off = phy.tx(pk)
+            so, oo = orc.tx(pk)
+            assert np.array_equal(off.cpu().numpy(), oo)
+            s = s.cpu().numpy()
+            assert s.shape == so.shape and np.abs(s - so).max() <= 1e-5 * np.abs(so).max()
+            assert phy.frame_samples(plen) == orc.frame_samples(plen)
+            x = cm.channel(cm.split_frames(s, oo), rng, gaps=(300, 700), tail=1500, snr_db=40.0,
+                           fft_len=cfg["fft_len"], scale=100.0)
+            got = phy.rx(torch.from_numpy(x).to(_dev())).payloads()
+            assert got == orc.payloads(orc.rx(x, byte_stride=phy.byte_stride, want_z=False))
+            assert [g for g in got if len(g) > 1] == [p_ for p_ in pk if len(p_) > 1]
+    tx = ofdm_tx(fft_len=64, cp_len=16, bps_header=1, bps_payload=2, rolloff=4)
+    assert tx.rolloff == 4 and tx.phy.frame_samples(96) == cm.make_phy(cm.cfg_c1()).frame_samples(96) + 3
+    with pytest.raises(Exception):
+        ofdm_tx(fft_len=64, cp_len=16, rolloff=17).work([b"abc"])

@@ -1184,4 +1184,32 @@ int ofdmx_papr(ofdmx_ctx *c, const float *in_dev, int64_t n, float *out3_dev, vo
     return OFDMX_OK;
 }
 
+int ofdmx_reconfigure(ofdmx_ctx **ctx_io, const ofdmx_params *prm)
+{
+    if (!ctx_io || !*ctx_io || !prm) return fail(ctx_io ? *ctx_io : nullptr, OFDMX_ERR_PARAM, "bad ofdmx_reconfigure arguments");
+    ofdmx_ctx *old = *ctx_io, *nw = nullptr;
+    // work enqueued with the old tables must have finished before they are freed
+    if (int rc = check_device(old)) return rc;
+    CUDA_TRY(old, cudaDeviceSynchronize());
+    if (int rc = ofdmx_create(prm, old->device, &nw)) { old->err = g_err; return rc; }
+    // everything that is not a function of the PHY parameters moves over: workspace, pinned staging buffers,
+    // the private stream, the profiling state and the counters
+    std::swap(nw->ws, old->ws);
+    std::swap(nw->h_samples, old->h_samples);
+    std::swap(nw->h_frames, old->h_frames);
+    std::swap(nw->h_bytes, old->h_bytes);
+    std::swap(nw->h_counts, old->h_counts);
+    std::swap(nw->own_stream, old->own_stream);
+    std::swap(nw->prof_pending, old->prof_pending);
+    std::swap(nw->prof_pool, old->prof_pool);
+    nw->profiling = old->profiling;
+    std::memcpy(nw->prof_ms, old->prof_ms, sizeof nw->prof_ms);
+    std::memcpy(nw->prof_calls, old->prof_calls, sizeof nw->prof_calls);
+    nw->launches = old->launches;
+    nw->emit_all = old->emit_all;
+    ofdmx_destroy(old);
+    *ctx_io = nw;
+    return OFDMX_OK;
+}
+
 }  // extern "C"

@@ -60,6 +60,7 @@ SYMBOLS = {
     "ofdmx_iir_state_doubles": (_I64, []),
     "ofdmx_iir_ccd": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P, _I32, _I64, _P, _P]),
     "ofdmx_papr": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "ofdmx_reconfigure": (C.c_int, [_P, _P]),
 }
 
 _lib = None

@@ -78,6 +78,20 @@ class ofdm_radio_hier(object):
         self._agc_gain = None
         self._iir_state = None
 
+    def reconfigure(self, occupied_carriers, pilot_carriers, pilot_symbols, sync_word1, sync_word2):
+        """New carrier plan and sync words on the running block -- the tuple ofdm_cr_tools.spectrum_enforcer
+        returns (python/ofdm_cr_tools.py:348-378), which cognitive_engine_mac forwards to the radios
+        (python/cognitive_engine_mac.py:278-285).  fft_len follows the sync words as in the constructor (:76)."""
+        fft_len = (len(sync_word1) + len(sync_word2)) // 2
+        self.phy.reconfigure(fft_len=fft_len, cp_len=fft_len // 4, occupied_carriers=occupied_carriers,
+                             pilot_carriers=pilot_carriers, pilot_symbols=pilot_symbols,
+                             sync_word1=sync_word1, sync_word2=sync_word2)
+        self.occupied_carriers, self.pilot_carriers, self.pilot_symbols = occupied_carriers, pilot_carriers, pilot_symbols
+        self.sync_word1, self.sync_word2 = sync_word1, sync_word2
+        self.fft_len, self.cp_len = fft_len, fft_len // 4
+        self.len_ocup_carr = len(occupied_carriers[0])
+        self.active_carriers = len(occupied_carriers[0]) + 4
+
     # port 0 (bytes) in -> port 1 (samples) out
     def tx(self, packets):
         """-> (samples, sample offsets).  With filter_mode=1 (the reference default, :39) the burst stream runs

@@ -95,6 +95,13 @@ class OfdmPhy(object):
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
                  max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None,
                  max_pkt_bytes=4095, device=0, tx_clip=0.0, rolloff=0):
+        self._cfg = dict(fft_len=fft_len, cp_len=cp_len, occupied_carriers=occupied_carriers,
+                         pilot_carriers=pilot_carriers, pilot_symbols=pilot_symbols, sync_word1=sync_word1,
+                         sync_word2=sync_word2, bps_header=bps_header, bps_payload=bps_payload,
+                         scramble_bits=scramble_bits, scramble_header=scramble_header, crc_mode=crc_mode,
+                         threshold=threshold, max_carr_offset=max_carr_offset, alpha=alpha, tx_scale=tx_scale,
+                         demux_holdoff=demux_holdoff, max_pkt_bytes=max_pkt_bytes, device=device, tx_clip=tx_clip,
+                         rolloff=rolloff)
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occupied_carriers = [list(map(int, s)) for s in occupied_carriers]
         self.pilot_carriers = [list(map(int, s)) for s in pilot_carriers]
@@ -154,6 +161,27 @@ class OfdmPhy(object):
             _lib.check(L.ofdmx_create(C.byref(self.params), self.device, C.byref(h)))
             self._ctx = h
         return self._ctx
+
+    def reconfigure(self, **changes):
+        """Run-time reconfiguration: new constructor arguments -- typically the
+        occupied_carriers / pilot_carriers / pilot_symbols / sync_word1 / sync_word2 that
+        ofdm_cr_tools.spectrum_enforcer returns (python/ofdm_cr_tools.py:348-378,
+        python/cognitive_engine_mac.py:278-285) -- replace the PHY tables of the live context
+        (ofdmx_reconfigure); workspace, staging buffers, stream and counters are kept.  When the carrier plan
+        changes and no sync words are given they are regenerated as the constructor would."""
+        cfg = dict(self._cfg)
+        if any(k in changes for k in ("fft_len", "occupied_carriers", "pilot_carriers")):
+            cfg["sync_word1"] = cfg["sync_word2"] = None
+        cfg.update(changes)
+        if int(cfg["device"]) != self.device:
+            raise ValueError("reconfigure cannot move a context to another device")
+        fresh = OfdmPhy(**cfg)          # host-side validation and parameter block only (no context yet)
+        if self._ctx is not None:
+            _lib.check(_lib.load().ofdmx_reconfigure(C.byref(self._ctx), C.byref(fresh.params)), self._ctx)
+        ctx = self._ctx
+        self.__dict__.update(fresh.__dict__)
+        self._ctx = ctx
+        return self
 
     def close(self):
         if self._ctx is not None:

@@ -205,6 +205,14 @@ int ofdmx_iir_ccd(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n
  * out3_dev[0] = max|x|^2 / mean|x|^2, out3_dev[1] = max|x|^2, out3_dev[2] = mean|x|^2. */
 int ofdmx_papr(ofdmx_ctx *ctx, const float *in_dev, int64_t n, float *out3_dev, void *cuda_stream);
 
+/* Run-time reconfiguration: what cognitive_engine_mac does to the radios when
+ * spectrum_enforcer hands it a new carrier plan and sync words (python/cognitive_engine_mac.py:278-285,
+ * python/ofdm_cr_tools.py:348-378).  Replaces the PHY tables of *ctx_io by those of prm and keeps everything that
+ * does not depend on them (workspace, pinned staging buffers, private stream, profiling state, counters), so the
+ * next call runs without a new allocation.  Waits for the work already enqueued.  On success *ctx_io holds the
+ * (new) handle; on failure the old context is untouched and still valid. */
+int ofdmx_reconfigure(ofdmx_ctx **ctx_io, const ofdmx_params *prm);
+
 #ifdef __cplusplus
 }
 #endif

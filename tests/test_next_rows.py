@@ -472,3 +472,44 @@ def test_tx_rolloff_parity_and_loopback():
     assert tx.rolloff == 4 and tx.phy.frame_samples(96) == cm.make_phy(cm.cfg_c1()).frame_samples(96) + 3
     with pytest.raises(Exception):
         ofdm_tx(fft_len=64, cp_len=16, rolloff=17).work([b"abc"])
+
+
+@pytest.mark.gpu
+def test_runtime_reconfiguration():
+    """ofdm_radio_hier.reconfigure / OfdmPhy.reconfigure (ofdmx_reconfigure): the carrier plans spectrum_enforcer
+    derives for three spectrum masks (and a change of fft_len) applied to ONE live context; after every change
+    TX and RX equal a fresh oracle of that plan, the packet counter and the launch counter run on, the
+    workspace is kept, and a refused plan leaves the old one working."""
+    import torch
+    import oracle as O
+    from ofdm_tools import ofdm_radio_hier, ofdm_cr_tools as T
+    rng = np.random.default_rng(31)
+    radio = ofdm_radio_hier(payload_mod='qpsk', scramble_mode=1, crc_mode=1, filter_mode=0)
+    n0, launches = 0, 0
+    for fft_len, mask in ((128, []), (128, list(range(-30, -10))), (256, list(range(40, 90))), (128, [5, 6, 7, -50])):
+        occ, pil, pls, sw1, sw2 = T.spectrum_enforcer(fft_len, mask, 10)
+        radio.reconfigure(occ, pil, pls, sw1, sw2)
+        assert radio.phy.fft_len == fft_len and radio.phy.launch_count() >= launches
+        orc = O.Oracle(fft_len=fft_len, cp_len=fft_len // 4, occupied_carriers=occ, pilot_carriers=pil,
+                       pilot_symbols=pls, sync_word1=sw1, sync_word2=sw2, bps_header=1, bps_payload=2,
+                       scramble_bits=True, scramble_header=True, crc_mode=1, tx_scale=0.01, max_carr_offset=3)
+        pk = cm.rand_packets(rng, 5, 150)
+        s, off = radio.tx(pk)
+        so, oo = orc.tx(pk, first_pkt_num=n0)
+        n0 += len(pk)
+        s = s.cpu().numpy()
+        assert np.array_equal(off.cpu().numpy(), oo) and np.abs(s - so).max() <= 1e-5 * np.abs(so).max()
+        x = cm.channel(cm.split_frames(s, oo), rng, gaps=(400, 900), tail=2500, snr_db=40.0, cfo=0.2,
+                       fft_len=fft_len, scale=100.0)
+        res = radio.rx(torch.from_numpy(x).to(_dev()), agc=False)
+        ref = orc.rx(x, byte_stride=radio.phy.byte_stride, want_z=False)
+        assert np.array_equal(res.frames["trigger"], ref["frames"]["trigger"])
+        assert res.payloads() == orc.payloads(ref) == pk
+        launches = radio.phy.launch_count()
+        assert launches > 0
+    # a plan the library refuses: error raised, the live context keeps working with the old plan
+    with pytest.raises(Exception):
+        radio.phy.reconfigure(rolloff=1000)
+    s2, _ = radio.tx(pk)
+    so2, _ = orc.tx(pk, first_pkt_num=n0)
+    assert np.abs(s2.cpu().numpy() - so2).max() <= 1e-5 * np.abs(so2).max()

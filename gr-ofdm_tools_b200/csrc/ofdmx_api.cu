@@ -1102,34 +1102,31 @@ int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_stre
     return OFDMX_OK;
 }
 
-int64_t ofdmx_iir_state_doubles(void) { return 4 * (IIR_MAXT - 1); }
+int64_t ofdmx_iir_state_doubles(void) { return IIR_STATE_DOUBLES; }
 
-int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
-                  const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb, int64_t span,
-                  double *state_io_dev, void *stream)
+extern "C++" {
+template <int MAXT>
+static int iir_launch(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
+                      const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb, int64_t span,
+                      double *state_io_dev, cudaStream_t st)
 {
-    if (!c || !in_dev || !out_dev || !state_io_dev || !fftaps || n_streams < 0 || n < 0 || stride < n ||
-        n_streams > (1 << 24) || n_ff < 1 || n_ff > IIR_MAXT || n_fb < 0 || n_fb > IIR_MAXT || (n_fb > 0 && !fbtaps))
-        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_iir_ccd arguments (at most 9 feed-forward and 9 feedback taps)");
-    if (n_streams == 0 || n == 0) return OFDMX_OK;
-    if (int rc = check_device(c)) return rc;
-    iir_taps t;
-    for (int i = 0; i < IIR_MAXT; i++) {
+    iir_taps<MAXT> t;
+    for (int i = 0; i < MAXT; i++) {
         t.ff[i] = i < n_ff ? fftaps[i] : 0.0;
         t.fb[i] = (i >= 1 && i < n_fb) ? -fbtaps[i] : 0.0;   // oldstyle=False: a[k] enter with a minus sign
     }
     // warm-up length: where the impulse response has decayed below 1e-18 of its peak (host, double)
     int64_t warm = 0;
     {
-        double x[IIR_MAXT - 1] = { 0 }, y[IIR_MAXT - 1] = { 0 }, peak = 0.0;
+        double x[MAXT - 1] = { 0 }, y[MAXT - 1] = { 0 }, peak = 0.0;
         const int64_t cap = 1 << 20;
         int64_t last = 0;
         for (int64_t k = 0; k < cap; k++) {
             const double in = k == 0 ? 1.0 : 0.0;
             double acc = t.ff[0] * in;
-            for (int i = 1; i < IIR_MAXT; i++) acc += t.ff[i] * x[i - 1];
-            for (int i = 1; i < IIR_MAXT; i++) acc += t.fb[i] * y[i - 1];
-            for (int i = IIR_MAXT - 2; i > 0; i--) { x[i] = x[i - 1]; y[i] = y[i - 1]; }
+            for (int i = 1; i < MAXT; i++) acc += t.ff[i] * x[i - 1];
+            for (int i = 1; i < MAXT; i++) acc += t.fb[i] * y[i - 1];
+            for (int i = MAXT - 2; i > 0; i--) { x[i] = x[i - 1]; y[i] = y[i - 1]; }
             x[0] = in; y[0] = acc;
             const double a = std::fabs(acc);
             if (!(a < 1e300)) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: unstable filter");
@@ -1138,7 +1135,7 @@ int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_s
             if (k - last > 64) break;
         }
         if (last >= cap - 65) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: impulse response does not decay");
-        warm = last + 1 + (IIR_MAXT - 1);
+        warm = last + 1 + (MAXT - 1);
     }
     // span: caller's choice, else one full wave of lanes (12 resident warps per SM; the recurrence is a chain of
     // dependent double additions ~350 cycles per sample long, so more lanes is the only way to go faster until
@@ -1159,13 +1156,29 @@ int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_s
     const int64_t sps = (n + span - 1) / span;
     if (sps > (1 << 30)) return fail(c, OFDMX_ERR_PARAM, "ofdmx_iir_ccd: too many spans");
     const int64_t lanes = n_streams * sps;
-    cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((lanes + 32 * IIR_WARPS - 1) / (32 * IIR_WARPS));
     ofdmx_ctx *ctx_ = c;
-    { KT(K_IIR); iir_ccd_kernel<<<grid, IIR_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
-                                                        (int)sps, span, warm, t, state_io_dev); }
+    { KT(K_IIR); iir_ccd_kernel<MAXT><<<grid, IIR_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
+                                                              (int)sps, span, warm, t, state_io_dev); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
+}
+}  // extern "C++"
+
+int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
+                  const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb, int64_t span,
+                  double *state_io_dev, void *stream)
+{
+    if (!c || !in_dev || !out_dev || !state_io_dev || !fftaps || n_streams < 0 || n < 0 || stride < n ||
+        n_streams > (1 << 24) || n_ff < 1 || n_ff > 17 || n_fb < 0 || n_fb > 17 || (n_fb > 0 && !fbtaps))
+        return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_iir_ccd arguments (at most 17 feed-forward and 17 feedback taps)");
+    if (n_streams == 0 || n == 0) return OFDMX_OK;
+    if (int rc = check_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = std::max(n_ff, n_fb);
+    if (m <= 9) return iir_launch<9>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, st);
+    if (m <= 13) return iir_launch<13>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, st);
+    return iir_launch<17>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, st);
 }
 
 int ofdmx_papr(ofdmx_ctx *c, const float *in_dev, int64_t n, float *out3_dev, void *stream)

@@ -80,17 +80,21 @@ agc2_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n
 // poles at radius <= 0.985 next to z = -1: ~1e-10 relative in the double accumulator, measured: every float
 // within one ulp, 99.4 % identical).  Same 32 x 32 shared-memory
 // transpose as the AGC: rows are lanes, coalesced 256-byte row segments on the global side.
-// state_io[n_streams][4*(IIR_MAXT-1)] doubles: x[n-1..n-8] (re,im) then y[n-1..n-8] (re,im).
-#define IIR_MAXT 9
+// The kernel is a template of the tap capacity IIR_MAXT (9: the 8th-order filter of ofdm_radio_hier; 13: the
+// 12th-order one of sync_radio_hier, python/sync_radio_hier.py:66-67; 17) because the histories live in registers.
+// state_io[n_streams][IIR_STATE_DOUBLES] doubles: x[n-1..] (re,im pairs, IIR_MAXT-1 of them) then y[n-1..].
 #define IIR_WARPS 2
+#define IIR_STATE_DOUBLES 64
+template <int IIR_MAXT>
 struct iir_taps { double ff[IIR_MAXT]; double fb[IIR_MAXT]; };  // fb already negated, fb[0] unused; zero padded
 
 // Tiles travel global -> shared with 8-byte cp.async (no staging registers: the 32 history doubles and the
 // accumulators fill the register file), double buffered so the next tile is in flight while the recurrence
 // walks the current one.
+template <int IIR_MAXT>
 __global__ void __launch_bounds__(IIR_WARPS * 32)
 iir_ccd_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, long long stride, int n_streams,
-               int spans_per_stream, long long span, long long warm, const iir_taps taps,
+               int spans_per_stream, long long span, long long warm, const iir_taps<IIR_MAXT> taps,
                double *__restrict__ state_io)
 {
     __shared__ float2 tile[IIR_WARPS][2][32][33];
@@ -115,7 +119,7 @@ iir_ccd_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
 #pragma unroll
     for (int k = 0; k < IIR_MAXT - 1; k++) { xr[k] = xi[k] = yr[k] = yi[k] = 0.0; }
     if (beg == 0) {
-        const double *st = state_io + (long long)ms * (4 * (IIR_MAXT - 1));
+        const double *st = state_io + (long long)ms * IIR_STATE_DOUBLES;
 #pragma unroll
         for (int k = 0; k < IIR_MAXT - 1; k++) {
             xr[k] = st[2 * k]; xi[k] = st[2 * k + 1];
@@ -175,7 +179,7 @@ iir_ccd_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long lon
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // the lane that filtered the last sample of a stream leaves the history for the next call
     if (lane < nl && end == n) {
-        double *st = state_io + (long long)ms * (4 * (IIR_MAXT - 1));
+        double *st = state_io + (long long)ms * IIR_STATE_DOUBLES;
 #pragma unroll
         for (int k = 0; k < IIR_MAXT - 1; k++) {
             st[2 * k] = xr[k]; st[2 * k + 1] = xi[k];

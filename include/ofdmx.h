@@ -189,7 +189,8 @@ int ofdmx_agc2(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_st
 /* filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False), the out-of-band filter ofdm_radio_hier puts behind the
  * TX chain when filter_mode=1 (python/ofdm_radio_hier.py:83-84,93,232-237; python/sync_radio_hier.py:73,165):
  * complex float in/out, double taps, complex double accumulator, y[n] = sum ff[i] x[n-i] - sum_{j>=1} fb[j] y[n-j]
- * (fb[0] is not used, as in GNU Radio).  At most 9 + 9 taps (the reference filter is 8th order).  Each stream is
+ * (fb[0] is not used, as in GNU Radio).  At most 17 + 17 taps (the reference filters: 9 + 9 taps in
+ * ofdm_radio_hier, 13 + 13 in sync_radio_hier).  Each stream is
  * cut into spans of `span` samples (<= 0: chosen by the library) that run in parallel, each warmed up from a
  * zero state over the length the impulse response needs to fall below 1e-18 of its peak; the first span starts
  * from state_io and is bit-exact against the sequential filter, later spans agree to the round-off noise of the

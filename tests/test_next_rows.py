@@ -362,10 +362,10 @@ def test_iir_ccd_parity():
     y, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, span=1 << 20)
     ref, rst = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB)
     assert np.array_equal(y.cpu().numpy(), ref)
-    assert np.array_equal(st.cpu().numpy().ravel(), rst)
+    assert np.array_equal(st.cpu().numpy().ravel()[:32], rst)
     y2, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, state=st, span=1 << 20)     # continues the stream
     ref2, rst2 = O.iir_ccd(x, FORWARD_OOB, FEEDBACK_OOB, rst)
-    assert np.array_equal(y2.cpu().numpy(), ref2) and np.array_equal(st.cpu().numpy().ravel(), rst2)
+    assert np.array_equal(y2.cpu().numpy(), ref2) and np.array_equal(st.cpu().numpy().ravel()[:32], rst2)
     # parallel spans (explicit and library-chosen), ragged tail, carried state
     x = _cnoise(rng, 300001)
     xd = torch.from_numpy(x).to(_dev())
@@ -377,7 +377,7 @@ def test_iir_ccd_parity():
         assert np.abs(y - ref).max() <= 2.4e-7 * np.abs(ref).max()
         assert np.mean(y == ref) > 0.98
         assert np.array_equal(y[:1024], ref[:1024])                 # the first span is the sequential filter
-        assert np.abs(st.cpu().numpy().ravel() - rst).max() <= 1e-8 * np.abs(rst).max()
+        assert np.abs(st.cpu().numpy().ravel()[:32] - rst).max() <= 1e-8 * np.abs(rst).max()
         yb, st = phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, state=st, span=span)
         assert np.abs(yb.cpu().numpy() - refb).max() <= 2.4e-7 * np.abs(refb).max()
     # streams = rows of a wider matrix
@@ -386,14 +386,14 @@ def test_iir_ccd_parity():
     y, st = phy.iir_ccd(md[:, :5555], FORWARD_OOB, FEEDBACK_OOB, span=1 << 20)
     for r in range(37):
         rr, rs = O.iir_ccd(m[r, :5555], FORWARD_OOB, FEEDBACK_OOB)
-        assert np.array_equal(y[r].cpu().numpy(), rr) and np.array_equal(st[r].cpu().numpy(), rs)
+        assert np.array_equal(y[r].cpu().numpy(), rr) and np.array_equal(st[r].cpu().numpy()[:32], rs)
     y, _ = phy.iir_ccd(md[:, :5555], FORWARD_OOB, FEEDBACK_OOB, span=2048)
     assert np.abs(y.cpu().numpy() - np.stack([O.iir_ccd(m[r, :5555], FORWARD_OOB, FEEDBACK_OOB)[0] for r in range(37)])).max() < 1e-5
     # FIR only
     yf, _ = phy.iir_ccd(xd, [0.25, 0.5, 0.25], [1.0], span=0)
     assert np.array_equal(yf.cpu().numpy(), O.iir_ccd(x, [0.25, 0.5, 0.25], [1.0])[0])
     with pytest.raises(Exception):
-        phy.iir_ccd(xd, [1.0] * 10, FEEDBACK_OOB)
+        phy.iir_ccd(xd, [1.0] * 18, FEEDBACK_OOB)
     with pytest.raises(Exception):
         phy.iir_ccd(xd, FORWARD_OOB, FEEDBACK_OOB, span=1024, out=xd)
     with pytest.raises(Exception):
@@ -513,3 +513,44 @@ def test_runtime_reconfiguration():
     s2, _ = radio.tx(pk)
     so2, _ = orc.tx(pk, first_pkt_num=n0)
     assert np.abs(s2.cpu().numpy() - so2).max() <= 1e-5 * np.abs(so2).max()
+
+
+@pytest.mark.gpu
+def test_sync_radio_hier_facade():
+    """sync_radio_hier (python/sync_radio_hier.py:50-68): fft_len 64 narrow-band plan, QPSK, the 12th-order
+    iir_filter_ccd always behind the TX chain (13 + 13 taps: the 13-tap instantiation of the kernel, bit-exact in
+    its first span), AGC in front of the receiver.  TX equals oracle TX -> oracle IIR, RX equals oracle AGC -> RX,
+    and the filtered bursts decode."""
+    import torch
+    import oracle as O
+    from ofdm_tools import sync_radio_hier
+    rng = np.random.default_rng(17)
+    radio = sync_radio_hier()
+    g = cm.GOLD["sync_radio_hier"]
+    assert radio.fft_len == 64 and radio.cp_len == 16 and len(radio.forward_OOB) == len(radio.feedback_OOB) == 13
+    assert np.allclose(np.asarray(radio.sync_word1, np.complex64), np.array([complex(a, b) for a, b in g["sync_word1"]]))
+    orc = O.Oracle(fft_len=64, cp_len=16, occupied_carriers=radio.occupied_carriers, pilot_carriers=radio.pilot_carriers,
+                   pilot_symbols=radio.pilot_symbols, sync_word1=radio.sync_word1, sync_word2=radio.sync_word2,
+                   bps_header=1, bps_payload=2, scramble_bits=False, scramble_header=True, crc_mode=0, tx_scale=0.01,
+                   max_carr_offset=3)
+    x1 = (rng.standard_normal(4000) + 1j * rng.standard_normal(4000)).astype(np.complex64)
+    y, st = radio.phy.iir_ccd(torch.from_numpy(x1).to(_dev()), radio.forward_OOB, radio.feedback_OOB, span=1 << 20)
+    ref, rst = O.iir_ccd(x1, radio.forward_OOB, radio.feedback_OOB)
+    assert np.array_equal(y.cpu().numpy(), ref) and np.array_equal(st.cpu().numpy().ravel()[:48], rst)
+    st, n0 = None, 0
+    for call in range(2):
+        pk = cm.rand_packets(rng, 6, 40)
+        s, off = radio.tx(pk)
+        so, oo = orc.tx(pk, first_pkt_num=n0)
+        n0 += len(pk)
+        ref, st = O.iir_ccd(so, radio.forward_OOB, radio.feedback_OOB, st)
+        s = s.cpu().numpy()
+        assert np.array_equal(off.cpu().numpy(), oo) and np.abs(s - ref).max() <= 1e-5 * np.abs(ref).max()
+        x = cm.channel(cm.split_frames(s, oo), rng, gaps=(300, 700), tail=1500, snr_db=40.0, fft_len=64, scale=1.0)
+        radio._agc_gain = None
+        res = radio.rx(torch.from_numpy(x).to(_dev()))
+        want = orc.rx(O.agc2(x)[0], byte_stride=radio.phy.byte_stride, want_z=False)
+        assert np.array_equal(res.frames["trigger"], want["frames"]["trigger"])
+        assert res.payloads() == orc.payloads(want)
+        xs = cm.channel(cm.split_frames(s, oo), rng, gaps=(300, 700), tail=1500, snr_db=40.0, fft_len=64, scale=100.0)
+        assert radio.rx(torch.from_numpy(xs).to(_dev()), agc=False).payloads() == pk

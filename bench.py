@@ -363,7 +363,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks,
             "stats": {k: int(v) for k, v in summ.items() if k != "per_rank"},
         }
-        out["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline(args.ref_frames)
+        # the CPU port is timed on rank 0 at N=1 only (at N>1 the other ranks' host threads would compete with it)
+        out["cpu_baseline"] = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.ref_frames)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

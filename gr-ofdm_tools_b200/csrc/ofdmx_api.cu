@@ -1,5 +1,6 @@
 // ofdmx_api.cu -- C ABI (include/ofdmx.h) over the sm_100a kernels.  No CPU fallback: every
 // entry point needs a CUDA device and reports OFDMX_ERR_CUDA otherwise.
+#define OFDMX_GENERIC_KERNELS 1
 #include "ofdmx_kernels.cuh"
 #include "ofdmx_sync.cuh"
 #include "ofdmx_sync_tma.cuh"
@@ -9,6 +10,7 @@
 #include "ofdmx_sync_warp.cuh"
 #include "ofdmx_tx1024w.cuh"
 #include "ofdmx_chain.cuh"
+#include "ofdmx_launch.h"
 
 #include <algorithm>
 #include <cmath>
@@ -396,6 +398,54 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
 
 }  // namespace
 
+// dispatch over fft_len to the per-fft_len objects (ofdmx_k_framew.cu, ofdmx_k_txw.cu)
+cudaError_t ofdmx_fw_configure(int nfft, int bps, size_t smem, int threads, int *occ)
+{
+    switch (nfft) {
+    case 64: return ofdmx_fw_configure_64(bps, smem, threads, occ);
+    case 128: return ofdmx_fw_configure_128(bps, smem, threads, occ);
+    case 256: return ofdmx_fw_configure_256(bps, smem, threads, occ);
+    case 512: return ofdmx_fw_configure_512(bps, smem, threads, occ);
+    case 1024: return ofdmx_fw_configure_1024(bps, smem, threads, occ);
+    case 2048: return ofdmx_fw_configure_2048(bps, smem, threads, occ);
+    default: return cudaErrorInvalidValue;
+    }
+}
+bool ofdmx_fw_launch(int nfft, int bps, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, const FwArgs &a)
+{
+    switch (nfft) {
+    case 64: return ofdmx_fw_launch_64(bps, grid, threads, smem, st, a);
+    case 128: return ofdmx_fw_launch_128(bps, grid, threads, smem, st, a);
+    case 256: return ofdmx_fw_launch_256(bps, grid, threads, smem, st, a);
+    case 512: return ofdmx_fw_launch_512(bps, grid, threads, smem, st, a);
+    case 1024: return ofdmx_fw_launch_1024(bps, grid, threads, smem, st, a);
+    case 2048: return ofdmx_fw_launch_2048(bps, grid, threads, smem, st, a);
+    default: return false;
+    }
+}
+cudaError_t ofdmx_txw_configure(int nfft, int bps, size_t smem)
+{
+    switch (nfft) {
+    case 64: return ofdmx_txw_configure_64(bps, smem);
+    case 128: return ofdmx_txw_configure_128(bps, smem);
+    case 256: return ofdmx_txw_configure_256(bps, smem);
+    case 512: return ofdmx_txw_configure_512(bps, smem);
+    case 1024: return ofdmx_txw_configure_1024(bps, smem);
+    default: return cudaErrorInvalidValue;
+    }
+}
+bool ofdmx_txw_launch(int nfft, int bps, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, const TxwArgs &a)
+{
+    switch (nfft) {
+    case 64: return ofdmx_txw_launch_64(bps, grid, threads, smem, st, a);
+    case 128: return ofdmx_txw_launch_128(bps, grid, threads, smem, st, a);
+    case 256: return ofdmx_txw_launch_256(bps, grid, threads, smem, st, a);
+    case 512: return ofdmx_txw_launch_512(bps, grid, threads, smem, st, a);
+    case 1024: return ofdmx_txw_launch_1024(bps, grid, threads, smem, st, a);
+    default: return false;
+    }
+}
+
 // =============================================================================================
 extern "C" {
 
@@ -705,18 +755,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         if (N == 1024) {
             c->frame1k_warps = std::max(4, std::min(F1K_MAXW, 3 + kp.max_frame_syms));
             c->frame1k_smem = frame1024_smem_bytes(c->frame1k_warps, kp.n_occ_u, c->hl, kp.max_pkt_syms, kp.max_pkt_bytes);
-            cudaError_t e1 = cudaSuccess;
-#define F1K_ATTR(B, S, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_frame1024_kernel<B, S, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1k_smem); if (e2 != cudaSuccess) e1 = e2; }
-#define F1K_ATTR4(B) F1K_ATTR(B, true, false) F1K_ATTR(B, true, true) F1K_ATTR(B, false, false) F1K_ATTR(B, false, true)
-            switch (kp.bps_p) {
-            case 1: F1K_ATTR4(1) break;
-            case 2: F1K_ATTR4(2) break;
-            case 3: F1K_ATTR4(3) break;
-            case 4: F1K_ATTR4(4) break;
-            default: F1K_ATTR4(6) break;
-            }
-#undef F1K_ATTR4
-#undef F1K_ATTR
+            const cudaError_t e1 = ofdmx_f1k_configure(kp.bps_p, c->frame1k_smem);
             if (e1 != cudaSuccess)
                 return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(e1)));
         }
@@ -754,38 +793,15 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                           && c->hl >= 32 && c->hl <= 2048
                           && c->frame1kw_smem <= 227 * 1024;
             if (c->frame1kw) {
-                cudaError_t e1 = cudaSuccess;
                 int occ = 1;
-#define FW_ATTR1(NN, B, Z) { cudaError_t e2 = cudaFuncSetAttribute(rx_framew_kernel<NN, B, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame1kw_smem); if (e2 != cudaSuccess) e1 = e2; \
-                             if (!Z) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rx_framew_kernel<NN, B, Z>, c->frame1kw_warps * 32, c->frame1kw_smem); }
-#define FW_ATTR(B, Z) { if (N == 1024) FW_ATTR1(1024, B, Z) else if (N == 2048) FW_ATTR1(2048, B, Z) else if (N == 512) FW_ATTR1(512, B, Z) else if (N == 256) FW_ATTR1(256, B, Z) else if (N == 128) FW_ATTR1(128, B, Z) else FW_ATTR1(64, B, Z) }
-                switch (kp.bps_p) {
-                case 1: FW_ATTR(1, false) FW_ATTR(1, true) break;
-                case 2: FW_ATTR(2, false) FW_ATTR(2, true) break;
-                case 3: FW_ATTR(3, false) FW_ATTR(3, true) break;
-                case 4: FW_ATTR(4, false) FW_ATTR(4, true) break;
-                default: FW_ATTR(6, false) FW_ATTR(6, true) break;
-                }
-#undef FW_ATTR
-#undef FW_ATTR1
+                const cudaError_t e1 = ofdmx_fw_configure(N, kp.bps_p, c->frame1kw_smem, c->frame1kw_warps * 32, &occ);
                 c->frame1kw_ctas = std::max(1, occ);
                 if (e1 != cudaSuccess) c->frame1kw = false;
             }
         }
         if (c->tx1kw) {
             c->tx1kw_smem = txw_smem_bytes(N, kp.max_pkt_bytes, TXW_WARPS);
-            cudaError_t e1 = cudaSuccess;
-#define TXW_ATTR1(NN, B) { cudaError_t e2 = cudaFuncSetAttribute(tx_framew_kernel<NN, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx1kw_smem); if (e2 != cudaSuccess) e1 = e2; }
-#define TXW_ATTR(B) { if (N == 1024) TXW_ATTR1(1024, B) else if (N == 512) TXW_ATTR1(512, B) else if (N == 256) TXW_ATTR1(256, B) else if (N == 128) TXW_ATTR1(128, B) else TXW_ATTR1(64, B) }
-            switch (kp.bps_p) {
-            case 1: TXW_ATTR(1) break;
-            case 2: TXW_ATTR(2) break;
-            case 3: TXW_ATTR(3) break;
-            case 4: TXW_ATTR(4) break;
-            default: TXW_ATTR(6) break;
-            }
-#undef TXW_ATTR
-#undef TXW_ATTR1
+            const cudaError_t e1 = (c->tx1kw_smem <= 227 * 1024) ? ofdmx_txw_configure(N, kp.bps_p, c->tx1kw_smem) : cudaErrorInvalidValue;
             if (e1 != cudaSuccess || c->tx1kw_smem > 227 * 1024) c->tx1kw = false;
         }
         c->sync_tma_smem = sync_tma_smem_bytes(N);
@@ -928,48 +944,16 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     ofdmx_ctx *ctx_ = c;
     if (c->frame1kw && !c->force_generic && !c->no_warp_frame) {
         KT(K_FRAME1KW);
-#define FW_GO(NN, B) { if (z_out) rx_framew_kernel<NN, B, true><<<fwgrid, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(        \
-            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,                 \
-            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all);                             \
-        else rx_framew_kernel<NN, B, false><<<fwgrid, c->frame1kw_warps * 32, c->frame1kw_smem, st>>>(                         \
-            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,                 \
-            bytes_out, byte_stride, (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all); }
-#define FW_LAUNCH(B)                                                                                               \
-    do {                                                                                                           \
-        const unsigned fwgrid = (unsigned)(c->sm_count * c->frame1kw_ctas);                                                        \
-        if (c->kp.N == 1024) FW_GO(1024, B) else if (c->kp.N == 2048) FW_GO(2048, B) else if (c->kp.N == 512) FW_GO(512, B) else if (c->kp.N == 256) FW_GO(256, B)  \
-        else if (c->kp.N == 128) FW_GO(128, B) else FW_GO(64, B)                                \
-    } while (0)
-        switch (c->kp.bps_p) {
-        case 1: FW_LAUNCH(1); break;
-        case 2: FW_LAUNCH(2); break;
-        case 3: FW_LAUNCH(3); break;
-        case 4: FW_LAUNCH(4); break;
-        default: FW_LAUNCH(6); break;
-        }
-#undef FW_LAUNCH
-#undef FW_GO
+        FwArgs fa{ c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out, byte_stride,
+                   (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all };
+        if (!ofdmx_fw_launch(c->kp.N, c->kp.bps_p, (unsigned)(c->sm_count * c->frame1kw_ctas), c->frame1kw_warps * 32, c->frame1kw_smem, st, fa))
+            return fail(c, OFDMX_ERR_PARAM, "no warp-per-frame kernel for this configuration");
     } else if (c->frame1k_warps > 0 && !c->force_generic) {
         KT(K_FRAME1K);
-#define F1K_LAUNCH3(B, S, Z)                                                                                       \
-    rx_frame1024_kernel<B, S, Z><<<c->sm_count * 2, F1K_THREADS, c->frame1k_smem, st>>>(                           \
-        c->kp, c->frame1k_warps, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig,   \
-        w.spec, bytes_out, byte_stride, (float2 *)z_out, z_stride)
-#define F1K_LAUNCH(B)                                                                                              \
-    do {                                                                                                           \
-        if (simple) { if (z_out) F1K_LAUNCH3(B, true, true); else F1K_LAUNCH3(B, true, false); }                   \
-        else { if (z_out) F1K_LAUNCH3(B, false, true); else F1K_LAUNCH3(B, false, false); }                        \
-    } while (0)
         const bool simple = (c->kp.n_occ_sets == 1 && c->kp.n_pil_sets <= 1 && !c->kp.pil_in_occ);
-        switch (c->kp.bps_p) {
-        case 1: F1K_LAUNCH(1); break;
-        case 2: F1K_LAUNCH(2); break;
-        case 3: F1K_LAUNCH(3); break;
-        case 4: F1K_LAUNCH(4); break;
-        default: F1K_LAUNCH(6); break;
-        }
-#undef F1K_LAUNCH3
-#undef F1K_LAUNCH
+        F1kArgs fa{ c->kp, c->frame1k_warps, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,
+                    bytes_out, byte_stride, (float2 *)z_out, z_stride };
+        ofdmx_f1k_launch(c->kp.bps_p, simple, (unsigned)(c->sm_count * 2), c->frame1k_smem, st, fa);
     } else {
         KT(K_FRAME);
         rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
@@ -1030,18 +1014,10 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
         const unsigned grid = (unsigned)std::min<int64_t>((n_pkts + TXW_WARPS - 1) / TXW_WARPS, (int64_t)c->sm_count);
         const int pbb = (int)tx1024w_pb_bytes(c->kp.max_pkt_bytes);
         KT(K_TX1KW);
-#define TXW1(NN, B) tx_framew_kernel<NN, B><<<grid, TXW_WARPS * 32, c->tx1kw_smem, st>>>(c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts, \
-            first_pkt_num, (float2 *)samples_out, cap_samples, (const long long *)sample_off_dev, c->tx_map, c->sync_td, c->x_2048, pbb)
-#define TXW(B) { if (c->kp.N == 1024) TXW1(1024, B); else if (c->kp.N == 512) TXW1(512, B); else if (c->kp.N == 256) TXW1(256, B); else if (c->kp.N == 128) TXW1(128, B); else TXW1(64, B); }
-        switch (c->kp.bps_p) {
-        case 1: TXW(1); break;
-        case 2: TXW(2); break;
-        case 3: TXW(3); break;
-        case 4: TXW(4); break;
-        default: TXW(6); break;
-        }
-#undef TXW
-#undef TXW1
+        TxwArgs ta{ c->kp, payload_dev, (const long long *)pkt_off_dev, n_pkts, first_pkt_num, (float2 *)samples_out, cap_samples,
+                    (const long long *)sample_off_dev, c->tx_map, c->sync_td, c->x_2048, pbb };
+        if (!ofdmx_txw_launch(c->kp.N, c->kp.bps_p, grid, TXW_WARPS * 32, c->tx1kw_smem, st, ta))
+            return fail(c, OFDMX_ERR_PARAM, "no warp-per-packet TX kernel for this configuration");
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
         KT(K_TX);

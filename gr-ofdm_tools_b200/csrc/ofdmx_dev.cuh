@@ -159,7 +159,7 @@ __device__ __forceinline__ uint32_t gf2_mul(uint32_t a, uint32_t b)
 // by x^(8*bytes that follow); the XOR of all terms is the raw CRC.  The 0xFFFFFFFF initial value is
 // folded in by XOR-ing the first four message bytes with 0xFF.  Longer messages are processed in
 // 4096-byte super-chunks.
-__device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__restrict__ tab,
+static __device__ uint32_t crc32_block(const uint8_t *msg, int len, const uint32_t *__restrict__ tab,
                                 const uint32_t *__restrict__ powtab, uint32_t *scratch)
 {
     const int tid = threadIdx.x;

@@ -23,7 +23,7 @@
 
 // exact NCO phasor at item i (piecewise accumulation over the raw triggers); kept out of line: it is only
 // needed for the few samples that follow another trigger inside a frame
-__device__ __noinline__ float2 f1k_exact_phasor(long long i, int j, int jend, const long long *__restrict__ trig,
+static __device__ __noinline__ float2 f1k_exact_phasor(long long i, int j, int jend, const long long *__restrict__ trig,
                                                 const float *__restrict__ cfo)
 {
     double turns = nco_turns(i, j, jend, trig, cfo, 1024);

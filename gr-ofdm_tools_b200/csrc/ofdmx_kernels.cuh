@@ -23,6 +23,7 @@
 // the detect bits equal the oracle's exact evaluation).
 // =============================================================================================
 #define SYNC_T 2048
+#ifdef OFDMX_GENERIC_KERNELS   // the non-template kernels are compiled by ofdmx_api.cu only
 
 __device__ __forceinline__ int padi(int i, int ce) { return i + i / ce; }
 
@@ -315,6 +316,7 @@ cfo_kernel(const float2 *__restrict__ samples, long long n, long long stride, in
     (void)n;
 }
 
+#endif  // OFDMX_GENERIC_KERNELS
 // =============================================================================================
 // RX frame kernel: everything downstream of the trigger for one frame, in one CTA.
 // =============================================================================================
@@ -398,6 +400,7 @@ __device__ __forceinline__ void equalize_symbol(const float2 *buf, const KP &p, 
     }
 }
 
+#ifdef OFDMX_GENERIC_KERNELS   // the non-template kernels are compiled by ofdmx_api.cu only
 __global__ void __launch_bounds__(OFDMX_THREADS)
 rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, long long stride,
                 const long long *__restrict__ trig, const int *__restrict__ trig_stream,
@@ -797,3 +800,5 @@ crc32_kernel(const uint8_t *__restrict__ bytes, const long long *__restrict__ pk
         if (threadIdx.x == 0) crc_out[pk] = c;
     }
 }
+
+#endif  // OFDMX_GENERIC_KERNELS

@@ -1,14 +1,20 @@
 #!/usr/bin/env python3
-"""bench.py -- OFDM RX Msamples/s on BASELINE.json config[2] (the configuration the metric is quoted
-on): fft_len 1024, cp 72, 600 data carriers, 16-QAM, 1500-byte packets (+CRC-32, scrambler), CFO 0.3
-subcarriers + 4-tap multipath + AWGN, back-to-back frames, one stream per GPU.
+"""bench.py -- OFDM RX Msamples/s.  The headline is BASELINE.json configs[2] (the configuration the metric is
+quoted on): fft_len 1024, cp 72, 600 data carriers, 16-QAM, 1500-byte packets (+CRC-32, scrambler), CFO 0.3
+subcarriers + 4-tap multipath + AWGN 25 dB, 65 536 back-to-back frames, one stream per GPU.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun by the driver)
+  python bench.py --config {0,1,2,3,4} ...                 one BASELINE.json configuration at its stated size
   python bench.py --impl reference ...                     CPU arm: the oracle port of the GNU Radio chain
 
-A step = one pass of the full RX chain (sync -> ... -> CRC) over the rank's resident sample buffer
-(inputs far larger than L2).  `value` = samples of all ranks / max-over-ranks device time.  `e2e` = the
-same through ofdmx_rx_host with pinned HOST buffers (H2D + D2H inside the timed region).
+A step = one pass of the hot path (full RX chain sync -> ... -> CRC; configs[4]: the Schmidl & Cox stage alone)
+over the rank's resident sample buffer.  `value` = samples of all ranks / max-over-ranks device time of the K
+steps.  `e2e` = the same through the host-buffer call (H2D + D2H inside the timed region).  Every configuration
+carries a gate: the GPU result on a sub-sample must equal the oracle's on the same samples (trigger indices,
+flags, header fields, payload bytes), and size-independent properties hold at the full size.
+
+The default run (config 2, the line's top level) also measures the other four configurations at N=1 (key
+"configs"; skip with --headline-only) and, at N>1, configs[3] sharded over the ranks (key "config3").
 """
 import argparse
 import json
@@ -26,17 +32,39 @@ for _p in (os.path.join(ROOT, "gr-ofdm_tools_b200"), os.path.join(ROOT, "tests")
 import numpy as np  # noqa: E402
 
 METRIC = "OFDM RX Msamples/s (fft_len=1024, 16-QAM)"
-FRAME_SAMPLES = 9864            # (2 sync + 1 header + 6 payload symbols) x 1096
-FRAME_ALGO_BYTES = 8 * FRAME_SAMPLES + 1500 + 32   # samples once + payload + record
-SNR_DB = 40.0
-CFO = 0.3
-WORKLOAD = ("config[2]: fft_len=1024 cp=72 600 carriers 16-QAM 1500B+CRC32 scrambled, back-to-back frames, "
-            "CFO 0.3 + 4-tap multipath + AWGN %.0f dB, 1 stream/GPU" % SNR_DB)
+L2_BYTES = 126 * 1024 * 1024
 
 
-def phy_cfg():
+# ------------------------------------------------------------------------------------------------------------
+# The five configurations of BASELINE.json at the sizes SURVEY.md 8(d) states.
+def config_table():
     import common as cm
-    return cm.cfg_c3()
+    return {
+        0: dict(name="configs[0] ofdm_hier loopback", cfg=cm.cfg_c1(2, False, 0), fft_len=64, plen=96, streams=1,
+                frames=2000, gaps=(200, 2000), snr=20.0, cfo=0.0, taps=None, lead=600, tail=2400, scaling="weak",
+                gate_streams=1, ref_frames=2000,
+                workload="config[0]: fft_len=64 cp=16 802.11a carriers, BPSK header / QPSK payload, 96-byte packets, "
+                         "AWGN 20 dB, 2000 frames separated by 200-2000 zero samples, 1 stream"),
+        1: dict(name="configs[1] 4096 streams", cfg=cm.cfg_c1(2, False, 0), fft_len=64, plen=96, streams=4096,
+                frames=64, gaps=(200, 2000), snr=20.0, cfo=0.0, taps=None, lead=600, tail=2400, scaling="strong",
+                gate_streams=2, ref_frames=64 * 32,
+                workload="config[1]: fft_len=64 cp=16, QPSK, 96-byte packets, 4096 independent streams x 64 frames "
+                         "(gaps 200-2000), AWGN 20 dB"),
+        2: dict(name="configs[2] headline", cfg=cm.cfg_c3(), fft_len=1024, plen=1500, streams=1, frames=65536,
+                gaps=(0, 0), snr=25.0, cfo=0.3, taps=cm.MULTIPATH, lead=512, tail=4096, scaling="weak",
+                gate_frames=256, ref_frames=4096,
+                workload="config[2]: fft_len=1024 cp=72 600 carriers 16-QAM 1500B+CRC32 scrambled, back-to-back "
+                         "frames, CFO 0.3 + 4-tap multipath + AWGN 25 dB, 1 stream/GPU"),
+        3: dict(name="configs[3] 1024 streams 64-QAM", cfg=cm.cfg_c4(), fft_len=2048, plen=1500, streams=1024,
+                frames=256, gaps=(0, 0), snr=40.0, cfo=0.2, taps=None, lead=512, tail=4608, scaling="strong",
+                gate_streams=2, ref_frames=256,
+                workload="config[3]: fft_len=2048 cp=144 1200 carriers 64-QAM 1500B+CRC32, 1024 streams x 256 "
+                         "back-to-back frames sharded over the GPUs, CFO 0.2 + AWGN 40 dB"),
+        4: dict(name="configs[4] preamble search", cfg=cm.cfg_c3(), fft_len=1024, plen=1500, streams=1, frames=1000,
+                n_samples=1000000000, snr=10.0, snr2=16.0, scaling="weak", gate_samples=1 << 22, ref_samples=1 << 24,
+                workload="config[4]: Schmidl&Cox sync only over 1e9 samples of unit-variance complex noise with 1000 "
+                         "embedded config[2]-format frames at 10 dB (second pass: the same frames at 16 dB)"),
+    }
 
 
 def peaks():
@@ -45,6 +73,15 @@ def peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    """Host threads the CPU arm may use: the cores this process is allowed on (torchrun exports OMP_NUM_THREADS=1
+    to its workers; the reference arm sets the OpenMP team size explicitly instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler(object):
@@ -130,87 +167,510 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
-def make_stream(phy, n_frames, seed, dev):
-    """Synthetic input resident in HBM: GPU TX of random packets, then the channel (torch is only the
-    data generator here)."""
+# ------------------------------------------------------------------------------------------------------------
+# Synthetic inputs, generated on the GPU (torch is only the data generator here).
+def make_streams(phy, C, n_streams, seed, dev, stream0=0):
+    """n_streams rows of C['frames'] frames each: GPU TX of random packets, gaps, multipath, CFO, AWGN.
+    Returns (x [n_streams, L] complex64, payload uint8 [n_streams*frames*plen], frame start offsets int64
+    [n_streams, frames] relative to the row, frame length in samples)."""
+    import torch
+    F, plen, fft_len = C["frames"], C["plen"], C["fft_len"]
+    g = torch.Generator(device=dev).manual_seed(seed)
+    npk = n_streams * F
+    payload = torch.randint(0, 256, (npk * plen,), dtype=torch.uint8, device=dev, generator=g)
+    off = torch.arange(npk + 1, dtype=torch.int64, device=dev) * plen
+    FS = int(phy.frame_samples(plen))
+    s = torch.empty(npk * FS, dtype=torch.complex64, device=dev)
+    phy.tx((payload, off), out=s)
+    torch.cuda.synchronize()
+    s = s.view(n_streams, F, FS)
+    lo, hi = C["gaps"]
+    if hi > 0:
+        gaps = torch.randint(lo, hi + 1, (n_streams, F), device=dev, generator=g, dtype=torch.int64)
+        gaps[:, 0] = 0
+    else:
+        gaps = torch.zeros((n_streams, F), dtype=torch.int64, device=dev)
+    starts = C["lead"] + torch.cumsum(gaps, 1) + torch.arange(F, device=dev, dtype=torch.int64)[None, :] * FS
+    L = int(starts[:, -1].max()) + FS + C["tail"]
+    L = (L + 15) // 16 * 16                                  # 128-byte rows: every stream qualifies for the TMA / cp.async loads
+    x = torch.zeros((n_streams, L), dtype=torch.complex64, device=dev)
+    if hi == 0:
+        x[:, C["lead"]: C["lead"] + F * FS] = s.reshape(n_streams, F * FS)
+    else:
+        ar = torch.arange(FS, device=dev, dtype=torch.int64)
+        rows = torch.arange(n_streams, device=dev, dtype=torch.int64)[:, None]
+        for f in range(F):
+            x[rows, starts[:, f, None] + ar[None, :]] = s[:, f, :]
+    pw = float((s[: min(n_streams, 8)].abs() ** 2).mean())
+    del s
+    if C["taps"] is not None:
+        y = torch.zeros_like(x)
+        for d, v in C["taps"]:
+            y[:, d:] += x[:, : L - d] * complex(v)
+        x = y
+        del y
+    sig = float(np.sqrt(pw / 10 ** (C["snr"] / 10) / 2))
+    CW = 1 << 24                                             # CFO + AWGN in blocks of <= 16 M samples (bounded temporaries)
+    for c0 in range(0, L, CW):
+        c1 = min(c0 + CW, L)
+        rot = None
+        if C["cfo"]:
+            t = torch.arange(c0, c1, device=dev, dtype=torch.float64)
+            rot = torch.polar(torch.ones_like(t), 2 * np.pi * C["cfo"] / fft_len * t).to(torch.complex64)
+            del t
+        rows = max(1, CW // (c1 - c0))
+        for a in range(0, n_streams, rows):
+            b = min(a + rows, n_streams)
+            if rot is not None:
+                x[a:b, c0:c1] *= rot
+            x[a:b, c0:c1] += torch.view_as_complex(torch.randn(b - a, c1 - c0, 2, device=dev, generator=g) * sig)
+    return x, payload, starts, FS
+
+
+def make_search_stream(phy, C, seed, dev):
+    """config[4]: unit-variance complex Gaussian noise with C['frames'] config[2]-format frames added at drawn,
+    non-overlapping offsets.  Returns (x [n] complex64, offsets int64 numpy, frame waveform scaled to 0 dB SNR)."""
+    import torch
+    n, F = C["n_samples"], C["frames"]
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.empty(n, dtype=torch.complex64, device=dev)
+    for a in range(0, n, 1 << 25):
+        b = min(a + (1 << 25), n)
+        x[a:b] = torch.view_as_complex(torch.randn(b - a, 2, device=dev, generator=g) * float(np.sqrt(0.5)))
+    rng = np.random.default_rng(6)
+    payload = torch.from_numpy(rng.integers(0, 256, C["plen"], dtype=np.uint8)).to(dev)
+    off = torch.tensor([0, C["plen"]], dtype=torch.int64, device=dev)
+    fr, _ = phy.tx((payload, off), out=torch.empty(int(phy.frame_samples(C["plen"])), dtype=torch.complex64, device=dev))
+    torch.cuda.synchronize()
+    fr = fr / float(torch.sqrt((fr.abs() ** 2).mean()))       # unit power = 0 dB against the noise
+    FS = fr.numel()
+    # non-overlapping offsets: one frame per slot of n/F samples, at a drawn position inside it; the first four in the
+    # first gate_samples so that the oracle gate sees frames
+    slot = n // F
+    offs = np.arange(F, dtype=np.int64) * slot + rng.integers(2048, slot - FS - 4096, F)
+    k = min(4, F)
+    offs[:k] = np.sort(rng.choice(np.arange(4096, min(C["gate_samples"], k * slot) - 2 * FS, 2 * FS), k, replace=False))
+    return x, np.sort(offs), fr
+
+
+def add_frames(x, offs, fr, amp):
+    for o in offs:
+        x[int(o): int(o) + fr.numel()] += fr * float(amp)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def oracle_gate_rx(C, phy, x_rows, byte_stride):
+    """GPU == oracle on the given rows (each a whole stream or a prefix): triggers, flags, header fields, bytes."""
     import torch
     import common as cm
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    orc = cm.make_oracle(C["cfg"])
+    n_frames = n_crc = 0
+    for row in x_rows:
+        xr = row.contiguous()
+        res = phy.rx(xr)
+        ref = orc.rx(xr.cpu().numpy(), byte_stride=byte_stride, want_z=False)
+        rf, gf = ref["frames"], res.frames
+        assert len(gf) == len(rf), "gate: GPU %d frames, oracle %d" % (len(gf), len(rf))
+        for k in ("trigger", "pkt_len", "pkt_num", "frame_syms", "carr_offset"):
+            assert np.array_equal(gf[k].astype(np.int64), rf[k].astype(np.int64)), "gate: %s differs" % k
+        assert np.array_equal(gf["flags"] & 7, rf["flags"] & 7), "gate: flags differ"
+        sl = res.slots[torch.from_numpy(gf["slot"].astype(np.int64)).to(res.slots.device)].cpu().numpy()
+        for i in range(len(gf)):
+            nb = int(gf["pkt_len"][i])
+            assert np.array_equal(sl[i, :nb], ref["bytes"][i, :nb]), "gate: payload bytes of frame %d differ" % i
+        n_frames += len(gf)
+        n_crc += int(np.count_nonzero(gf["flags"] & 2))
+    return {"frames_compared": n_frames, "crc_ok": n_crc, "against": "oracle (orc_rx), records and payload bytes equal"}
+
+
+def time_steps(enqueue, steps, flush, barrier):
+    """K timed steps on the current stream.  Returns (ms of the whole bracket with the flushes taken out, per-step
+    ms list).  With `flush` (inputs smaller than L2) a buffer larger than L2 is rewritten between the steps."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for a, b in ev:
+        if flush is not None:
+            flush.add_(1)
+        a.record()
+        enqueue()
+        b.record()
+    barrier()
+    per = [a.elapsed_time(b) for a, b in ev]
+    if flush is None:
+        tot = ev[0][0].elapsed_time(ev[-1][1])
+    else:
+        tot = float(sum(per))
+    return tot, per
+
+
+def run_rx_config(cid, C, args, dev, world, rank, dist, clock_sampler=None, with_cpu=True):
+    """One RX configuration on this rank's share.  Returns the result dict (rank 0) or None."""
+    import torch
+    from ofdm_tools import OfdmPhy
+    from ofdm_tools import dist as odist
+    local = dev.index
+    n_streams_all = C["streams"]
+    if C["scaling"] == "strong":
+        mine = odist.shard_streams(n_streams_all, rank, world)
+        n_streams = len(mine)
+        seed = 1000 * cid + 17 + mine.start if n_streams else 0
+    else:
+        n_streams, seed = n_streams_all, 1000 * cid + 17 + rank
+    frames = args.frames if (cid == 2 and args.frames) else C["frames"]
+    C = dict(C, frames=frames)
+    max_pkt = C["plen"] + 4
+    phy = OfdmPhy(device=local, tx_scale=0.01, max_pkt_bytes=max_pkt, **C["cfg"])
+    x, payload, starts, FS = make_streams(phy, C, n_streams, seed, dev)
+    n = x.numel()
+    L = x.shape[1]
+    torch.cuda.synchronize()
+    max_frames = n_streams * frames + 64 * n_streams
+    bufs = phy.rx_buffers(max_frames, dev)
+    gathered = torch.zeros((world, 4), dtype=torch.int32, device=dev)
+    flush = torch.zeros(L2_BYTES * 2 // 4, dtype=torch.int32, device=dev) if 8 * n < 2 * L2_BYTES else None
+
+    def enqueue():
+        phy.rx_enqueue(x, bufs)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), bufs["counts"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        enqueue()
+    res = phy.rx_collect(bufs)
+    # ---- gates.  (1) full size, size-independent: every transmitted frame is found at its position, and every
+    # frame whose CRC-32 passes carries exactly the bytes that were sent (compared on the GPU over ALL frames)
+    fr = res.frames
+    assert len(fr) > 0, "no frame decoded"
+    st_idx = torch.from_numpy(fr["stream"].astype(np.int64)).to(dev)
+    trig = torch.from_numpy(fr["trigger"].astype(np.int64)).to(dev)
+    skey = (torch.arange(n_streams, device=dev, dtype=torch.int64)[:, None] * L + starts).reshape(-1)   # ascending
+    gidx = (torch.searchsorted(skey, st_idx * L + trig, right=True) - 1).clamp_(0, n_streams * frames - 1)
+    fidx = gidx % frames
+    dpos = st_idx * L + trig - skey[gidx]
+    want_lo, want_hi = C["fft_len"], C["fft_len"] + 2 * (phy.cp_len + 24)
+    located = (dpos >= want_lo) & (dpos <= want_hi)           # trigger ~ frame start + fft_len + cp/2 (+ channel delay)
+    n_found = int(torch.unique(gidx[located]).numel())
+    crc = torch.from_numpy((fr["flags"] & 2).astype(np.bool_)).to(dev) & located
+    slots = res.slots[torch.from_numpy(fr["slot"].astype(np.int64)).to(dev)][:, : C["plen"]]
+    sent = payload.view(n_streams * frames, C["plen"])[gidx]
+    same = (slots == sent).all(1)
+    n_crc_ok = int(crc.sum())
+    n_bad = int((crc & ~same).sum())
+    n_same = int((same & located).sum())
+    if phy.crc_mode:
+        assert n_bad == 0, "gate: %d frames pass the CRC-32 with bytes that differ from what was sent" % n_bad
+    else:
+        n_crc_ok = n_bad = None                               # no in-graph CRC in this configuration
+    min_found = 0.999 if C["snr"] >= 25.0 else 0.98
+    assert n_found >= min_found * n_streams * frames, "gate: found %d of %d frames" % (n_found, n_streams * frames)
+    gate = {"full_size": {"frames_sent": n_streams * frames, "frames_found": n_found, "records": int(len(fr)),
+                          "crc_ok": n_crc_ok, "crc_ok_with_wrong_bytes": n_bad, "payload_equal_to_sent": n_same}}
+    # (2) GPU == oracle on a sub-sample (rank 0)
+    if rank == 0:
+        if "gate_frames" in C:
+            k = min(C["gate_frames"], frames)
+            rows = [x[0, : C["lead"] + k * FS + 2 * (phy.fft_len + phy.cp_len)]]
+        else:
+            rows = [x[i] for i in range(min(C["gate_streams"], n_streams))]
+        gate["oracle"] = oracle_gate_rx(C, phy, rows, phy.byte_stride)
+
+    if clock_sampler is not None and rank == 0:
+        clock_sampler.start()
+    launches0 = phy.launch_count()
+    phy.profile(True)
+    ms, per = time_steps(enqueue, args.steps, flush, barrier)
+    clocks = clock_sampler.stop() if (clock_sampler is not None and rank == 0) else None
+    res = phy.rx_collect(bufs)
+    assert len(res.frames) == len(fr)
+    prof = phy.profile_read()
+    phy.profile(False)
+    launches = phy.launch_count() - launches0
+    t = torch.tensor([ms, float(launches), float(n), float(n_found), float(n_crc_ok or 0), float(n_streams * frames)]
+                     + [float(np.min(per)), float(np.median(per))], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, best, med = float(tmax[0]), float(tmax[6]), float(tmax[7])
+        launches, n_all = int(t[1]), int(t[2])
+        gate["full_size"].update(frames_sent=int(t[5]), frames_found=int(t[3]), crc_ok=int(t[4]) if phy.crc_mode else None)
+    else:
+        best, med, n_all = float(np.min(per)), float(np.median(per)), n
+    value = n_all * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through ofdmx_rx_host (pinned input), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(x.shape, dtype=torch.complex64, pin_memory=True)
+        xh.copy_(x)
+        xh_np = xh.numpy()
+        r = phy.rx_host(xh_np, max_frames=max_frames)       # warm (allocates the staging buffers)
+        assert len(r.frames) == len(fr)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r = phy.rx_host(xh_np, max_frames=max_frames)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        d2h = 16 + 32 * len(r.frames) + r.n_triggers * phy.byte_stride
+        e2e = {"value": n_all / float(te[0]) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n,
+               "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "h2d_gbs_per_rank": 8 * n / float(te[0]) / 1e9, "api": "ofdmx_rx_host (C ABI, pinned host input)"}
+        del xh, xh_np
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    tot_ms = sum(v[0] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_calls = prof[dom]
+    algo_frame = 8 * FS + C["plen"] + 32                     # SURVEY.md 8(d): samples once + payload + record
+    algo_chain = 8 * n + n_streams * frames * (C["plen"] + 32)
+    algo = algo_frame * n_streams * frames if dom.startswith("rx_frame") else 8 * n
+    achieved = algo / (dom_ms / dom_calls * 1e-3) / 1e9
+    traffic = None
+    try:   # dram bytes per algorithmic byte from the committed ncu --set full capture (headline kernels)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if cid == 2:
+            traffic = tr[dom]["dram_bytes_per_algorithmic_byte"] * algo
+    except Exception:
+        pass
+    out = {
+        "value": value, "unit": "Msamples/s", "ms_per_step": ms / args.steps, "best_ms": best, "median_ms": med,
+        "steps": args.steps, "scaling": C["scaling"],
+        "config": {"workload": C["workload"], "streams_this_rank": n_streams, "frames_per_stream": frames,
+                   "samples_this_rank": n,
+                   "l2": ("inputs (%.2f GB on this rank) larger than L2" % (8 * n / 1e9)) if flush is None
+                   else "inputs (%.0f MB) fit L2: a %d MB buffer is rewritten between the timed steps" % (8 * n / 1e6, 2 * L2_BYTES >> 20),
+                   "parallelism": "independent streams sharded over the ranks; per-rank frame counters all-gathered over NCCL"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel_share_of_step": dom_ms / tot_ms,
+                     "chain_frac": algo_chain * args.steps / (ms * 1e-3) / 1e9 / peak,
+                     "note": "achieved = algorithmic bytes of the kernel's launch / its mean CUDA-event duration; "
+                             "chain_frac = whole-RX algorithmic GB/s of this rank / peak"},
+        "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "gate": gate,
+    }
+    if with_cpu and world == 1:
+        out["cpu_baseline"] = cpu_baseline_rx(C, C["ref_frames"])
+    return out
+
+
+def run_sync_config(cid, C, args, dev, world, rank, dist):
+    """configs[4]: the Schmidl & Cox stage alone (ofdmx_sync) over 1e9 samples per GPU."""
+    import torch
+    import common as cm
+    from ofdm_tools import OfdmPhy
+    local = dev.index
+    n = args.search_samples or C["n_samples"]
+    C = dict(C, n_samples=n, frames=max(8, int(C["frames"] * n / C["n_samples"])))
+    phy = OfdmPhy(device=local, tx_scale=0.01, max_pkt_bytes=C["plen"] + 4, **C["cfg"])
+    x, offs, fr = make_search_stream(phy, C, 5 + rank, dev)
+    FS = fr.numel()
+    max_trig = 1 << 16
+    trig = torch.zeros(max_trig, dtype=torch.int64, device=dev)
+    cfo = torch.zeros(max_trig, dtype=torch.float32, device=dev)
+    st = torch.zeros(max_trig, dtype=torch.int32, device=dev)
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    from ofdm_tools import _lib
+    L = _lib.load()
+    import ctypes as Cc
+
+    def enqueue(xx=None):
+        xx = x if xx is None else xx
+        _lib.check(L.ofdmx_sync(phy.ctx, xx.data_ptr(), 1, xx.numel(), xx.numel(), trig.data_ptr(), cfo.data_ptr(),
+                                st.data_ptr(), max_trig, counts.data_ptr(),
+                                Cc.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), phy.ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def detections():
+        c = counts.cpu().numpy()
+        assert not c[2], "trigger overflow"
+        return trig[: int(c[0])].cpu().numpy()
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    orc = cm.make_oracle(C["cfg"])
+    passes = []
+    amp_prev = 0.0
+    for snr in (C["snr"], C["snr2"]):
+        amp = float(np.sqrt(10 ** (snr / 10)))
+        add_frames(x, offs, fr, amp - amp_prev)
+        amp_prev = amp
+        torch.cuda.synchronize()
+        for _ in range(args.warmup):
+            enqueue()
+        det = detections()
+        # property at full size: which embedded frames have a trigger at their preamble (start + fft_len + cp/2 +- cp)
+        exp = offs + C["fft_len"] + phy.cp_len // 2
+        j = np.searchsorted(det, exp - phy.cp_len)
+        hit = (j < len(det)) & (np.abs(det[np.minimum(j, max(len(det) - 1, 0))] - exp) <= phy.cp_len) if len(det) else np.zeros(len(exp), bool)
+        # oracle gate on the first gate_samples (they hold four of the frames)
+        g = min(C["gate_samples"], n)
+        enqueue(x[:g])
+        dg = detections()
+        rt, _ = orc.sync(x[:g].cpu().numpy())
+        assert np.array_equal(dg, rt), "gate: detection indices differ from the oracle on the first %d samples" % g
+        enqueue()
+        passes.append({"snr_db": snr, "detections": int(len(det)), "embedded_frames": int(len(offs)),
+                       "embedded_frames_detected": int(hit.sum()), "other_detections": int(len(det) - hit.sum()),
+                       "oracle_gate": {"samples": int(g), "detections_compared": int(len(rt)), "equal": True}})
+    phy.profile(True)
+    launches0 = phy.launch_count()
+    ms, per = time_steps(enqueue, args.steps, None, barrier)
+    prof = phy.profile_read()
+    phy.profile(False)
+    launches = phy.launch_count() - launches0
+    t = torch.tensor([ms, float(launches), float(np.min(per)), float(np.median(per))], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(t[1])
+        t = tmax
+    value = n * world * args.steps / (ms * 1e-3) / 1e6
+    # e2e: pinned host samples -> device -> ofdmx_sync -> detections back on the host
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(n, dtype=torch.complex64, pin_memory=True)
+        xh.copy_(x)
+        xd = torch.empty_like(x)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.e2e_steps // 2)):
+            xd.copy_(xh, non_blocking=True)
+            enqueue(xd)
+            d = detections()
+        e2e_s = (time.perf_counter() - t0) / max(1, args.e2e_steps // 2)
+        e2e = {"value": n * world / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n,
+               "d2h_bytes_per_step": 16 + 8 * len(d), "api": "OfdmPhy.sync path: pinned host -> device copy + ofdmx_sync + triggers to host"}
+        del xh, xd
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_calls = prof[dom]
+    achieved = 8 * n / (dom_ms / dom_calls * 1e-3) / 1e9
+    out = {
+        "value": value, "unit": "Msamples/s", "ms_per_step": ms / args.steps, "best_ms": float(t[2]), "median_ms": float(t[3]),
+        "steps": args.steps, "scaling": "weak",
+        "config": {"workload": C["workload"], "samples_per_gpu": n, "l2": "inputs (%.1f GB/GPU) larger than L2" % (8 * n / 1e9),
+                   "note": "S&C needs (S/(S+N))^2 >= 0.9, i.e. > 12.8 dB SNR: at the 10 dB the configuration states the "
+                           "reference's detector (threshold 0.9) finds almost none of the frames, as the oracle confirms; the "
+                           "second pass embeds the same frames at 16 dB"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel_share_of_step": dom_ms / sum(v[0] for v in prof.values()),
+                     "chain_frac": 8 * n * args.steps / (ms * 1e-3) / 1e9 / peak},
+        "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+        "e2e": e2e, "gpu_launches": launches, "gate": {"passes": passes},
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline_sync(C, x[: min(n, C["ref_samples"])].cpu().numpy())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's GNU Radio chain, on all host threads
+def ref_stream(C, n_frames, seed=1):
+    import common as cm
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    orc = cm.make_oracle(C["cfg"])
     rng = np.random.default_rng(seed)
-    payload = torch.from_numpy(rng.integers(0, 256, n_frames * 1500, dtype=np.uint8)).to(dev)
-    off = torch.arange(n_frames + 1, dtype=torch.int64, device=dev) * 1500
-    s, soff = phy.tx((payload, off))
-    assert int(soff[-1]) == n_frames * FRAME_SAMPLES
-    lead, tail = 512, 4096
-    x = torch.zeros(lead + s.numel() + tail, dtype=torch.complex64, device=dev)
-    for d, v in cm.MULTIPATH:                      # 4-tap multipath
-        x[lead + d: lead + d + s.numel()] += s * complex(v)
-    del s
-    chunk = 1 << 24
-    g = torch.Generator(device=dev).manual_seed(seed + 1)
-    pw = 0.0
-    for a in range(0, x.numel(), chunk):           # CFO + AWGN in chunks (bounded temporaries)
-        b = min(a + chunk, x.numel())
-        t = torch.arange(a, b, device=dev, dtype=torch.float64)
-        x[a:b] *= torch.polar(torch.ones_like(t), 2 * np.pi * CFO / 1024 * t).to(torch.complex64)
-        if a == 0:
-            pw = float((x[lead:b].abs() ** 2).mean())
-        sig = float(np.sqrt(pw / 10 ** (SNR_DB / 10) / 2))
-        x[a:b] += torch.view_as_complex(torch.randn(b - a, 2, device=dev, generator=g) * sig)
-    return x, payload
+    pk = cm.rand_packets(rng, n_frames, C["plen"])
+    s, off = orc.tx(pk)
+    x = cm.channel(cm.split_frames(s, off), rng, gaps=C["gaps"], lead=C["lead"], tail=C["tail"], snr_db=C["snr"],
+                   cfo=C["cfo"], fft_len=C["fft_len"], taps=C["taps"])
+    return orc, x
+
+
+def cpu_baseline_rx(C, n_frames):
+    import oracle as O
+    orc, x = ref_stream(C, n_frames)
+    threads = O.set_threads(host_threads())
+    bs = (C["plen"] + 4 + 15) // 16 * 16
+    orc.rx_baseline(x[: max(len(x) // 16, 4096)], byte_stride=bs)     # warm
+    t0 = time.perf_counter()
+    r = orc.rx_baseline(x, byte_stride=bs)
+    dt = time.perf_counter() - t0
+    return {"value": len(x) / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": "%d frames (%d samples) of the same workload, %d decoded, %.2f s; float32 FIR sync as GNU Radio "
+                      "evaluates it + per-trigger demodulation, OpenMP over %d threads" % (n_frames, len(x), len(r), dt, threads)}
+
+
+def cpu_baseline_sync(C, x):
+    import oracle as O
+    import common as cm
+    orc = cm.make_oracle(C["cfg"])
+    threads = O.set_threads(host_threads())
+    orc.sync(x[: 1 << 18], f32=True)
+    t0 = time.perf_counter()
+    tr, _ = orc.sync(x, f32=True)
+    dt = time.perf_counter() - t0
+    return {"value": len(x) / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": "first %d samples of the same stream, %d detections, %.2f s; float32 FIR port of ofdm_sync_sc_cfb, "
+                      "OpenMP over %d threads" % (len(x), len(tr), dt, threads)}
 
 
 def run_reference(args):
-    """CPU arm: the oracle port of the reference's GNU Radio chain (float32 FIR sync as GNU Radio
-    evaluates it + the demod chain), all host threads, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import common as cm
-    cfg = phy_cfg()
-    orc = cm.make_oracle(cfg)
-    rng = np.random.default_rng(1)
-    n_frames = args.ref_frames
-    pk = cm.rand_packets(rng, n_frames, 1500)
-    s, off = orc.tx(pk)
-    x = cm.channel(cm.split_frames(s, off), rng, gaps=(0, 0), lead=512, tail=4096, snr_db=SNR_DB, cfo=CFO,
-                   fft_len=1024, taps=cm.MULTIPATH)
-    cores = os.cpu_count() or 1
+    import oracle as O
+    C = config_table()[args.config]
+    threads = O.set_threads(host_threads())
+    if args.config == 4:
+        import common as cm
+        orc = cm.make_oracle(C["cfg"])
+        rng = np.random.default_rng(5)
+        n = args.ref_samples
+        x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2)).astype(np.complex64)
+        pk = cm.rand_packets(rng, 1, C["plen"])
+        s, _ = orc.tx(pk)
+        s = s / np.sqrt(np.mean(np.abs(s) ** 2)) * np.sqrt(10 ** (C["snr2"] / 10))
+        for o in range(100000, n - len(s), n // 4):
+            x[o:o + len(s)] += s
+        run = lambda: len(orc.sync(x, f32=True)[0])
+        sample = "%d samples of noise with embedded frames per step" % n
+    else:
+        n_frames = args.ref_frames or C["ref_frames"]
+        orc, x = ref_stream(C, n_frames)
+        bs = (C["plen"] + 4 + 15) // 16 * 16
+        run = lambda: len(orc.rx_baseline(x, byte_stride=bs))
+        sample = "%d frames (%d samples) of the workload per step" % (n_frames, len(x))
     for _ in range(args.warmup):
-        orc.rx_baseline(x, byte_stride=1520)
+        run()
     t0 = time.perf_counter()
     nf = 0
     for _ in range(args.steps):
-        nf += len(orc.rx_baseline(x, byte_stride=1520))
+        nf += run()
     dt = time.perf_counter() - t0
     val = len(x) * args.steps / dt / 1e6
-    sample = "%d back-to-back frames (%d samples) per step" % (n_frames, len(x))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC if args.config == 2 else "OFDM RX Msamples/s (%s)" % C["name"],
+        "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "what": "CPU restatement of the GNU Radio chain (oracle port; GNU Radio itself is not installable here)"},
-        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": C["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": C["workload"],
+                   "what": "CPU restatement of the GNU Radio chain (oracle port; GNU Radio itself is not installable here): "
+                           "float32 FIR Schmidl&Cox + per-trigger demodulation, OpenMP over all host threads"},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "frames_decoded_per_step": nf // max(1, args.steps),
+        "results_per_step": nf // max(1, args.steps),
     }))
-
-
-def cpu_baseline(ref_frames):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import common as cm
-    orc = cm.make_oracle(phy_cfg())
-    rng = np.random.default_rng(1)
-    pk = cm.rand_packets(rng, ref_frames, 1500)
-    s, off = orc.tx(pk)
-    x = cm.channel(cm.split_frames(s, off), rng, gaps=(0, 0), lead=512, tail=4096, snr_db=SNR_DB, cfo=CFO,
-                   fft_len=1024, taps=cm.MULTIPATH)
-    orc.rx_baseline(x[: 20 * FRAME_SAMPLES], byte_stride=1520)     # warm
-    t0 = time.perf_counter()
-    r = orc.rx_baseline(x, byte_stride=1520)
-    dt = time.perf_counter() - t0
-    return {"value": len(x) / dt / 1e6, "unit": "Msamples/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "%d back-to-back frames (%d samples), %d decoded, %.1f s" % (ref_frames, len(x), len(r), dt)}
 
 
 def main():
@@ -219,10 +679,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=65536, help="frames per GPU (65536 = 646 M samples = 5.2 GB)")
-    ap.add_argument("--ref-frames", type=int, default=1024, help="frames in the CPU baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[0, 1, 2, 3, 4], help="BASELINE.json configs[i]; 2 = the headline")
+    ap.add_argument("--frames", type=int, default=0, help="config 2 only: frames per GPU (default 65536 = 646 M samples = 5.2 GB)")
+    ap.add_argument("--search-samples", type=int, default=0, help="config 4 only: samples per GPU (default 1e9)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames in the CPU sample (default: per configuration)")
+    ap.add_argument("--ref-samples", type=int, default=1 << 23, help="--impl reference --config 4: samples per step")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="do not measure the other configurations next to the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -230,8 +695,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from ofdm_tools import OfdmPhy
-    from ofdm_tools import dist as odist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,130 +704,42 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    phy = OfdmPhy(device=local, tx_scale=0.01, max_pkt_bytes=1504, **phy_cfg())
-    x, payload = make_stream(phy, args.frames, seed=1000 + rank, dev=dev)
-    n = x.numel()
-    max_frames = args.frames + 64
-    torch.cuda.synchronize()
-
-    bufs = phy.rx_buffers(max_frames, dev)
-    gathered = torch.zeros((world, 4), dtype=torch.int32, device=dev)
-
-    def enqueue():
-        """One step, launch only: the RX chain, then the per-rank frame counters all-gathered over
-        NCCL (the only collective on this path).  No host synchronisation inside the timed region."""
-        phy.rx_enqueue(x, bufs)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), bufs["counts"])
-
-    def step():
-        enqueue()
-        res = phy.rx_collect(bufs)
-        summ = odist.summarize(res, n)
-        if world > 1:
-            summ = odist.gather_stats(summ, dev)
-        return res, summ
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        res, summ = step()
-    # correctness gate: every frame decoded, CRC ok, payload identical to what was sent
-    assert len(res.frames) == args.frames, "decoded %d of %d frames" % (len(res.frames), args.frames)
-    assert bool(np.all(res.frames["flags"] & 2)), "CRC failures in the bench stream"
-    slots = res.slots[res.frames["slot"][:64].astype(np.int64)].cpu().numpy()[:, :1500]
-    assert np.array_equal(slots.reshape(-1), payload[: 64 * 1500].cpu().numpy()), "payload mismatch"
-
+    table = config_table()
+    C = table[args.config]
     sampler = ClockSampler(local)
-    launches0 = phy.launch_count()
-    phy.profile(True)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        enqueue()
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    res = phy.rx_collect(bufs)
-    summ = odist.summarize(res, n)
-    if world > 1:
-        summ = odist.gather_stats(summ, dev)
-    assert len(res.frames) == args.frames and bool(np.all(res.frames["flags"] & 2))
-    prof = phy.profile_read()
-    phy.profile(False)
-    launches = phy.launch_count() - launches0
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms, launches = float(tmax[0]), int(t[1])
-    total_samples = n * world * args.steps
-    value = total_samples / (ms * 1e-3) / 1e6
+    with_cpu = not args.no_cpu_baseline
 
-    # ---- e2e: host buffers through ofdmx_rx_host (pinned input), H2D + D2H inside the timed region
-    xh = torch.empty(n, dtype=torch.complex64, pin_memory=True)
-    xh.copy_(x)
-    xh_np = xh.numpy()
-    r = phy.rx_host(xh_np, max_frames=max_frames)       # warm (allocates the staging buffers)
-    assert len(r.frames) == args.frames
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        r = phy.rx_host(xh_np, max_frames=max_frames)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = n * world / float(te[0]) / 1e6
-    d2h = 16 + 32 * len(r.frames) + r.n_triggers * phy.byte_stride
+    def one(cid, sampler=None, with_cpu=True):
+        torch.cuda.empty_cache()
+        if cid == 4:
+            return run_sync_config(cid, table[cid], args, dev, world, rank, dist)
+        return run_rx_config(cid, table[cid], args, dev, world, rank, dist, clock_sampler=sampler, with_cpu=with_cpu)
 
+    head = one(args.config, sampler, with_cpu)
+    extra = {}
+    if args.config == 2 and not args.headline_only:
+        # the other configurations next to the headline: all of them on one GPU, the sharded one on N GPUs
+        saved = (args.steps, args.e2e_steps)
+        args.steps, args.e2e_steps = min(args.steps, 10), min(args.e2e_steps, 3)
+        for cid in ((0, 1, 3, 4) if world == 1 else (3,)):
+            try:
+                r = one(cid, None, with_cpu)
+            except Exception as e:           # a side measurement must not take the headline down
+                r = {"error": "%s: %s" % (type(e).__name__, e)} if rank == 0 else None
+            if rank == 0:
+                extra[str(cid)] = r
+        args.steps, args.e2e_steps = saved
     if rank == 0:
-        peak, peak_src = peaks()
-        tot_ms = sum(v[0] for v in prof.values())
-        dom = max(prof, key=lambda k: prof[k][0])
-        dom_ms, dom_calls = prof[dom]
-        # algorithmic bytes one launch of the dominant kernel is responsible for (DESIGN.md):
-        # the frame kernel: 80 444 B per frame; the sync kernel: 8 B per sample.
-        algo = FRAME_ALGO_BYTES * args.frames if dom.startswith("rx_frame") else 8 * n
-        achieved = algo / (dom_ms / dom_calls * 1e-3) / 1e9
-        traffic = None
-        try:   # dram bytes per algorithmic byte from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tr[dom]["dram_bytes_per_algorithmic_byte"] * algo
-        except Exception:
-            pass
-        chain_gbs = (8 * n + args.frames * (1500 + 32)) * world * args.steps / (ms * 1e-3) / 1e9
-        out = {
-            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": args.frames, "samples_per_gpu": n,
-                       "l2": "inputs (%.1f GB/GPU) larger than L2" % (8 * n / 1e9),
-                       "parallelism": "independent streams sharded 1/GPU; per-frame stats all-gathered over NCCL"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_share_of_step": dom_ms / tot_ms,
-                         "chain_frac": chain_gbs / world / peak,
-                         "note": "achieved = algorithmic bytes of the kernel's launch / its mean CUDA-event duration; "
-                                 "chain_frac = whole-RX algorithmic GB/s per GPU / peak"},
-            "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
-            "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": int(d2h),
-                    "api": "ofdmx_rx_host (C ABI, pinned host input)"},
-            "gpu_launches": launches, "clocks": clocks,
-            "stats": {k: int(v) for k, v in summ.items() if k != "per_rank"},
-        }
-        # the CPU port is timed on rank 0 at N=1 only (at N>1 the other ranks' host threads would compete with it)
-        out["cpu_baseline"] = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.ref_frames)
+        out = {"metric": METRIC if args.config == 2 else "OFDM RX Msamples/s (%s)" % C["name"],
+               "value": head["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": head["ms_per_step"], "best_ms": head["best_ms"], "median_ms": head["median_ms"],
+               "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        for k in ("config", "roofline", "kernels_ms_per_step", "e2e", "gpu_launches", "clocks", "gate", "cpu_baseline"):
+            out[k] = head.get(k)
+        if "clocks" not in head or head.get("clocks") is None:
+            out["clocks"] = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if extra:
+            out["configs"] = extra
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

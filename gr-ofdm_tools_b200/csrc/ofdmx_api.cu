@@ -37,7 +37,7 @@ enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
              K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
-    "sync_metric_kernel", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
+    "(unused)", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
     "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel" };
@@ -50,6 +50,7 @@ struct ofdmx_ctx {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[K_NSLOTS] = {0};
     int64_t prof_calls[K_NSLOTS] = {0};
+    int64_t prof_errors = 0;        // event create / record failures since ofdmx_profile(ctx, 1)
     int device = 0;
     int sm_count = 148;
     ofdmx_params prm{};
@@ -61,6 +62,8 @@ struct ofdmx_ctx {
     int hl = 0;
     // workspace
     DevBuf ws;
+    DevBuf ws_host;                 // workspace of ofdmx_rx_host (runs on own_stream, concurrently with the caller's stream)
+    DevBuf ws_papr;                 // partial sums of ofdmx_papr (may run on another stream than an RX call in flight)
     int64_t launches = 0;
     // host-buffer path
     DevBuf h_samples, h_frames, h_bytes, h_counts;
@@ -144,18 +147,27 @@ struct KTimer {
         ctx->launches++;
         if (!on) return;
         auto get = [&]() {
-            cudaEvent_t e;
+            cudaEvent_t e = nullptr;
             if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
-            else cudaEventCreate(&e);
+            else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
             return e;
         };
         r.slot = slot; r.a = get(); r.b = get();
-        cudaEventRecord(r.a, st);
+        // a failed event creation / record drops this sample (and is reported by ofdmx_profile_read) rather than
+        // timing garbage
+        if (!r.a || !r.b || cudaEventRecord(r.a, st) != cudaSuccess) { drop(); on = false; }
+    }
+    void drop()
+    {
+        if (r.a) c->prof_pool.push_back(r.a);
+        if (r.b) c->prof_pool.push_back(r.b);
+        c->prof_errors++;
+        (void)cudaGetLastError();
     }
     ~KTimer()
     {
         if (!on) return;
-        cudaEventRecord(r.b, st);
+        if (cudaEventRecord(r.b, st) != cudaSuccess) { drop(); return; }
         c->prof_pending.push_back(r);
     }
 };
@@ -168,8 +180,9 @@ inline int shifted_bin(int c, int n)
 }
 
 // _get_constellation(bps) (python/ofdm_txrx_modules.py:106-118); 6 = 64-QAM by the same qam.py rule
-bool make_constellation(int bps, std::vector<float2> &pts, std::vector<uint8_t> &lut)
+bool make_constellation(int bps, int qam_norm, std::vector<float2> &pts, std::vector<uint8_t> &lut, float *inv_w)
 {
+    *inv_w = 1.0f;
     pts.clear();
     lut.assign(64, 0);
     if (bps == 1) {
@@ -208,6 +221,16 @@ bool make_constellation(int bps, std::vector<float2> &pts, std::vector<uint8_t> 
                 }
                 lut[rs * side + is] = (uint8_t)best;
             }
+        // [UPSTREAM constellation.cc, GNU Radio >= 3.8] constellation_rect(..., AMPLITUDE_NORMALIZATION): the points
+        // and the sector widths are scaled by n / sum |p| (3.7, the reference's generation, has no such step)
+        double scale = 1.0;
+        if (qam_norm == 1) {
+            double sum = 0.0;
+            for (auto &v : pts) sum += std::sqrt((double)v.x * v.x + (double)v.y * v.y);
+            scale = (double)m / sum;
+            for (auto &v : pts) v = make_float2((float)(v.x * scale), (float)(v.y * scale));
+        }
+        *inv_w = (float)(1.0 / (w * scale));
     } else {
         return false;
     }
@@ -355,7 +378,7 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         KT(K_SYNC_WARP);
         sync_metric_warp_kernel<<<grid, SW_WARPS * 32, SW_WARPS * SW_RING_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr,
                                                                                       w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total);
-    } else if (kp.N >= 32 && !ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
+    } else if (!ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
         // TMA path: 3-D map {32 floats, rows of 16 samples, streams}; whole rows only (the kernel patches the tail)
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
         const long long spans = (tiles + ST_SPAN_TILES - 1) / ST_SPAN_TILES;
@@ -364,7 +387,7 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         KT(K_SYNC_TMA);
         sync_metric_tma_kernel<<<grid, SV_THREADS, ctx->sync_tma_smem, st>>>(tmap, samples, n_samples, stride, kp.N, (float)kp.thr,
                                                                               kp.thr, w.detmask, w.trigmask, w.wps, tiles, spans, total);
-    } else if (kp.N >= 32) {
+    } else {
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
         dim3 grid((unsigned)tiles, (unsigned)n_streams);
         KT(K_SYNC_FAST);
@@ -377,12 +400,6 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         default: SVF(0); break;
         }
 #undef SVF
-    } else {
-        const long long tiles = (n_samples + SYNC_T - 1) / SYNC_T;
-        dim3 grid((unsigned)tiles, (unsigned)n_streams);
-        CUDA_TRY(ctx, cudaMemsetAsync(w.trigmask, 0, sizeof(uint32_t) * (size_t)w.n_words, st));
-        KT(K_SYNC);
-        sync_metric_kernel<<<grid, OFDMX_THREADS, ctx->sync_smem, st>>>(samples, n_samples, stride, kp.N, kp.thr, w.detmask, w.wps);
     }
     const long long pb = (w.n_words + OFDMX_THREADS * PL_WPT - 1) / (OFDMX_THREADS * PL_WPT);
     { KT(K_PLATEAU); plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp,
@@ -450,6 +467,8 @@ bool ofdmx_txw_launch(int nfft, int bps, unsigned grid, unsigned threads, size_t
 extern "C" {
 
 int ofdmx_abi_version(void) { return OFDMX_ABI_VERSION; }
+int ofdmx_params_size(void) { return (int)sizeof(ofdmx_params); }
+int ofdmx_frame_size(void) { return (int)sizeof(ofdmx_frame); }
 
 const char *ofdmx_last_error(const ofdmx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
@@ -458,7 +477,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     if (!prm || !out) return fail(nullptr, OFDMX_ERR_PARAM, "null argument");
     *out = nullptr;
     const int N = prm->fft_len;
-    if (N < 16 || N > 4096 || (N & (N - 1))) return fail(nullptr, OFDMX_ERR_PARAM, "fft_len must be a power of two in 16..4096");
+    if (N < 32 || N > 4096 || (N & (N - 1))) return fail(nullptr, OFDMX_ERR_PARAM, "fft_len must be a power of two in 32..4096");
     if (prm->cp_len < 0 || prm->cp_len > N) return fail(nullptr, OFDMX_ERR_PARAM, "cp_len out of range");
     if (prm->rolloff < 0 || prm->rolloff > prm->cp_len)
         return fail(nullptr, OFDMX_ERR_PARAM, "cyclic prefixer: rolloff len must smaller than the cyclic prefix.");
@@ -466,7 +485,13 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     if (!prm->sync_word1 || !prm->sync_word2) return fail(nullptr, OFDMX_ERR_PARAM, "Length of sync sequence(s) must be FFT length.");
     std::vector<float2> hpts, ppts;
     std::vector<uint8_t> lut_h, lut_p;
-    if (!make_constellation(prm->bps_header, hpts, lut_h) || !make_constellation(prm->bps_payload, ppts, lut_p))
+    float qiw_h = 1.f, qiw_p = 1.f;
+    if (prm->qam_normalization < 0 || prm->qam_normalization > 1)
+        return fail(nullptr, OFDMX_ERR_PARAM, "unknown version switch value");
+    for (int i = 0; i < 7; i++)
+        if (prm->reserved[i] != 0) return fail(nullptr, OFDMX_ERR_PARAM, "ofdmx_params.reserved must be zero (ABI mismatch?)");
+    if (!make_constellation(prm->bps_header, prm->qam_normalization, hpts, lut_h, &qiw_h)
+        || !make_constellation(prm->bps_payload, prm->qam_normalization, ppts, lut_p, &qiw_p))
         return fail(nullptr, OFDMX_ERR_PARAM, "Modulation not supported.");
     if (prm->max_pkt_bytes < 1 || prm->max_pkt_bytes > 4095) return fail(nullptr, OFDMX_ERR_PARAM, "max_pkt_bytes must be 1..4095");
 
@@ -502,6 +527,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     kp.tx_clip = prm->tx_clip;
     kp.roll = prm->rolloff > 1 ? prm->rolloff : 0;      // a flank of length 1 would just be rectangular
     kp.roll_flank = nullptr;
+    kp.qiw_h = qiw_h;
+    kp.qiw_p = qiw_p;
 
     int rc = 0;
     auto bail = [&](int code) { ofdmx_destroy(c); return code; };
@@ -747,8 +774,6 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
 
     // shared-memory budgets
     {
-        const int L = SYNC_T + N, ce = (L + OFDMX_THREADS - 1) / OFDMX_THREADS, Lp = L + L / ce + 2;
-        c->sync_smem = (size_t)Lp * 32;
         c->frame_smem = (size_t)N * 8 * 4 + 64 + N + align_up(c->hl, 16) + align_up(kp.max_pkt_syms, 16)
                         + align_up(kp.max_pkt_bytes, 16) + 16;
         c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16 + (size_t)kp.roll * 8;
@@ -805,9 +830,9 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             if (e1 != cudaSuccess || c->tx1kw_smem > 227 * 1024) c->tx1kw = false;
         }
         c->sync_tma_smem = sync_tma_smem_bytes(N);
-        if (N >= 32 && cudaFuncSetAttribute(sync_metric_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_tma_smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(sync_metric_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_tma_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
-        if (N >= 32) {
+        {
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sync_metric_tma_kernel, SV_THREADS, c->sync_tma_smem) == cudaSuccess && occ > 0)
                 c->sync_tma_occ = occ;
@@ -820,7 +845,6 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             || cudaFuncSetAttribute(sync_metric_fast_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
             || cudaFuncSetAttribute(sync_metric_fast_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
             || cudaFuncSetAttribute(sync_metric_fast_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
-            || cudaFuncSetAttribute(sync_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_smem) != cudaSuccess
             || cudaFuncSetAttribute(rx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem) != cudaSuccess
             || cudaFuncSetAttribute(tx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s (is this an sm_100 device?)",
@@ -844,7 +868,7 @@ void ofdmx_destroy(ofdmx_ctx *c)
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     for (void *p : c->tables) cudaFree(p);
-    for (DevBuf *b : { &c->ws, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
+    for (DevBuf *b : { &c->ws, &c->ws_host, &c->ws_papr, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
         if (b->p) cudaFree(b->p);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -857,6 +881,7 @@ int ofdmx_profile(ofdmx_ctx *c, int enable)
     for (auto &r : c->prof_pending) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
     c->prof_pending.clear();
     for (int i = 0; i < K_NSLOTS; i++) { c->prof_ms[i] = 0; c->prof_calls[i] = 0; }
+    c->prof_errors = 0;
     return OFDMX_OK;
 }
 int ofdmx_profile_slots(void) { return K_NSLOTS; }
@@ -876,6 +901,7 @@ int ofdmx_profile_read(ofdmx_ctx *c, float *ms_total, int64_t *calls)
     }
     c->prof_pending.clear();
     for (int i = 0; i < K_NSLOTS; i++) { ms_total[i] = (float)c->prof_ms[i]; calls[i] = c->prof_calls[i]; }
+    if (c->prof_errors) return fail(c, OFDMX_ERR_CUDA, "%lld kernel timings lost (CUDA event creation / record failed)", (long long)c->prof_errors);
     return OFDMX_OK;
 }
 
@@ -925,9 +951,25 @@ int ofdmx_sync(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_
     return OFDMX_OK;
 }
 
+extern "C++" {
+static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_t n_streams, int64_t n_samples, int64_t stride,
+                   ofdmx_frame *frames_out, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+                   float *z_out, int64_t z_stride, ofdmx_counts *counts_dev, cudaStream_t st);
+}
+
 int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t n_samples, int64_t stride,
              ofdmx_frame *frames_out, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
              float *z_out, int64_t z_stride, ofdmx_counts *counts_dev, void *stream)
+{
+    if (!c) return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_rx arguments");
+    return rx_core(c, c->ws, samples_dev, n_streams, n_samples, stride, frames_out, max_frames, bytes_out, byte_stride, z_out,
+                   z_stride, counts_dev, (cudaStream_t)stream);
+}
+
+extern "C++" {
+static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_t n_streams, int64_t n_samples, int64_t stride,
+                   ofdmx_frame *frames_out, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+                   float *z_out, int64_t z_stride, ofdmx_counts *counts_dev, cudaStream_t st)
 {
     if (!c || !samples_dev || !frames_out || !bytes_out || !counts_dev || n_streams < 1 || n_samples < 1
         || max_frames < 1 || stride < n_samples)
@@ -936,9 +978,8 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     if (z_out && z_stride < c->hl) return fail(c, OFDMX_ERR_CAPACITY, "z_stride < header_len");
     if (max_frames > 0x7ffffff0LL) return fail(c, OFDMX_ERR_PARAM, "max_frames too large");
     if (int rc = check_device(c)) return rc;
-    if (int rc = ofdmx_reserve(c, n_streams, n_samples, max_frames)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    RxWs w = carve(c->ws.p, n_streams, n_samples, max_frames);
+    if (int rc = grow(c, wsbuf, carve(nullptr, n_streams, n_samples, max_frames).total)) return rc;
+    RxWs w = carve(wsbuf.p, n_streams, n_samples, max_frames);
     const float2 *smp = (const float2 *)samples_dev;
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
     ofdmx_ctx *ctx_ = c;
@@ -969,13 +1010,16 @@ int ofdmx_rx(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_t 
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }
+}  // extern "C++"
 
 int ofdmx_rx_host(ofdmx_ctx *c, const float *samples_host, int64_t n_streams, int64_t n_samples,
                   ofdmx_frame *frames_host, int64_t max_frames, uint8_t *bytes_host, int64_t byte_stride,
                   ofdmx_counts *counts_host)
 {
-    if (!c || !samples_host || !frames_host || !bytes_host || !counts_host)
+    if (!c || !samples_host || !frames_host || !bytes_host || !counts_host || n_streams < 1 || n_samples < 1 || max_frames < 1
+        || max_frames > 0x7ffffff0LL || n_streams > (1LL << 40) / n_samples)
         return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_rx_host arguments");
+    if (byte_stride < c->kp.max_pkt_bytes) return fail(c, OFDMX_ERR_CAPACITY, "byte_stride < max_pkt_bytes");
     if (int rc = check_device(c)) return rc;
     const size_t sbytes = sizeof(float2) * (size_t)n_streams * (size_t)n_samples;
     if (int rc = grow(c, c->h_samples, sbytes)) return rc;
@@ -984,9 +1028,10 @@ int ofdmx_rx_host(ofdmx_ctx *c, const float *samples_host, int64_t n_streams, in
     if (int rc = grow(c, c->h_counts, sizeof(ofdmx_counts))) return rc;
     cudaStream_t st = c->own_stream;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_samples.p, samples_host, sbytes, cudaMemcpyHostToDevice, st));
-    if (int rc = ofdmx_rx(c, (const float *)c->h_samples.p, n_streams, n_samples, n_samples,
-                          (ofdmx_frame *)c->h_frames.p, max_frames, (uint8_t *)c->h_bytes.p, byte_stride, nullptr, 0,
-                          (ofdmx_counts *)c->h_counts.p, st))
+    // own workspace: this call runs on the context's private stream, next to whatever the caller has enqueued
+    if (int rc = rx_core(c, c->ws_host, (const float *)c->h_samples.p, n_streams, n_samples, n_samples,
+                         (ofdmx_frame *)c->h_frames.p, max_frames, (uint8_t *)c->h_bytes.p, byte_stride, nullptr, 0,
+                         (ofdmx_counts *)c->h_counts.p, st))
         return rc;
     CUDA_TRY(c, cudaMemcpyAsync(counts_host, c->h_counts.p, sizeof(ofdmx_counts), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -1063,7 +1108,7 @@ int ofdmx_crc32(ofdmx_ctx *c, const uint8_t *bytes_dev, const int64_t *pkt_off_d
 }
 
 int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
-               float attack, float decay, float reference, float max_gain, float *gain_io_dev, void *stream)
+               float attack, float decay, float reference, float max_gain, float *gain_io_dev, int32_t flags, void *stream)
 {
     if (!c || !in_dev || !out_dev || !gain_io_dev || n_streams < 0 || n < 0 || stride < n || n_streams > (1 << 24))
         return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_agc2 arguments");
@@ -1073,7 +1118,8 @@ int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_stre
     const unsigned grid = (unsigned)((n_streams + 32 * AGC_WARPS - 1) / (32 * AGC_WARPS));
     ofdmx_ctx *ctx_ = c;
     { KT(K_AGC2); agc2_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
-                                                      attack, decay, reference, max_gain, gain_io_dev); }
+                                                      attack, decay, reference, max_gain, gain_io_dev,
+                                                      (flags & OFDMX_AGC2_ABS_RATE) ? 1 : 0); }
     CUDA_TRY(c, cudaGetLastError());
     return OFDMX_OK;
 }
@@ -1084,12 +1130,12 @@ extern "C++" {
 template <int MAXT>
 static int iir_launch(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
                       const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb, int64_t span,
-                      double *state_io_dev, cudaStream_t st)
+                      double *state_io_dev, bool oldstyle, cudaStream_t st)
 {
     iir_taps<MAXT> t;
     for (int i = 0; i < MAXT; i++) {
         t.ff[i] = i < n_ff ? fftaps[i] : 0.0;
-        t.fb[i] = (i >= 1 && i < n_fb) ? -fbtaps[i] : 0.0;   // oldstyle=False: a[k] enter with a minus sign
+        t.fb[i] = (i >= 1 && i < n_fb) ? (oldstyle ? fbtaps[i] : -fbtaps[i]) : 0.0;   // oldstyle=False: a[k] enter with a minus sign
     }
     // warm-up length: where the impulse response has decayed below 1e-18 of its peak (host, double)
     int64_t warm = 0;
@@ -1143,8 +1189,9 @@ static int iir_launch(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t
 
 int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n, int64_t stride,
                   const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb, int64_t span,
-                  double *state_io_dev, void *stream)
+                  double *state_io_dev, int32_t flags, void *stream)
 {
+    const bool oldstyle = (flags & OFDMX_IIR_OLDSTYLE) != 0;
     if (!c || !in_dev || !out_dev || !state_io_dev || !fftaps || n_streams < 0 || n < 0 || stride < n ||
         n_streams > (1 << 24) || n_ff < 1 || n_ff > 17 || n_fb < 0 || n_fb > 17 || (n_fb > 0 && !fbtaps))
         return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_iir_ccd arguments (at most 17 feed-forward and 17 feedback taps)");
@@ -1152,9 +1199,9 @@ int ofdmx_iir_ccd(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_s
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int m = std::max(n_ff, n_fb);
-    if (m <= 9) return iir_launch<9>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, st);
-    if (m <= 13) return iir_launch<13>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, st);
-    return iir_launch<17>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, st);
+    if (m <= 9) return iir_launch<9>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, oldstyle, st);
+    if (m <= 13) return iir_launch<13>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, oldstyle, st);
+    return iir_launch<17>(c, in_dev, out_dev, n_streams, n, stride, fftaps, n_ff, fbtaps, n_fb, span, state_io_dev, oldstyle, st);
 }
 
 int ofdmx_papr(ofdmx_ctx *c, const float *in_dev, int64_t n, float *out3_dev, void *stream)
@@ -1163,8 +1210,8 @@ int ofdmx_papr(ofdmx_ctx *c, const float *in_dev, int64_t n, float *out3_dev, vo
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int parts = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
-    if (int rc = grow(c, c->ws, (size_t)parts * 16)) return rc;
-    double *ps = (double *)c->ws.p;
+    if (int rc = grow(c, c->ws_papr, (size_t)c->sm_count * 8 * 16)) return rc;
+    double *ps = (double *)c->ws_papr.p;
     float *pp = (float *)(ps + parts);
     ofdmx_ctx *ctx_ = c;
     { KT(K_PAPR); papr_kernel<<<parts, 256, 0, st>>>((const float2 *)in_dev, n, ps, pp); }
@@ -1184,6 +1231,8 @@ int ofdmx_reconfigure(ofdmx_ctx **ctx_io, const ofdmx_params *prm)
     // everything that is not a function of the PHY parameters moves over: workspace, pinned staging buffers,
     // the private stream, the profiling state and the counters
     std::swap(nw->ws, old->ws);
+    std::swap(nw->ws_host, old->ws_host);
+    std::swap(nw->ws_papr, old->ws_papr);
     std::swap(nw->h_samples, old->h_samples);
     std::swap(nw->h_frames, old->h_frames);
     std::swap(nw->h_bytes, old->h_bytes);

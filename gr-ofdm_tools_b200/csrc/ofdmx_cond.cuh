@@ -15,7 +15,7 @@
 
 __global__ void __launch_bounds__(AGC_WARPS * 32)
 agc2_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, long long stride, int n_streams,
-            float attack, float decay, float reference, float max_gain, float *__restrict__ gain_io)
+            float attack, float decay, float reference, float max_gain, float *__restrict__ gain_io, int abs_rate)
 {
     __shared__ float2 tile[AGC_WARPS][32][33];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -48,7 +48,7 @@ agc2_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n
                 tile[w][lane][k] = make_float2(re, im);
                 const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
                 const float tmp = __fadd_rn(-reference, mag);
-                const float rate = (tmp > g) ? attack : decay;
+                const float rate = ((abs_rate ? fabsf(tmp) : tmp) > g) ? attack : decay;
                 g = __fsub_rn(g, __fmul_rn(tmp, rate));
                 if (g < 0.0f) g = 10e-5f;
                 if (max_gain > 0.0f && g > max_gain) g = max_gain;

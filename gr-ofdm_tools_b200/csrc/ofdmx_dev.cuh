@@ -54,6 +54,8 @@ struct KP {
     const uint32_t *crc_pow8;    // [65] x^(8*t) mod P (warp CRC tail shift)
     int y1_lo, y1_span;          // shifted-bin range of sync symbol 1 that the offset search reads
     int pil_in_occ;              // some pilot carrier is also in occupied_carriers (equaliser pilot branch reachable)
+    float qiw_h, qiw_p;          // constellation_rect: 1 / sector width of the header / payload QAM table
+                                 // (0.5 (side - 1) without normalisation; divided by the scale factor otherwise)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -75,7 +77,7 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 // decision_maker of constellation_bpsk / _qpsk / _8psk / constellation_rect (16-, 64-QAM)
-__device__ __forceinline__ int ofdm_decide(int bps, float re, float im, const uint8_t *lut)
+__device__ __forceinline__ int ofdm_decide(int bps, float re, float im, const uint8_t *lut, float inv_w)
 {
     if (bps == 1) return re > 0.f;
     if (bps == 2) return 2 * (im > 0.f) + (re > 0.f);
@@ -86,7 +88,6 @@ __device__ __forceinline__ int ofdm_decide(int bps, float re, float im, const ui
         return r;
     }
     const int side = (bps == 4) ? 4 : 8;
-    const float inv_w = 0.5f * (float)(side - 1);      // 1 / (2/(side-1))
     int rs = __float2int_rz(fmaf(re, inv_w, 0.5f * side));
     int is = __float2int_rz(fmaf(im, inv_w, 0.5f * side));
     rs = min(max(rs, 0), side - 1);

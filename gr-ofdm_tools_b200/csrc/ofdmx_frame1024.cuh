@@ -186,7 +186,7 @@ __device__ __forceinline__ void f2k_symbol(const KP &p, const float2 *__restrict
 
 // decision_maker with the modulation known at compile time
 template <int BPS>
-__device__ __forceinline__ int f1k_decide(float re, float im, const uint8_t *__restrict__ lut)
+__device__ __forceinline__ int f1k_decide(float re, float im, const uint8_t *__restrict__ lut, float inv_w)
 {
     if (BPS == 1) return re > 0.f;
     if (BPS == 2) return 2 * (im > 0.f) + (re > 0.f);
@@ -197,7 +197,7 @@ __device__ __forceinline__ int f1k_decide(float re, float im, const uint8_t *__r
         return r;
     }
     constexpr int side = (BPS == 4) ? 4 : 8;
-    constexpr float inv_w = 0.5f * (float)(side - 1), half = 0.5f * (float)side;
+    constexpr float half = 0.5f * (float)side;
     int rs = __float2int_rz(fmaf(re, inv_w, half));
     int is = __float2int_rz(fmaf(im, inv_w, half));
     rs = min(max(rs, 0), side - 1);
@@ -392,10 +392,10 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                     const float2 pv = p.pil_val[k];
                     const float2 q = cdivf(y, pv);
                     Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
-                    d = ofdm_decide(p.bps_h, pv.x, pv.y, p.lut_h);
+                    d = ofdm_decide(p.bps_h, pv.x, pv.y, p.lut_h, p.qiw_h);
                 } else {
                     z = cdivf(y, Hk);
-                    d = ofdm_decide(p.bps_h, z.x, z.y, p.lut_h);
+                    d = ofdm_decide(p.bps_h, z.x, z.y, p.lut_h, p.qiw_h);
                     const float2 q = cmul(y, p.inv_hpts[d]);
                     Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
                 }
@@ -460,11 +460,17 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
             continue;
         }
         rec.flags |= OFDMX_F_HDR_OK;
-        if ((long long)(3 + fsyms) * D > rem || s_plen > p.max_pkt_bytes) {
+        if ((long long)(3 + fsyms) * D > rem) {
             if (tid == 0) spec[j] = rec;
             continue;
         }
         rec.flags |= OFDMX_F_COMPLETE;
+        if (s_plen > p.max_pkt_bytes) {
+            // the demux consumes the declared payload and searches on behind it; the packet does not fit a slot
+            rec.flags |= OFDMX_F_OVERSIZE;
+            if (tid == 0) spec[j] = rec;
+            continue;
+        }
         {   // pull the next frame's trigger record towards L1 while this frame is equalised
             const int jn = j + gridDim.x;
             if (tid == 0 && jn < nt) {
@@ -512,12 +518,12 @@ rx_frame1024_kernel(const KP p, const int W, const float2 *__restrict__ samples,
                         const float2 pv = p.pil_val[pset * N + k];
                         const float2 q = cdivf(y, pv);
                         Hk = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
-                        d = f1k_decide<BPS_P>(pv.x, pv.y, lut);
+                        d = f1k_decide<BPS_P>(pv.x, pv.y, lut, p.qiw_p);
                     } else {
                         const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
                         const float2 nn = cmul_conj(y, Hk);
                         z = make_float2(nn.x * rinv, nn.y * rinv);
-                        d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                        d = f1k_decide<BPS_P>(z.x, z.y, lut, p.qiw_p);
                         const float2 q = cmul(y, ipts[d]);
                         Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                     }

@@ -214,7 +214,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
     const int D = p.D;
     LaneTw ltw = {};
     if (NFFT < 1024) ltw = lane_twiddles(lane);      // lane-FFT twiddles
-    const float al = p.alpha, oma = 1.0f - p.alpha;
+    const float al = p.alpha, oma = 1.0f - p.alpha, qiw = p.qiw_p;
     const int size0 = p.occ_size[0];
     const int sym_bytes = size0 * BPS_P / 8;
     const int ng = (p.gpos - p.gneg) / 2 + 1;
@@ -351,9 +351,14 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                 const bool ok = ((c8 ^ p.crc8_zero) == (bits >> 24));
                 psyms = (plen * 8 + BPS_P - 1) / BPS_P;
                 const int fsyms = (psyms + size0 - 1) / size0;
-                const bool complete = ok && !((long long)(3 + fsyms) * D > rem || plen > p.max_pkt_bytes);
+                // oversize: the samples are there, but the length field exceeds the slot capacity the caller configured
+                // (max_pkt_bytes): the demux still consumes the declared payload, the packet itself is not decoded
+                const bool present = ok && (long long)(3 + fsyms) * D <= rem;
+                const bool oversize = present && plen > p.max_pkt_bytes;
+                const bool complete = present && !oversize;
                 if (lane == 0) {
-                    fs->rec.flags = OFDMX_F_HDR_SEEN | (ok ? OFDMX_F_HDR_OK : 0) | (complete ? OFDMX_F_COMPLETE : 0);
+                    fs->rec.flags = OFDMX_F_HDR_SEEN | (ok ? OFDMX_F_HDR_OK : 0) | (present ? OFDMX_F_COMPLETE : 0)
+                                    | (oversize ? OFDMX_F_OVERSIZE : 0);
                     fs->rec.carr_offset = (int16_t)off;
                     fs->rec.pkt_len = (uint16_t)plen;
                     fs->rec.pkt_num = (uint16_t)pnum;
@@ -393,7 +398,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                     const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
                     const float2 nn = cmul_conj(y, Hk);
                     const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
-                    const int d = f1k_decide<BPS_P>(z.x, z.y, lut);
+                    const int d = f1k_decide<BPS_P>(z.x, z.y, lut, qiw);
                     const float2 q = cmul(y, ipts[d]);
                     Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
                     decw[posc] = (uint8_t)d;

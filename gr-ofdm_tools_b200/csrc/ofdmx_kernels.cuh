@@ -15,102 +15,9 @@
 #define TWO_PI_D 6.283185307179586476925286766559
 #define TRIG_WPT 4   // trigger-mask words per thread in the compaction kernels
 
-// =============================================================================================
-// K2: Schmidl & Cox metric.  Replaces ofdm_sync_sc_cfb's delay/conj/multiply/moving-average/
-// divide chain up to the plateau detector input (python/ofdm_txrx_modules.py:324).
-// One CTA = one tile of SYNC_T samples of one stream plus an N-sample halo.  Window sums come
-// from exclusive prefix sums over the tile (float64 accumulators: order-independent to ~1e-15, so
-// the detect bits equal the oracle's exact evaluation).
-// =============================================================================================
-#define SYNC_T 2048
+// K2 (the Schmidl & Cox metric kernels) lives in ofdmx_sync*.cuh; the kernels below turn its detect bits into
+// triggers.
 #ifdef OFDMX_GENERIC_KERNELS   // the non-template kernels are compiled by ofdmx_api.cu only
-
-__device__ __forceinline__ int padi(int i, int ce) { return i + i / ce; }
-
-__global__ void __launch_bounds__(OFDMX_THREADS)
-sync_metric_kernel(const float2 *__restrict__ samples, long long n, long long stride, int N, double thr,
-                   uint32_t *__restrict__ detmask, long long wps)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int L = SYNC_T + N;
-    const int ce = (L + OFDMX_THREADS - 1) / OFDMX_THREADS;
-    const int Lp = L + L / ce + 2;
-    double *Sxr = reinterpret_cast<double *>(smem_raw);
-    double *Sxi = Sxr + Lp;
-    double *Se = Sxi + Lp;
-    float2 *r_s = reinterpret_cast<float2 *>(Se + Lp);
-    __shared__ double wtot[3][9];
-
-    const long long ts = (long long)blockIdx.x * SYNC_T;
-    const float2 *r = samples + (long long)blockIdx.y * stride;
-    const int h = N >> 1;
-
-    for (int i = tid; i < L; i += OFDMX_THREADS) {
-        long long m = ts - N + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (m >= 0 && m < n) v = __ldg(&r[m]);
-        r_s[padi(i, ce)] = v;
-    }
-    __syncthreads();
-
-    // pass 1: chunk totals
-    const int i0 = tid * ce, i1 = min(i0 + ce, L);
-    double txr = 0, txi = 0, te = 0;
-    for (int i = i0; i < i1; i++) {
-        float2 a = r_s[padi(i, ce)];
-        te += (double)a.x * a.x + (double)a.y * a.y;
-        if (i >= h) {
-            float2 b = r_s[padi(i - h, ce)];
-            txr += (double)a.x * b.x + (double)a.y * b.y;
-            txi += (double)a.y * b.x - (double)a.x * b.y;
-        }
-    }
-    // block exclusive scan of (txr, txi, te)
-    const int lane = tid & 31, wid = tid >> 5;
-    double ixr = txr, ixi = txi, ie = te;
-    for (int o = 1; o < 32; o <<= 1) {
-        double a = __shfl_up_sync(0xffffffffu, ixr, o);
-        double b = __shfl_up_sync(0xffffffffu, ixi, o);
-        double c = __shfl_up_sync(0xffffffffu, ie, o);
-        if (lane >= o) { ixr += a; ixi += b; ie += c; }
-    }
-    if (lane == 31) { wtot[0][wid] = ixr; wtot[1][wid] = ixi; wtot[2][wid] = ie; }
-    __syncthreads();
-    double oxr = 0, oxi = 0, oe = 0;
-    for (int w = 0; w < wid; w++) { oxr += wtot[0][w]; oxi += wtot[1][w]; oe += wtot[2][w]; }
-    double rxr = oxr + ixr - txr, rxi = oxi + ixi - txi, re_ = oe + ie - te;   // exclusive offsets
-    // pass 2: exclusive prefix at every item
-    for (int i = i0; i < i1; i++) {
-        const int pi = padi(i, ce);
-        Sxr[pi] = rxr; Sxi[pi] = rxi; Se[pi] = re_;
-        float2 a = r_s[pi];
-        re_ += (double)a.x * a.x + (double)a.y * a.y;
-        if (i >= h) {
-            float2 b = r_s[padi(i - h, ce)];
-            rxr += (double)a.x * b.x + (double)a.y * b.y;
-            rxi += (double)a.y * b.x - (double)a.x * b.y;
-        }
-    }
-    if (i1 == L && i0 < L) { const int pi = padi(L, ce); Sxr[pi] = rxr; Sxi[pi] = rxi; Se[pi] = re_; }
-    __syncthreads();
-
-    // metric + threshold, one detect bit per sample
-    for (int jj = 0; jj < SYNC_T / OFDMX_THREADS; jj++) {
-        const int nl = jj * OFDMX_THREADS + tid;
-        const long long ng = ts + nl;
-        const int i = N + nl;   // item index of sample ng
-        const int a1 = padi(i + 1, ce);
-        double pr = Sxr[a1] - Sxr[padi(i + 1 - h, ce)];
-        double pim = Sxi[a1] - Sxi[padi(i + 1 - h, ce)];
-        double R = 0.5 * (Se[a1] - Se[padi(i + 1 - N, ce)]);
-        double R2 = R * R, pm2 = pr * pr + pim * pim;
-        bool det = (ng < n) && (R2 > 0.0) && (pm2 >= thr * R2);
-        unsigned word = __ballot_sync(0xffffffffu, det);
-        long long w = ng >> 5;
-        if (lane == 0 && w < wps) detmask[(long long)blockIdx.y * wps + w] = word;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // plateau_detector_fb(max_len = cp_len, threshold) evaluated over the whole stream
@@ -372,6 +279,7 @@ __device__ __forceinline__ void equalize_symbol(const float2 *buf, const KP &p, 
                                                 int pset, int bps, const float2 *pts, const uint8_t *lut,
                                                 bool want_z)
 {
+    const float qiw = (bps == p.bps_p && lut == p.lut_p) ? p.qiw_p : p.qiw_h;
     const float arg = (float)(-TWO_PI_D * off * p.cp / p.N * i1);
     float sn, cs;
     sincosf(arg, &sn, &cs);
@@ -387,11 +295,11 @@ __device__ __forceinline__ void equalize_symbol(const float2 *buf, const KP &p, 
             const float2 q = cdivf(y, p.pil_val[pset * p.N + k]);
             sm.H[k] = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
             const float2 pv = p.pil_val[pset * p.N + k];      // the serialiser sees the pilot value
-            sm.dec[k] = (uint8_t)ofdm_decide(bps, pv.x, pv.y, lut);
+            sm.dec[k] = (uint8_t)ofdm_decide(bps, pv.x, pv.y, lut, qiw);
             if (want_z) sm.zs[k] = make_float2(0.f, 0.f);
         } else {
             const float2 z = cdivf(y, Hk);
-            const int d = ofdm_decide(bps, z.x, z.y, lut);
+            const int d = ofdm_decide(bps, z.x, z.y, lut, qiw);
             const float2 q = cdivf(y, pts[d]);
             sm.H[k] = make_float2(al * Hk.x + oma * q.x, al * Hk.y + oma * q.y);
             sm.dec[k] = (uint8_t)d;
@@ -547,12 +455,18 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
             continue;
         }
         rec.flags |= OFDMX_F_HDR_OK;
-        if (t + (long long)(3 + fsyms) * D > n || s_plen > p.max_pkt_bytes) {
-            // payload never completes in this buffer (or exceeds the configured slot size)
+        if (t + (long long)(3 + fsyms) * D > n) {
+            // payload never completes in this buffer
             if (tid == 0) spec[j] = rec;
             continue;
         }
         rec.flags |= OFDMX_F_COMPLETE;
+        if (s_plen > p.max_pkt_bytes) {
+            // the demux consumes the declared payload and searches on behind it; the packet does not fit a slot
+            rec.flags |= OFDMX_F_OVERSIZE;
+            if (tid == 0) spec[j] = rec;
+            continue;
+        }
         // ---- payload symbols
         int cnt = 0;                      // serialised symbols so far
         int pset = p.n_pil_sets ? 1 % p.n_pil_sets : 0;

@@ -10,7 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libofdmx.so"))
 
 OK, ERR_PARAM, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM = 0, -1, -2, -3, -4
-F_HDR_OK, F_CRC_OK, F_COMPLETE, F_ACCEPTED, F_HDR_SEEN = 1, 2, 4, 8, 16
+F_HDR_OK, F_CRC_OK, F_COMPLETE, F_ACCEPTED, F_HDR_SEEN, F_OVERSIZE = 1, 2, 4, 8, 16, 32
+ABI_VERSION = 4
+AGC2_ABS_RATE, IIR_OLDSTYLE = 1, 1
 
 
 class Params(C.Structure):
@@ -26,6 +28,7 @@ class Params(C.Structure):
         ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
         ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32),
         ("max_pkt_bytes", C.c_int32), ("tx_clip", C.c_float), ("rolloff", C.c_int32),
+        ("qam_normalization", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -38,6 +41,8 @@ class Counts(C.Structure):
 _P, _I64, _I32 = C.c_void_p, C.c_int64, C.c_int32
 SYMBOLS = {
     "ofdmx_abi_version": (C.c_int, []),
+    "ofdmx_params_size": (C.c_int, []),
+    "ofdmx_frame_size": (C.c_int, []),
     "ofdmx_create": (C.c_int, [_P, C.c_int, _P]),
     "ofdmx_destroy": (None, [_P]),
     "ofdmx_last_error": (C.c_char_p, [_P]),
@@ -56,9 +61,9 @@ SYMBOLS = {
     "ofdmx_profile_read": (C.c_int, [_P, _P, _P]),
     "ofdmx_fft": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P]),
     "ofdmx_crc32": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
-    "ofdmx_agc2": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "ofdmx_agc2": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, C.c_float, C.c_float, C.c_float, C.c_float, _P, _I32, _P]),
     "ofdmx_iir_state_doubles": (_I64, []),
-    "ofdmx_iir_ccd": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P, _I32, _I64, _P, _P]),
+    "ofdmx_iir_ccd": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P, _I32, _I64, _P, _I32, _P]),
     "ofdmx_papr": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ofdmx_reconfigure": (C.c_int, [_P, _P]),
 }
@@ -80,6 +85,12 @@ def load():
         fn = getattr(lib, name)    # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
+    # a stale .so with another ofdmx_params layout must not be driven with this binding's structs
+    if lib.ofdmx_abi_version() != ABI_VERSION or lib.ofdmx_params_size() != C.sizeof(Params) \
+            or lib.ofdmx_frame_size() != 32 or C.sizeof(Counts) != 16:
+        raise ImportError("%s has ABI version %d / ofdmx_params of %d bytes; this binding needs version %d / %d bytes "
+                          "(rebuild with `python __graft_entry__.py`)"
+                          % (LIB_PATH, lib.ofdmx_abi_version(), lib.ofdmx_params_size(), ABI_VERSION, C.sizeof(Params)))
     _lib = lib
     return lib
 

@@ -102,6 +102,8 @@ def rx_segmented(phy, samples, n_segments, max_pkt_bytes=None):
             if not (int(f["flags"]) & _lib.F_CRC_OK):
                 continue
             nb -= 4
+        if int(f["flags"]) & _lib.F_OVERSIZE:
+            continue
         payloads.append(bytes(row[:nb]))
     return recs, payloads
 

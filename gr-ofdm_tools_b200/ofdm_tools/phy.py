@@ -85,6 +85,8 @@ class RxResult(object):
                 if not (int(f["flags"]) & _lib.F_CRC_OK):
                     continue
                 n -= 4
+            if int(f["flags"]) & _lib.F_OVERSIZE:
+                continue        # longer than max_pkt_bytes: consumed by the demux, not decoded (no slot content)
             out.append(bytes(slots[int(f["slot"]), :n]))
         return out
 
@@ -94,14 +96,14 @@ class OfdmPhy(object):
                  pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
                  max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None,
-                 max_pkt_bytes=4095, device=0, tx_clip=0.0, rolloff=0):
+                 max_pkt_bytes=4095, device=0, tx_clip=0.0, rolloff=0, qam_normalization=0):
         self._cfg = dict(fft_len=fft_len, cp_len=cp_len, occupied_carriers=occupied_carriers,
                          pilot_carriers=pilot_carriers, pilot_symbols=pilot_symbols, sync_word1=sync_word1,
                          sync_word2=sync_word2, bps_header=bps_header, bps_payload=bps_payload,
                          scramble_bits=scramble_bits, scramble_header=scramble_header, crc_mode=crc_mode,
                          threshold=threshold, max_carr_offset=max_carr_offset, alpha=alpha, tx_scale=tx_scale,
                          demux_holdoff=demux_holdoff, max_pkt_bytes=max_pkt_bytes, device=device, tx_clip=tx_clip,
-                         rolloff=rolloff)
+                         rolloff=rolloff, qam_normalization=qam_normalization)
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occupied_carriers = [list(map(int, s)) for s in occupied_carriers]
         self.pilot_carriers = [list(map(int, s)) for s in pilot_carriers]
@@ -148,6 +150,7 @@ class OfdmPhy(object):
         p.max_pkt_bytes = self.max_pkt_bytes
         p.tx_clip = float(tx_clip)
         p.rolloff = int(rolloff)
+        p.qam_normalization = int(qam_normalization)
         self.rolloff = int(rolloff)
         self.params = p
         self._ctx = None
@@ -179,6 +182,7 @@ class OfdmPhy(object):
         if self._ctx is not None:
             _lib.check(_lib.load().ofdmx_reconfigure(C.byref(self._ctx), C.byref(fresh.params)), self._ctx)
         ctx = self._ctx
+        self.__dict__.pop("_host_bufs", None)     # sized by the old max_pkt_bytes: rx_host re-allocates them
         self.__dict__.update(fresh.__dict__)
         self._ctx = ctx
         return self
@@ -389,7 +393,8 @@ class OfdmPhy(object):
                                            self._stream()), self.ctx)
         return out[: len(lens)].cpu().numpy().astype(np.uint32)
 
-    def agc2(self, samples, gain=None, attack=1e-1, decay=1e-2, reference=1.0, max_gain=65536.0, out=None):
+    def agc2(self, samples, gain=None, attack=1e-1, decay=1e-2, reference=1.0, max_gain=65536.0, out=None,
+             abs_rate=False):
         """analog.agc2_cc(attack, decay, reference, 1.0) + set_max_gain, the block in front of ofdm_rx in both
         hier surfaces (python/ofdm_tx_rx_hier.py:75-76, python/ofdm_radio_hier.py:180-181).  samples: cuda
         complex64 [n] or [n_streams, n]; gain: None (1.0 per stream, a fresh block) or a cuda float32
@@ -408,10 +413,11 @@ class OfdmPhy(object):
         assert out.shape == samples.shape and out.stride() == samples.stride()
         _lib.check(_lib.load().ofdmx_agc2(self.ctx, samples.data_ptr(), out.data_ptr(), n_streams, n,
                                           samples.stride(0) if n_streams > 1 else max(n, 1), attack, decay, reference,
-                                          max_gain, gain.data_ptr(), self._stream()), self.ctx)
+                                          max_gain, gain.data_ptr(), _lib.AGC2_ABS_RATE if abs_rate else 0,
+                                          self._stream()), self.ctx)
         return out, gain
 
-    def iir_ccd(self, samples, fftaps, fbtaps, state=None, span=0, out=None):
+    def iir_ccd(self, samples, fftaps, fbtaps, state=None, span=0, out=None, oldstyle=False):
         """filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False): the out-of-band filter behind the TX chain of
         ofdm_radio_hier when filter_mode=1 (python/ofdm_radio_hier.py:83-84,93,232-237).  samples: cuda complex64
         [n] or [n_streams, n]; state: None (a fresh block) or the cuda float64 [n_streams, 32] tensor a previous
@@ -438,7 +444,8 @@ class OfdmPhy(object):
         fb = (C.c_double * max(len(fbtaps), 1))(*[float(t) for t in fbtaps])
         _lib.check(lib.ofdmx_iir_ccd(self.ctx, samples.data_ptr(), out.data_ptr(), n_streams, n,
                                      samples.stride(0) if n_streams > 1 else max(n, 1), ff, len(fftaps), fb,
-                                     len(fbtaps), int(span), state.data_ptr(), self._stream()), self.ctx)
+                                     len(fbtaps), int(span), state.data_ptr(), _lib.IIR_OLDSTYLE if oldstyle else 0,
+                                     self._stream()), self.ctx)
         return (out[0] if one else out), state
 
     def papr(self, block):

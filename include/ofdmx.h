@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OFDMX_ABI_VERSION 3
+#define OFDMX_ABI_VERSION 4
 
 typedef enum {
     OFDMX_OK = 0,
@@ -50,7 +50,7 @@ typedef struct ofdmx_ctx ofdmx_ctx;
  * ofdm_radio_hier (python/ofdm_radio_hier.py:34-39), flattened.  All pointers are HOST memory and
  * are copied by ofdmx_create. */
 typedef struct {
-    int32_t fft_len;                /* power of two, 16..4096 */
+    int32_t fft_len;                /* power of two, 32..4096 (every power of two in that range has a parity test) */
     int32_t cp_len;
     int32_t n_occ_sets;             /* occupied_carriers: set-major flat list of carrier numbers */
     const int32_t *occ_sizes;
@@ -62,7 +62,9 @@ typedef struct {
     const int32_t *pilot_sym_sizes;
     const float *pilot_symbols;
     const float *sync_word1;        /* fft_len x (re,im), shifted order */
-    const float *sync_word2;
+    const float *sync_word2;        /* NULL: the single-sync-word mode, sync_word2=() in the reference constructors
+                                       (python/ofdm_txrx_modules.py:174-183,311-321): one preamble symbol, two OFDM
+                                       symbols before the payload, channel taps from sync word 1 (interpolated) */
     int32_t bps_header;             /* 1 BPSK, 2 QPSK, 3 8PSK, 4 16-QAM, 6 64-QAM (extension) */
     int32_t bps_payload;
     int32_t scramble_header;        /* packet_header_ofdm(scramble_header=...) */
@@ -83,6 +85,11 @@ typedef struct {
                                        raised-cosine flanks of rolloff-1 samples; every burst grows by rolloff-1
                                        samples (the flushed down flank of its last symbol).  0 or 1 = rectangular;
                                        must not exceed cp_len */
+    /* ---- GNU Radio version switches (every semantic the survey marked "(?)") ---- */
+    int32_t qam_normalization;      /* constellation_rect normalisation of the 16-/64-QAM tables: 0 = none (GNU Radio 3.7,
+                                       the reference's generation: mean power 10/9), 1 = AMPLITUDE_NORMALIZATION (the
+                                       default from 3.8 on: points and sector widths scaled by n / sum|p|) */
+    int32_t reserved[7];            /* must be zero */
 } ofdmx_params;
 
 /* Per-frame record (replaces the stream tags / PMT header dict of the reference). 32 bytes. */
@@ -103,6 +110,9 @@ typedef struct {
 #define OFDMX_F_COMPLETE 4u   /* whole frame lies inside the buffer */
 #define OFDMX_F_ACCEPTED 8u   /* the header/payload demux would have examined this trigger */
 #define OFDMX_F_HDR_SEEN 16u  /* the 3 header-side symbols lie inside the buffer */
+#define OFDMX_F_OVERSIZE 32u  /* header ok, payload samples present, but pkt_len > max_pkt_bytes: the demux
+                                 consumes the frame (the search resumes behind it) and the record is emitted,
+                                 but the payload is not decoded (no slot content, OFDMX_F_CRC_OK never set) */
 
 typedef struct {
     int32_t n_triggers;     /* plateau-detector triggers found (all streams) */
@@ -113,6 +123,8 @@ typedef struct {
 
 /* ---- lifetime ---- */
 int  ofdmx_abi_version(void);
+int  ofdmx_params_size(void);      /* sizeof(ofdmx_params) / sizeof(ofdmx_frame) as this library was compiled: an adaptor */
+int  ofdmx_frame_size(void);       /* checks its own struct declarations against them before the first call */
 int  ofdmx_create(const ofdmx_params *params, int device, ofdmx_ctx **ctx_out);
 void ofdmx_destroy(ofdmx_ctx *ctx);
 const char *ofdmx_last_error(const ofdmx_ctx *ctx);   /* ctx may be NULL (creation errors) */
@@ -183,7 +195,8 @@ int ofdmx_crc32(ofdmx_ctx *ctx, const uint8_t *bytes_dev, const int64_t *pkt_off
  * in_dev == out_dev is allowed.  stride in complex samples. */
 int ofdmx_agc2(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n,
                int64_t stride, float attack, float decay, float reference, float max_gain,
-               float *gain_io_dev, void *cuda_stream);
+               float *gain_io_dev, int32_t flags, void *cuda_stream);
+#define OFDMX_AGC2_ABS_RATE 1   /* rate = attack when fabsf(tmp) > gain (agc2.h from GNU Radio 3.8 on); default: tmp > gain (3.7) */
 
 /* ---- TX conditioning and the PAPR probe (rank 4) ---- */
 /* filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False), the out-of-band filter ofdm_radio_hier puts behind the
@@ -200,7 +213,8 @@ int ofdmx_agc2(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_st
 int64_t ofdmx_iir_state_doubles(void);
 int ofdmx_iir_ccd(ofdmx_ctx *ctx, const float *in_dev, float *out_dev, int64_t n_streams, int64_t n,
                   int64_t stride, const double *fftaps, int32_t n_ff, const double *fbtaps, int32_t n_fb,
-                  int64_t span, double *state_io_dev, void *cuda_stream);
+                  int64_t span, double *state_io_dev, int32_t flags, void *cuda_stream);
+#define OFDMX_IIR_OLDSTYLE 1    /* iir_filter_ccd(..., oldstyle=True): feedback taps enter with a plus sign as given */
 
 /* papr_sink.level() (python/papr_sink.py:46-54) of one block of n complex samples:
  * out3_dev[0] = max|x|^2 / mean|x|^2, out3_dev[1] = max|x|^2, out3_dev[2] = mean|x|^2. */

@@ -14,6 +14,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <complex.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 typedef double complex cd;
 #define TWO_PI 6.283185307179586476925286766559
@@ -166,7 +169,32 @@ static void rect_lut(int bps, int *lut)
 
 /* decision_maker of the constellation object handed to ofdm_equalizer_simpledfe and
  * constellation_decoder_cb (python/ofdm_txrx_modules.py:342-350,362,386-395,407). */
-int orc_decide(int bps, double re, double im)
+/* [UPSTREAM constellation.cc, GNU Radio >= 3.8] AMPLITUDE_NORMALIZATION: points (and the sector widths of
+ * constellation_rect) scaled by n / sum |p|; 3.7 has no normalisation step.  Restated from memory. */
+static double qam_scale(int bps, int norm)
+{
+    if (norm != 1 || (bps != 4 && bps != 6)) return 1.0;
+    static double cache[2] = { 0.0, 0.0 };
+    double cv = cache[bps == 6];
+    if (cv != 0.0) return cv;
+    float pts[128];
+    int m = orc_constellation(bps, pts);
+    double sum = 0;
+    for (int i = 0; i < m; i++) sum += sqrt((double)pts[2 * i] * pts[2 * i] + (double)pts[2 * i + 1] * pts[2 * i + 1]);
+    cache[bps == 6] = (double)m / sum;      /* idempotent: a race writes the same value */
+    return (double)m / sum;
+}
+
+int orc_constellation_n(int bps, int norm, float *pts)
+{
+    int m = orc_constellation(bps, pts);
+    double sc = qam_scale(bps, norm);
+    if (sc != 1.0)
+        for (int i = 0; i < 2 * m; i++) pts[i] = (float)((double)pts[i] * sc);
+    return m;
+}
+
+int orc_decide_n(int bps, int norm, double re, double im)
 {
     if (bps == 1) return re > 0;
     if (bps == 2) return 2 * (im > 0) + (re > 0);
@@ -185,7 +213,8 @@ int orc_decide(int bps, double re, double im)
         }
     }
     int side = (bps == 4) ? 4 : 8;
-    float w = (float)(2.0 / (side - 1));
+    /* the sector LUT is invariant under the common scaling of points and widths */
+    float w = (float)(2.0 / (side - 1) * qam_scale(bps, norm));
     int rsec = (int)(re / w + side / 2.0);
     int isec = (int)(im / w + side / 2.0);
     if (rsec < 0) rsec = 0;
@@ -193,6 +222,19 @@ int orc_decide(int bps, double re, double im)
     if (isec < 0) isec = 0;
     if (isec >= side) isec = side - 1;
     return (bps == 4 ? lut16 : lut64)[rsec * side + isec];
+}
+
+int orc_decide(int bps, double re, double im) { return orc_decide_n(bps, 0, re, im); }
+
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -380,8 +422,8 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
     if (check_params(p)) return -1;
     const int n = p->fft_len, cp = p->cp_len, hl = orc_header_len(p);
     float hpts[128], ppts[128];
-    orc_constellation(p->bps_header, hpts);
-    orc_constellation(p->bps_payload, ppts);
+    orc_constellation_n(p->bps_header, p->qam_normalization, hpts);
+    orc_constellation_n(p->bps_payload, p->qam_normalization, ppts);
     /* offsets of each set in the flat arrays */
     int *occ_base = (int *)malloc(sizeof(int) * (size_t)p->n_occ_sets);
     for (int s = 0, a = 0; s < p->n_occ_sets; s++) { occ_base[s] = a; a += p->occ_sizes[s]; }
@@ -719,7 +761,7 @@ static void frame_equalize(const rx_ctx *c, cd *frame, int n_sym, int off, cd *H
     const int n = p->fft_len;
     const int64_t tot = (int64_t)n * n_sym;
     float pts[128];
-    orc_constellation(bps, pts);
+    orc_constellation_n(bps, p->qam_normalization, pts);
     /* shift the whole frame buffer by the integer carrier offset (flat memcpy semantics) */
     cd *tmp = (cd *)malloc(sizeof(cd) * (size_t)tot);
     for (int64_t q = 0; q < tot; q++) {
@@ -746,7 +788,7 @@ static void frame_equalize(const rx_ctx *c, cd *frame, int n_sym, int off, cd *H
             } else {
                 cd ze = *y / H[k];
                 if (z) z[(int64_t)i * n + k] = ze;
-                int d = orc_decide(bps, creal(ze), cimag(ze));
+                int d = orc_decide_n(bps, p->qam_normalization, creal(ze), cimag(ze));
                 cd se = pts[2 * d] + I * pts[2 * d + 1];
                 H[k] = alpha * H[k] + (1 - alpha) * (*y) / se;
                 *y = se;
@@ -759,20 +801,12 @@ static void frame_equalize(const rx_ctx *c, cd *frame, int n_sym, int off, cd *H
     for (int k = 0; k < n; k++) H[k] *= pc;
 }
 
-static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
-                   orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
-                   float *z_out, int64_t z_stride, int64_t *n_frames,
-                   int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig, int f32sync)
+static void rx_ctx_init(rx_ctx *cp, const orc_params *p, const float *r, int64_t n_samp, const int64_t *trig,
+                        const float *cfo, int64_t n_trig_v)
 {
-    if (check_params(p)) return -1;
-    const int n = p->fft_len, D = n + p->cp_len, hl = orc_header_len(p);
-    if (n > 4096) return -1;
-    int rc = f32sync ? orc_sync_f32(p, r, n_samp, trig, cfo, max_trig, n_trig)
-                     : orc_sync(p, r, n_samp, NULL, trig, cfo, max_trig, n_trig);
-    if (rc) return rc;
-    if (*n_trig > max_trig) return -3;
-
-    rx_ctx c;
+    const int n = p->fft_len;
+    const int64_t *n_trig = &n_trig_v;
+#define c (*cp)
     memset(&c, 0, sizeof c);
     c.p = p; c.r = r; c.n_samp = n_samp; c.trig = trig; c.cfo = cfo; c.n_trig = *n_trig;
     double *base = (double *)malloc(sizeof(double) * (size_t)(*n_trig + 1));
@@ -811,96 +845,200 @@ static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
         c.sw2[k] = p->sync_word2[2 * k] + I * p->sync_word2[2 * k + 1];
     }
 
+#undef c
+}
+
+static void rx_ctx_free(rx_ctx *c)
+{
+    free((void *)c->base); free(c->occ_mask); free(c->occ_base); free(c->pil_mask); free(c->pil_val);
+}
+
+/* Everything the chain computes for ONE trigger: 3 header-side symbols, chanest, header equaliser + parser and,
+ * when the header parses and the samples are there, the payload (python/ofdm_txrx_modules.py:340-426).
+ * status: 1 = header CRC-8 failed, 2 = payload samples missing, 3 = decoded.  The caller has checked that the
+ * 3 header-side symbols lie inside the buffer. */
+typedef struct { int status, off, plen, pnum, psyms, fsyms, crc_ok; int64_t nbytes; } trig_dec;
+
+static void decode_trigger(const rx_ctx *c, int64_t ti, int hl, uint8_t *dst, int64_t byte_stride,
+                           float *zo, int64_t z_stride, trig_dec *o)
+{
+    const orc_params *p = c->p;
+    const int n = p->fft_len, D = n + p->cp_len;
+    const int64_t t = c->trig[ti];
+    memset(o, 0, sizeof *o);
+    if (t + 3 * (int64_t)D > c->n_samp) { o->status = 2; return; }
     cd *y = (cd *)malloc(sizeof(cd) * (size_t)n * 3), *H = (cd *)malloc(sizeof(cd) * (size_t)n);
     cd *zh = (cd *)malloc(sizeof(cd) * (size_t)n);
     uint8_t *hbits = (uint8_t *)malloc((size_t)hl);
+    for (int j = 0; j < 3; j++) rx_symbol(c, t + (int64_t)j * D + p->cp_len, y + (size_t)j * n);
+    int off = chanest(c, y, y + n, H);
+    frame_equalize(c, y + 2 * n, 1, off, H, p->bps_header, 0, zh);
+    /* header serializer: set 0, all carriers; constellation_decoder_cb(header const) */
+    for (int k = 0; k < hl; k++) {
+        int bin = shifted_bin(p->occ_carriers[c->occ_base[0] + k], n);
+        cd s = y[2 * n + bin];
+        hbits[k] = (uint8_t)orc_decide_n(p->bps_header, p->qam_normalization, creal(s), cimag(s));
+    }
+    int plen, pnum, psyms, fsyms;
+    int ok = orc_header_parse(p, hbits, &plen, &pnum, &psyms, &fsyms);
+    o->off = off;
+    if (!ok) { o->status = 1; goto done; }
+    o->plen = plen; o->pnum = pnum; o->psyms = psyms; o->fsyms = fsyms;
+    if (t + (int64_t)(3 + fsyms) * D > c->n_samp) { o->status = 2; goto done; }
+    o->status = 3;
+    o->crc_ok = 1;
+    if (zo)
+        for (int k = 0; k < hl; k++) {
+            int bin = shifted_bin(p->occ_carriers[c->occ_base[0] + k], n);
+            zo[2 * k] = (float)creal(zh[bin]); zo[2 * k + 1] = (float)cimag(zh[bin]);
+        }
+    if (fsyms > 0) {
+        cd *pf = (cd *)malloc(sizeof(cd) * (size_t)n * (size_t)fsyms);
+        cd *pz = (cd *)malloc(sizeof(cd) * (size_t)n * (size_t)fsyms);
+        for (int i = 0; i < fsyms; i++)
+            rx_symbol(c, t + (int64_t)(3 + i) * D + p->cp_len, pf + (size_t)i * n);
+        frame_equalize(c, pf, fsyms, off, H, p->bps_payload, 1, pz);
+        /* ofdm_serializer_vcc(fft_len, occupied, frame_key, packet_len_key, 1) +
+         * constellation_decoder_cb + repack_bits_bb(bps, 8, key, True) + descrambler */
+        uint8_t *syms = (uint8_t *)malloc((size_t)psyms + 1);
+        int64_t cnt = 0;
+        int set = 1 % p->n_occ_sets;
+        for (int i = 0; i < fsyms && cnt < psyms; i++) {
+            for (int k = 0; k < p->occ_sizes[set] && cnt < psyms; k++) {
+                int bin = shifted_bin(p->occ_carriers[c->occ_base[set] + k], n);
+                cd s = pf[(size_t)i * n + bin];
+                syms[cnt] = (uint8_t)orc_decide_n(p->bps_payload, p->qam_normalization, creal(s), cimag(s));
+                if (zo && hl + cnt < z_stride) {
+                    zo[2 * (hl + cnt)] = (float)creal(pz[(size_t)i * n + bin]);
+                    zo[2 * (hl + cnt) + 1] = (float)cimag(pz[(size_t)i * n + bin]);
+                }
+                cnt++;
+            }
+            set = (set + 1) % p->n_occ_sets;
+        }
+        uint8_t *pb = (uint8_t *)malloc((size_t)(cnt * p->bps_payload / 8 + 2));
+        int64_t nbytes = orc_repack(syms, cnt, p->bps_payload, 8, 1, pb);
+        orc_scramble(pb, nbytes, (uint32_t)p->scramble_seed);
+        if (p->crc_mode) { /* crc32_bb(True): compare with trailing 4 bytes (LE) */
+            if (nbytes < 4) o->crc_ok = 0;
+            else {
+                uint32_t cc = orc_crc32(pb, nbytes - 4);
+                uint32_t got = (uint32_t)pb[nbytes - 4] | ((uint32_t)pb[nbytes - 3] << 8)
+                               | ((uint32_t)pb[nbytes - 2] << 16) | ((uint32_t)pb[nbytes - 1] << 24);
+                o->crc_ok = (cc == got);
+            }
+        }
+        if (nbytes > byte_stride) nbytes = byte_stride;
+        memcpy(dst, pb, (size_t)nbytes);
+        o->nbytes = nbytes;
+        free(pf); free(pz); free(syms); free(pb);
+    }
+done:
+    free(y); free(H); free(zh); free(hbits);
+}
+
+static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
+                   orc_frame *recs, int64_t max_frames, uint8_t *bytes_out, int64_t byte_stride,
+                   float *z_out, int64_t z_stride, int64_t *n_frames,
+                   int64_t *trig, float *cfo, int64_t max_trig, int64_t *n_trig, int f32sync)
+{
+    if (check_params(p)) return -1;
+    const int n = p->fft_len, D = n + p->cp_len, hl = orc_header_len(p);
+    if (n > 4096) return -1;
+    int rc = f32sync ? orc_sync_f32(p, r, n_samp, trig, cfo, max_trig, n_trig)
+                     : orc_sync(p, r, n_samp, NULL, trig, cfo, max_trig, n_trig);
+    if (rc) return rc;
+    if (*n_trig > max_trig) return -3;
+
+    rx_ctx c;
+    rx_ctx_init(&c, p, r, n_samp, trig, cfo, *n_trig);
+
+    /* Per-trigger decode (header, then payload) is a pure function of the trigger: the float32-sync baseline
+     * decodes every trigger speculatively on all host threads and then walks the demux state machine over the
+     * results -- what the CUDA path does; the exact path decodes on demand inside the walk. */
+    trig_dec *spec = NULL;
+    uint8_t *spec_bytes = NULL;
+    if (f32sync && *n_trig > 0) {
+        spec = (trig_dec *)calloc((size_t)*n_trig, sizeof(trig_dec));
+        spec_bytes = (uint8_t *)malloc((size_t)*n_trig * (size_t)byte_stride);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int64_t ti = 0; ti < *n_trig; ti++)
+            decode_trigger(&c, ti, hl, spec_bytes + ti * byte_stride, byte_stride, NULL, 0, &spec[ti]);
+    }
     int64_t nf = 0, pos = 0, ti = 0;
+    uint8_t *scratch = (uint8_t *)malloc((size_t)(byte_stride > 0 ? byte_stride : 1));
     /* digital.header_payload_demux(3, fft_len, cp_len, key, "", True) state machine
      * (python/ofdm_txrx_modules.py:328-334,382) [UPSTREAM header_payload_demux_impl.cc] */
     while (ti < *n_trig) {
         int64_t t = trig[ti];
         if (t < pos) { ti++; continue; }
         if (t + 3 * (int64_t)D > n_samp) break; /* header never completes */
-        for (int j = 0; j < 3; j++) rx_symbol(&c, t + (int64_t)j * D + p->cp_len, y + (size_t)j * n);
-        int off = chanest(&c, y, y + n, H);
-        frame_equalize(&c, y + 2 * n, 1, off, H, p->bps_header, 0, zh);
-        /* header serializer: set 0, all carriers; constellation_decoder_cb(header const) */
-        for (int k = 0; k < hl; k++) {
-            int bin = shifted_bin(p->occ_carriers[c.occ_base[0] + k], n);
-            cd s = y[2 * n + bin];
-            hbits[k] = (uint8_t)orc_decide(p->bps_header, creal(s), cimag(s));
+        trig_dec dd, *d = &dd;
+        const int full = nf >= max_frames;                     /* no room: decode into the scratch slot, then fail */
+        uint8_t *dst = full ? scratch : bytes_out + nf * byte_stride;
+        float *zo = (z_out && !full) ? z_out + 2 * nf * z_stride : NULL;
+        if (spec) {
+            d = &spec[ti];
+            if (d->status == 3) memcpy(dst, spec_bytes + ti * byte_stride, (size_t)d->nbytes);
+        } else {
+            decode_trigger(&c, ti, hl, dst, byte_stride, zo, z_stride, &dd);
         }
-        int plen, pnum, psyms, fsyms;
-        int ok = orc_header_parse(p, hbits, &plen, &pnum, &psyms, &fsyms);
-        if (!ok) { pos = t + 1; ti++; continue; }
-        if (t + (int64_t)(3 + fsyms) * D > n_samp) break; /* payload never completes */
-        if (nf >= max_frames) { rc = -4; break; }
+        if (d->status == 1) { pos = t + 1; ti++; continue; }   /* header CRC-8 failed */
+        if (d->status == 2) break;                             /* payload never completes */
+        if (full) { rc = -4; break; }
         orc_frame *f = &recs[nf];
         memset(f, 0, sizeof *f);
-        f->trigger = t; f->cfo = cfo[ti]; f->carr_offset = off;
-        f->pkt_len = (uint16_t)plen; f->pkt_num = (uint16_t)pnum; f->frame_syms = (uint32_t)fsyms;
+        f->trigger = t; f->cfo = cfo[ti]; f->carr_offset = d->off;
+        f->pkt_len = (uint16_t)d->plen; f->pkt_num = (uint16_t)d->pnum; f->frame_syms = (uint32_t)d->fsyms;
         f->flags = ORC_F_HDR_OK | ORC_F_COMPLETE | ORC_F_ACCEPTED;
         f->slot = (uint32_t)nf;
-        float *zo = z_out ? z_out + 2 * nf * z_stride : NULL;
-        if (zo)
-            for (int k = 0; k < hl; k++) {
-                int bin = shifted_bin(p->occ_carriers[c.occ_base[0] + k], n);
-                zo[2 * k] = (float)creal(zh[bin]); zo[2 * k + 1] = (float)cimag(zh[bin]);
-            }
-        /* payload */
-        uint8_t *dst = bytes_out + nf * byte_stride;
-        int64_t nbytes = 0;
-        int crc_ok = 1;
-        if (fsyms > 0) {
-            cd *pf = (cd *)malloc(sizeof(cd) * (size_t)n * (size_t)fsyms);
-            cd *pz = (cd *)malloc(sizeof(cd) * (size_t)n * (size_t)fsyms);
-            for (int i = 0; i < fsyms; i++)
-                rx_symbol(&c, t + (int64_t)(3 + i) * D + p->cp_len, pf + (size_t)i * n);
-            frame_equalize(&c, pf, fsyms, off, H, p->bps_payload, 1, pz);
-            /* ofdm_serializer_vcc(fft_len, occupied, frame_key, packet_len_key, 1) +
-             * constellation_decoder_cb + repack_bits_bb(bps, 8, key, True) + descrambler */
-            uint8_t *syms = (uint8_t *)malloc((size_t)psyms + 1);
-            int64_t cnt = 0;
-            int set = 1 % p->n_occ_sets;
-            for (int i = 0; i < fsyms && cnt < psyms; i++) {
-                for (int k = 0; k < p->occ_sizes[set] && cnt < psyms; k++) {
-                    int bin = shifted_bin(p->occ_carriers[c.occ_base[set] + k], n);
-                    cd s = pf[(size_t)i * n + bin];
-                    syms[cnt] = (uint8_t)orc_decide(p->bps_payload, creal(s), cimag(s));
-                    if (zo && hl + cnt < z_stride) {
-                        zo[2 * (hl + cnt)] = (float)creal(pz[(size_t)i * n + bin]);
-                        zo[2 * (hl + cnt) + 1] = (float)cimag(pz[(size_t)i * n + bin]);
-                    }
-                    cnt++;
-                }
-                set = (set + 1) % p->n_occ_sets;
-            }
-            uint8_t *pb = (uint8_t *)malloc((size_t)(cnt * p->bps_payload / 8 + 2));
-            nbytes = orc_repack(syms, cnt, p->bps_payload, 8, 1, pb);
-            orc_scramble(pb, nbytes, (uint32_t)p->scramble_seed);
-            if (nbytes > byte_stride) nbytes = byte_stride;
-            memcpy(dst, pb, (size_t)nbytes);
-            if (p->crc_mode) { /* crc32_bb(True): compare with trailing 4 bytes (LE) */
-                if (nbytes < 4) crc_ok = 0;
-                else {
-                    uint32_t cc = orc_crc32(pb, nbytes - 4);
-                    uint32_t got = (uint32_t)pb[nbytes - 4] | ((uint32_t)pb[nbytes - 3] << 8)
-                                   | ((uint32_t)pb[nbytes - 2] << 16) | ((uint32_t)pb[nbytes - 1] << 24);
-                    crc_ok = (cc == got);
-                }
-            }
-            free(pf); free(pz); free(syms); free(pb);
-        }
-        if (crc_ok) f->flags |= ORC_F_CRC_OK;
+        if (d->crc_ok) f->flags |= ORC_F_CRC_OK;
         nf++;
-        if (fsyms > 0) pos = t + (int64_t)(3 + fsyms) * D - p->demux_holdoff;
+        if (d->fsyms > 0) pos = t + (int64_t)(3 + d->fsyms) * D - p->demux_holdoff;
         else pos = t + 3 * (int64_t)D;
         ti++;
     }
+    free(spec); free(spec_bytes); free(scratch);
     *n_frames = nf;
-    free(base); free(c.occ_mask); free(c.occ_base); free(c.pil_mask); free(c.pil_val);
-    free(y); free(H); free(zh); free(hbits);
+    rx_ctx_free(&c);
     return rc;
+}
+
+/* One record per raw plateau trigger, each decoded on its own (what ofdmx_set_emit_all returns): flags carry
+ * ORC_F_HDR_SEEN (the 3 header-side symbols lie inside the buffer), ORC_F_HDR_OK, ORC_F_COMPLETE, ORC_F_CRC_OK;
+ * slot = trigger ordinal.  The demux acceptance rule is NOT applied (ORC_F_ACCEPTED never set). */
+int orc_rx_all(const orc_params *p, const float *r, int64_t n_samp, orc_frame *recs, int64_t max_recs,
+               uint8_t *bytes_out, int64_t byte_stride, int64_t *n_recs)
+{
+    if (check_params(p)) return -1;
+    int64_t max_trig = n_samp / (p->cp_len > 0 ? p->cp_len : 1) + 16, nt = 0;
+    int64_t *trig = (int64_t *)malloc(sizeof(int64_t) * (size_t)max_trig);
+    float *cfo = (float *)malloc(sizeof(float) * (size_t)max_trig);
+    int rc = orc_sync(p, r, n_samp, NULL, trig, cfo, max_trig, &nt);
+    if (rc == 0 && nt > max_recs) rc = -4;
+    if (rc) { free(trig); free(cfo); return rc; }
+    rx_ctx c;
+    rx_ctx_init(&c, p, r, n_samp, trig, cfo, nt);
+    const int hl = orc_header_len(p), D = p->fft_len + p->cp_len;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t ti = 0; ti < nt; ti++) {
+        orc_frame *f = &recs[ti];
+        memset(f, 0, sizeof *f);
+        f->trigger = trig[ti]; f->cfo = cfo[ti]; f->slot = (uint32_t)ti;
+        if (trig[ti] + 3 * (int64_t)D > n_samp) continue;
+        trig_dec d;
+        decode_trigger(&c, ti, hl, bytes_out + ti * byte_stride, byte_stride, NULL, 0, &d);
+        f->flags = ORC_F_HDR_SEEN;
+        f->carr_offset = d.off;
+        if (d.status == 1) continue;
+        f->flags |= ORC_F_HDR_OK;
+        f->pkt_len = (uint16_t)d.plen; f->pkt_num = (uint16_t)d.pnum; f->frame_syms = (uint32_t)d.fsyms;
+        if (d.status == 3) f->flags |= ORC_F_COMPLETE | (d.crc_ok ? ORC_F_CRC_OK : 0);
+    }
+    *n_recs = nt;
+    rx_ctx_free(&c);
+    free(trig); free(cfo);
+    return 0;
 }
 
 int orc_rx(const orc_params *p, const float *r, int64_t n_samp,
@@ -937,6 +1075,13 @@ int orc_rx_baseline(const orc_params *p, const float *r, int64_t n_samp,
 void orc_agc2(const float *in, float *out, int64_t n, float attack, float decay, float reference,
               float max_gain, float *gain)
 {
+    orc_agc2_v(in, out, n, attack, decay, reference, max_gain, gain, 0);
+}
+
+/* abs_rate != 0: the rule of agc2.h from GNU Radio 3.8 on, rate = (fabsf(tmp) > gain) ? attack : decay */
+void orc_agc2_v(const float *in, float *out, int64_t n, float attack, float decay, float reference,
+                float max_gain, float *gain, int abs_rate)
+{
     float g = *gain;
     for (int64_t i = 0; i < n; i++) {
         const float re = in[2 * i] * g, im = in[2 * i + 1] * g;
@@ -944,7 +1089,7 @@ void orc_agc2(const float *in, float *out, int64_t n, float attack, float decay,
         out[2 * i + 1] = im;
         const float rr = re * re, ii = im * im;
         const float tmp = -reference + sqrtf(rr + ii);
-        const float rate = (tmp > g) ? attack : decay;
+        const float rate = ((abs_rate ? fabsf(tmp) : tmp) > g) ? attack : decay;
         g -= tmp * rate;
         if (g < 0.0f) g = 10e-5f;
         if (max_gain > 0.0f && g > max_gain) g = max_gain;
@@ -978,6 +1123,13 @@ uint32_t orc_crc32_mac(const uint8_t *buf, int64_t len)
 void orc_iir_ccd(const float *in, float *out, int64_t n, const double *ff, int n_ff, const double *fb, int n_fb,
                  double *state)
 {
+    orc_iir_ccd_v(in, out, n, ff, n_ff, fb, n_fb, state, 0);
+}
+
+/* oldstyle != 0: iir_filter_ccd(..., oldstyle=True), set_taps() keeps the feedback taps as given (plus sign) */
+void orc_iir_ccd_v(const float *in, float *out, int64_t n, const double *ff, int n_ff, const double *fb, int n_fb,
+                   double *state, int oldstyle)
+{
     double *xh = state, *yh = state + 2 * (n_ff - 1);
     const int nx = n_ff - 1, ny = n_fb > 0 ? n_fb - 1 : 0;
     for (int64_t k = 0; k < n; k++) {
@@ -988,7 +1140,7 @@ void orc_iir_ccd(const float *in, float *out, int64_t n, const double *ff, int n
             ai += ff[i] * xh[2 * (i - 1) + 1];
         }
         for (int i = 1; i < n_fb; i++) {
-            const double t = -fb[i];
+            const double t = oldstyle ? fb[i] : -fb[i];
             ar += t * yh[2 * (i - 1)];
             ai += t * yh[2 * (i - 1) + 1];
         }

@@ -59,6 +59,8 @@ typedef struct {
                                        +-tx_clip (python/clipper.py:45-58, ofdm_radio_hier.py:92,229); 0 = off */
     int32_t rolloff;                /* ofdm_cyclic_prefixer rolloff_len (python/ofdm_txrx_modules.py:247-253);
                                        0 or 1 = rectangular */
+    int32_t qam_normalization;      /* 16-/64-QAM constellation_rect: 0 = no normalisation (GNU Radio 3.7), 1 =
+                                       AMPLITUDE_NORMALIZATION (default from 3.8 on) */
 } orc_params;
 
 typedef struct {
@@ -77,6 +79,7 @@ typedef struct {
 #define ORC_F_CRC_OK   2u
 #define ORC_F_COMPLETE 4u
 #define ORC_F_ACCEPTED 8u
+#define ORC_F_HDR_SEEN 16u   /* orc_rx_all only: the 3 header-side symbols lie inside the buffer */
 
 /* ---- integer primitives ---- */
 uint32_t orc_crc32(const uint8_t *buf, int64_t len);                 /* zlib CRC-32 (crc32_bb) */
@@ -90,6 +93,14 @@ int      orc_header_parse(const orc_params *p, const uint8_t *in, int *pkt_len_b
                           int *pkt_syms, int *frame_syms);
 int      orc_constellation(int bps, float *points /* 2^bps x (re,im) */);
 int      orc_decide(int bps, double re, double im);
+/* the same with the constellation_rect normalisation switch (0 none, 1 amplitude) */
+int      orc_constellation_n(int bps, int norm, float *points);
+int      orc_decide_n(int bps, int norm, double re, double im);
+int      orc_rx_all(const orc_params *p, const float *r, int64_t n_samp, orc_frame *recs, int64_t max_recs,
+                    uint8_t *bytes_out, int64_t byte_stride, int64_t *n_recs);
+/* OpenMP team size used by the parallel loops (0: leave as is); returns the team size in effect.  The
+ * reference arm sets it explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers. */
+int      orc_set_threads(int n);
 
 /* ---- float primitives ---- */
 void orc_fft(int n, int forward, const double *in, double *out);   /* unnormalised DFT, no shift */
@@ -125,11 +136,15 @@ int orc_rx_baseline(const orc_params *p, const float *samples, int64_t n,
  * *gain: loop gain before the first sample on entry, after the last sample on return. */
 void orc_agc2(const float *in, float *out, int64_t n, float attack, float decay, float reference,
               float max_gain, float *gain);
+void orc_agc2_v(const float *in, float *out, int64_t n, float attack, float decay, float reference,
+                float max_gain, float *gain, int abs_rate);
 /* digital.crc32() of gr-digital/lib/crc32.cc as used by digital.crc.gen_and_append_crc32
  * (examples/benchmarks.py:347, python/ofdm_cr_tools.py:1760): MSB-first, poly 0x04C11DB7,
  * init and final XOR 0xFFFFFFFF; check value 0xFC891918. */
 void orc_iir_ccd(const float *in, float *out, int64_t n, const double *ff, int n_ff, const double *fb, int n_fb,
                  double *state);
+void orc_iir_ccd_v(const float *in, float *out, int64_t n, const double *ff, int n_ff, const double *fb, int n_fb,
+                   double *state, int oldstyle);
 uint32_t orc_crc32_mac(const uint8_t *buf, int64_t len);
 
 #ifdef __cplusplus

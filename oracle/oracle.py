@@ -39,6 +39,7 @@ class _Params(C.Structure):
         ("scramble_header", C.c_int32), ("scramble_seed", C.c_int32),
         ("crc_mode", C.c_int32), ("threshold", C.c_float), ("max_carr_offset", C.c_int32),
         ("alpha", C.c_float), ("tx_scale", C.c_float), ("demux_holdoff", C.c_int32), ("tx_clip", C.c_float), ("rolloff", C.c_int32),
+        ("qam_normalization", C.c_int32),
     ]
 
 
@@ -71,11 +72,16 @@ def lib():
         L.orc_fft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_tx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                              C.c_void_p, C.c_int64, C.c_void_p]
-        L.orc_agc2.restype = None
-        L.orc_agc2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
-        L.orc_iir_ccd.restype = None
-        L.orc_iir_ccd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
-                                  C.c_void_p]
+        L.orc_agc2_v.restype = None
+        L.orc_agc2_v.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                 C.c_int]
+        L.orc_iir_ccd_v.restype = None
+        L.orc_iir_ccd_v.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_void_p, C.c_int]
+        L.orc_set_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_constellation_n.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.orc_decide_n.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_crc32_mac.restype = C.c_uint32
         L.orc_crc32_mac.argtypes = [C.c_void_p, C.c_int64]
         L.orc_tx_frame_samples.restype = C.c_int64
@@ -87,6 +93,8 @@ def lib():
         L.orc_rx.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                              C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_int64, C.c_void_p]
+        L.orc_rx_all.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                 C.c_void_p]
         L.orc_rx_baseline.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     return _LIB
@@ -156,7 +164,8 @@ class Oracle:
     def __init__(self, fft_len=64, cp_len=16, occupied_carriers=None, pilot_carriers=None,
                  pilot_symbols=None, sync_word1=None, sync_word2=None, bps_header=1, bps_payload=1,
                  scramble_bits=False, scramble_header=None, crc_mode=0, threshold=0.9,
-                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None, tx_clip=0.0, rolloff=0):
+                 max_carr_offset=-1, alpha=0.1, tx_scale=1.0, demux_holdoff=None, tx_clip=0.0, rolloff=0,
+                 qam_normalization=0):
         self.fft_len, self.cp_len = int(fft_len), int(cp_len)
         self.occ = [list(map(int, s)) for s in occupied_carriers]
         self.pil = [list(map(int, s)) for s in pilot_carriers]
@@ -192,6 +201,7 @@ class Oracle:
         p.demux_holdoff = (self.fft_len + self.cp_len) if demux_holdoff is None else int(demux_holdoff)
         p.tx_clip = float(tx_clip)
         p.rolloff = int(rolloff)
+        p.qam_normalization = int(qam_normalization)
         self.p = p
         self.L = lib()
 
@@ -272,6 +282,20 @@ class Oracle:
         return {"frames": recs[:k].copy(), "bytes": by[:k], "z": z[:k] if want_z else None,
                 "triggers": trig[:nt.value].copy(), "cfo": cfo[:nt.value].copy()}
 
+    def rx_all(self, samples, byte_stride=4096):
+        """One record per raw plateau trigger, each decoded on its own (the counterpart of ofdmx_set_emit_all):
+        returns {"frames": records (flags: 1 hdr ok, 2 crc ok, 4 complete, 16 hdr seen), "bytes": [n, stride]}."""
+        s = np.ascontiguousarray(samples, np.complex64)
+        n = s.shape[0]
+        cap = n // max(1, self.cp_len) + 16
+        recs = np.zeros(cap, FRAME_DTYPE)
+        by = np.zeros((cap, byte_stride), np.uint8)
+        k = C.c_int64()
+        rc = self.L.orc_rx_all(self._pp, _ptr(s), n, _ptr(recs), cap, _ptr(by), byte_stride, C.byref(k))
+        if rc:
+            raise RuntimeError("orc_rx_all failed: %d" % rc)
+        return {"frames": recs[:k.value].copy(), "bytes": by[:k.value]}
+
     def rx_baseline(self, samples, max_frames=None, byte_stride=4096):
         """RX with the float32 FIR sync port (CPU-baseline timing only). Returns frame records."""
         s = np.ascontiguousarray(samples, np.complex64)
@@ -320,7 +344,12 @@ def crc32_mac(data):
     return lib().orc_crc32_mac(_ptr(a) if len(a) else None, len(a))
 
 
-def agc2(samples, gain=1.0, attack=1e-1, decay=1e-2, reference=1.0, max_gain=65536.0):
+def set_threads(n=0):
+    """OpenMP team size of the oracle's parallel loops (0: query).  Returns the size in effect."""
+    return int(lib().orc_set_threads(int(n)))
+
+
+def agc2(samples, gain=1.0, attack=1e-1, decay=1e-2, reference=1.0, max_gain=65536.0, abs_rate=False):
     """analog.agc2_cc over one stream (or each row of a 2-D array).  Returns (out, final gain(s))."""
     x = np.ascontiguousarray(samples, np.complex64)
     one = x.ndim == 1
@@ -329,12 +358,13 @@ def agc2(samples, gain=1.0, attack=1e-1, decay=1e-2, reference=1.0, max_gain=655
     g = np.broadcast_to(np.asarray(gain, np.float32), (x2.shape[0],)).copy()
     for s in range(x2.shape[0]):
         gs = np.array([g[s]], np.float32)
-        lib().orc_agc2(_ptr(x2[s]), _ptr(out[s]), x2.shape[1], attack, decay, reference, max_gain, _ptr(gs))
+        lib().orc_agc2_v(_ptr(x2[s]), _ptr(out[s]), x2.shape[1], attack, decay, reference, max_gain, _ptr(gs),
+                         int(bool(abs_rate)))
         g[s] = gs[0]
     return (out[0], float(g[0])) if one else (out, g)
 
 
-def iir_ccd(samples, fftaps, fbtaps, state=None):
+def iir_ccd(samples, fftaps, fbtaps, state=None, oldstyle=False):
     """filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False) over one stream.  state: None (fresh block) or the
     float64 array a previous call returned.  Returns (out complex64, state)."""
     x = np.ascontiguousarray(samples, np.complex64)
@@ -343,7 +373,7 @@ def iir_ccd(samples, fftaps, fbtaps, state=None):
     ns = 2 * (len(ff) - 1) + 2 * max(len(fb) - 1, 0)
     st = np.zeros(max(ns, 1), np.float64) if state is None else np.array(state, np.float64)
     out = np.empty_like(x)
-    lib().orc_iir_ccd(_ptr(x), _ptr(out), len(x), _ptr(ff), len(ff), _ptr(fb), len(fb), _ptr(st))
+    lib().orc_iir_ccd_v(_ptr(x), _ptr(out), len(x), _ptr(ff), len(ff), _ptr(fb), len(fb), _ptr(st), int(bool(oldstyle)))
     return out, st
 
 
@@ -374,14 +404,14 @@ def repack(items, k, l, align_output):
     return out[:n]
 
 
-def constellation(bps):
+def constellation(bps, norm=0):
     pts = np.zeros(1 << bps, np.complex64)
-    lib().orc_constellation(bps, _ptr(pts))
+    lib().orc_constellation_n(bps, int(norm), _ptr(pts))
     return pts
 
 
-def decide(bps, z):
-    return lib().orc_decide(bps, float(np.real(z)), float(np.imag(z)))
+def decide(bps, z, norm=0):
+    return lib().orc_decide_n(bps, int(norm), float(np.real(z)), float(np.imag(z)))
 
 
 def fft(x, forward=True):

@@ -22,9 +22,9 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.ofdmx_abi_version() == 3
+    assert lib.ofdmx_abi_version() == 4 == _lib.ABI_VERSION
     assert lib.ofdmx_profile_slots() >= 10
-    assert lib.ofdmx_profile_name(0) == b"sync_metric_kernel"
+    assert lib.ofdmx_profile_name(1) == b"plateau_kernel"
     names = {lib.ofdmx_profile_name(i) for i in range(lib.ofdmx_profile_slots())}
     assert {b"rx_framew_kernel", b"sync_metric_fast_kernel", b"sync_metric_tma_kernel"} <= names
 
@@ -35,6 +35,37 @@ def test_struct_layouts():
     assert phy.FRAME_DTYPE.itemsize == 32
     assert C.sizeof(_lib.Counts) == 16
     assert _lib.Params.fft_len.offset == 0 and _lib.Params.occ_sizes.offset == 16
+    # the binding's structs against the sizes the library itself was compiled with, and against the C header
+    # compiled here by gcc (field by field)
+    lib = _lib.load()
+    assert lib.ofdmx_params_size() == C.sizeof(_lib.Params)
+    assert lib.ofdmx_frame_size() == phy.FRAME_DTYPE.itemsize
+    import subprocess
+    import tempfile
+    fields = [n for n, _ in _lib.Params._fields_]
+    prog = "#include <stdio.h>\n#include <stddef.h>\n#include \"ofdmx.h\"\nint main(void){printf(\"%zu\", sizeof(ofdmx_params));" \
+        + "".join('printf(" %%zu", offsetof(ofdmx_params, %s));' % f for f in fields) \
+        + 'printf(" %zu %zu", sizeof(ofdmx_frame), sizeof(ofdmx_counts)); return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "l.c"), os.path.join(td, "l")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+        vals = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert vals[0] == C.sizeof(_lib.Params)
+    assert vals[1:1 + len(fields)] == [getattr(_lib.Params, f).offset for f in fields]
+    assert vals[-2:] == [32, 16]
+
+
+def test_integration_md_stub_matches_binding():
+    """The ctypes stub INTEGRATION.md shows a maintainer is generated from _lib.Params: every field, in order."""
+    from ofdm_tools import _lib
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = txt[txt.index("class Params(C.Structure)"):]
+    block = block[:block.index("```")]
+    names = re.findall(r'\("([a-z0-9_]+)",', block)
+    assert names == [n for n, _ in _lib.Params._fields_]
+    assert "OFDMX_ABI_VERSION" in txt or "ofdmx_abi_version" in txt
+    assert "not built" not in txt
 
 
 def test_no_cpu_fallback():

@@ -198,10 +198,9 @@ __device__ __forceinline__ int f1k_decide(float re, float im, const uint8_t *__r
     }
     constexpr int side = (BPS == 4) ? 4 : 8;
     constexpr float half = 0.5f * (float)side;
-    int rs = __float2int_rz(fmaf(re, inv_w, half));
-    int is = __float2int_rz(fmaf(im, inv_w, half));
-    rs = min(max(rs, 0), side - 1);
-    is = min(max(is, 0), side - 1);
+    // float -> unsigned conversion saturates at 0 (negative, NaN) by itself: only the upper clamp is an instruction
+    const unsigned rs = min(__float2uint_rz(fmaf(re, inv_w, half)), (unsigned)(side - 1));
+    const unsigned is = min(__float2uint_rz(fmaf(im, inv_w, half)), (unsigned)(side - 1));
     return lut[rs * side + is];
 }
 

@@ -19,6 +19,7 @@
 #pragma once
 #include "ofdmx_frame1024.cuh"
 #include "ofdmx_symbol_small.cuh"
+#include <type_traits>
 
 #define FW_WARPS 16
 #define FW_THREADS (FW_WARPS * 32)
@@ -158,9 +159,11 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
     float2 *ipts = tws + TWN;                                    // [64]
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(ipts + 64);    // [256] CRC-32 table
     uint32_t *s_pow = s_tab + 256;                                // [32]
-    uint16_t *s_occ = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] union bin of carrier u
-    uint16_t *s_pos = s_occ + ((nu + 7) & ~7);                    // [nu] position in the serialiser order
-    uint8_t *lut = reinterpret_cast<uint8_t *>(s_pos + ((nu + 7) & ~7));   // [64]
+    // carriers are walked in SERIALISER order (position p in occupied_carriers[0]): the decisions of a symbol land at
+    // dec[p] without a position look-up, and the channel state Hs[p] is read lane-contiguously
+    uint16_t *s_bin = reinterpret_cast<uint16_t *>(s_pow + 32);   // [nu] shifted bin of the carrier at position p
+    uint16_t *s_nat = s_bin + ((nu + 7) & ~7);                    // [nu] its natural-order FFT bin when the carrier offset is 0
+    uint8_t *lut = reinterpret_cast<uint8_t *>(s_nat + ((nu + 7) & ~7));   // [64]
     // ---- per-warp buffers
     constexpr int YSLOT = (NFFT == 2048) ? 2 * F1K_SLOT : (NFFT == 1024) ? F1K_SLOT : NFFT;      // float2 per symbol buffer
     // fft_len 1024 keeps its steady-state code minimal: configurations whose bits per OFDM symbol are not a byte
@@ -199,13 +202,15 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
             sincospif(-(float)i * (1.0f / 1024.0f), &sn, &cs);
             tws[1024 + i] = make_float2(cs, sn);
         }
-    for (int i = tid; i < nu; i += NTH) { s_occ[i] = (uint16_t)p.occ_u[i]; s_pos[i] = (uint16_t)p.pos_su[i]; }
+    for (int i = tid; i < nu; i += NTH) { const int b = p.occ_bins[i]; s_bin[i] = (uint16_t)b; s_nat[i] = (uint16_t)(b ^ (NFFT / 2)); }
     // (strided loops: the CTA may have fewer than 256 threads when the per-warp buffers are large)
     for (int i = tid; i < 256; i += NTH) s_tab[i] = p.crc_tab[i];
     for (int i = tid; i < 32; i += NTH) s_pow[i] = p.crc_pow64[i];
     for (int i = tid; i < 64; i += NTH) {
         lut[i] = p.lut_p[i];
-        ipts[i] = (i < (1 << BPS_P)) ? p.inv_ppts[i] : make_float2(0.f, 0.f);
+        // (1 - alpha) / constellation point: the decision-directed update is H <- alpha H + (1 - alpha) y / s
+        const float2 ip = (i < (1 << BPS_P)) ? p.inv_ppts[i] : make_float2(0.f, 0.f);
+        ipts[i] = make_float2((1.0f - p.alpha) * ip.x, (1.0f - p.alpha) * ip.y);
     }
     __syncthreads();
 
@@ -310,7 +315,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                 __syncwarp();
                 // H[k] = Y2[k+off] / sw2[k] (overwrites the parked Y1 bins)
                 for (int u = lane; u < nu; u += 32) {
-                    const int k = s_occ[u];
+                    const int k = s_bin[u];
                     const int src = k + off;
                     float2 Hk = make_float2(0.f, 0.f);
                     if (src >= 0 && src < N) Hk = cmul(ybin(src ^ HALF), p.inv_sw2[k]);
@@ -326,22 +331,40 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                     pc = make_float2(cs, -sn);
                     rot = make_float2(cs, sn);
                 }
-                for (int u = lane; u < nu; u += 32) {
-                    const int src = (int)s_occ[u] + off;
-                    float2 y = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) y = cmul(ybin(src ^ HALF), pc);
-                    float2 Hk = Hs[u];
-                    const float hinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
-                    const float2 hn = cmul_conj(y, Hk);
-                    const float2 z = make_float2(hn.x * hinv, hn.y * hinv);
-                    const int d = z.x > 0.f;
-                    const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
-                    Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
-                    const int pos = s_pos[u];
-                    if (pos < 64) hb[pos] = (uint8_t)d;          // descrambled after the ballot (hmask32)
-                    if (WANT_Z) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + pos] = z;
-                    Hs[u] = cmul(Hk, rot);
-                }
+                // two carriers per lane and trip, straight-line (clamped index, predicated stores): the two dependent
+                // chains interleave
+                auto hdr_eq = [&](auto off0) {
+                    constexpr bool OFF0 = decltype(off0)::value;
+                    for (int p0 = lane; p0 < nu; p0 += 64) {
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++) {
+                        // lanes past the end redo a carrier of their own (position `lane`): nothing is stored for them
+                        const int pp = p0 + 32 * jj, pc_ = (pp < nu) ? pp : lane;
+                        float2 y;
+                        if (OFF0) y = ybin(s_nat[pc_]);
+                        else {
+                            const int src = (int)s_bin[pc_] + off;
+                            y = (src >= 0 && src < N) ? cmul(ybin(src ^ HALF), pc) : make_float2(0.f, 0.f);
+                        }
+                        float2 Hk = Hs[pc_];
+                        const float2 hn = cmul_conj(y, Hk);
+                        const int d = hn.x > 0.f;                    // sign of re(y / H): |H|^2 > 0 does not change it
+                        const float2 q = make_float2(d ? y.x : -y.x, d ? y.y : -y.y);       // y / (+-1)
+                        Hk = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
+                        if (!OFF0) Hk = cmul(Hk, rot);
+                        if (pp < nu) {
+                            if (pp < 64) hb[pp] = (uint8_t)d;        // descrambled after the ballot (hmask32)
+                            if (WANT_Z) {
+                                const float2 H0 = Hs[pc_];
+                                const float hinv = f1k_rcp(fmaf(H0.x, H0.x, H0.y * H0.y));
+                                z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + pp] = make_float2(hn.x * hinv, hn.y * hinv);
+                            }
+                            Hs[pp] = Hk;
+                        }
+                    }
+                    }
+                };
+                if (off == 0) hdr_eq(std::true_type{}); else hdr_eq(std::false_type{});
                 __syncwarp();
                 const unsigned bits = __ballot_sync(0xffffffffu, hb[lane] & 1) ^ hmask32;
                 const int plen = (int)(bits & 0xFFFu);
@@ -380,35 +403,55 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                 const int cb = i * size0;
                 // bits per OFDM symbol not a multiple of 8 (dec_all > 0): keep the decisions of the whole packet, pack at the end
                 uint8_t *decw = dec + (dec_all > 0 ? cb : 0);
-                // one carrier per lane per trip; the index look-ups of the NEXT trip are issued before the arithmetic of
-                // this one, so the dependent chain of a trip starts at the data loads (deeper pipelining, also of the Y/H
-                // loads, measured slower: more code and registers)
-                int kc = (lane < nu) ? (int)s_occ[lane] : 0, posc = (lane < nu) ? (int)s_pos[lane] : 0;
-                for (int u = lane; u < nu; u += 32) {
-                    const int un = u + 32;
-                    int kn = 0, posn = 0;
-                    if (un < nu) { kn = (int)s_occ[un]; posn = (int)s_pos[un]; }
-                    const int src = kc + off;
-                    float2 y = make_float2(0.f, 0.f);
-                    if (src >= 0 && src < N) {
-                        y = ybin(src ^ HALF);
-                        if (off != 0) y = cmul(y, pc);
+                // two carriers per lane and trip in serialiser order, straight-line (clamped index, predicated stores) so
+                // that the two dependent chains (loads -> 1/|H|^2 -> decision -> table -> update) interleave
+                auto pay_eq = [&](auto off0) {
+                    constexpr bool OFF0 = decltype(off0)::value;
+                    for (int p0 = lane; p0 < nu; p0 += 64) {
+                        // phase 1: all loads of both carriers (lanes past the end redo a carrier of their own, position
+                        // `lane`; nothing is stored for them), phase 2: arithmetic, phase 3: stores -- no store sits
+                        // between the loads, so the two chains are free to interleave
+                        float2 y[2], Hk[2];
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const int pp = p0 + 32 * jj, pc_ = (pp < nu) ? pp : lane;
+                            if (OFF0) y[jj] = ybin(s_nat[pc_]);
+                            else {
+                                const int src = (int)s_bin[pc_] + off;
+                                y[jj] = (src >= 0 && src < N) ? cmul(ybin(src ^ HALF), pc) : make_float2(0.f, 0.f);
+                            }
+                            Hk[jj] = Hs[pc_];
+                        }
+                        int d[2];
+                        float2 hq[2], z[2];
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const float rinv = f1k_rcp(fmaf(Hk[jj].x, Hk[jj].x, Hk[jj].y * Hk[jj].y));
+                            const float2 nn = cmul_conj(y[jj], Hk[jj]);
+                            if (WANT_Z) {
+                                z[jj] = make_float2(nn.x * rinv, nn.y * rinv);
+                                d[jj] = f1k_decide<BPS_P>(z[jj].x, z[jj].y, lut, qiw);
+                            } else {
+                                d[jj] = f1k_decide<BPS_P>(nn.x, nn.y, lut, rinv * qiw);      // sector of nn / |H|^2
+                            }
+                            const float2 q = cmul(y[jj], ipts[d[jj]]);          // (1 - alpha) * y / decided point
+                            hq[jj] = make_float2(fmaf(al, Hk[jj].x, q.x), fmaf(al, Hk[jj].y, q.y));
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const int pp = p0 + 32 * jj;
+                            if (pp < nu) {
+                                Hs[pp] = hq[jj];
+                                decw[pp] = (uint8_t)d[jj];
+                                if (WANT_Z) {
+                                    const int idx = cb + pp;
+                                    if (idx < psyms && p.hl + idx < z_stride) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + p.hl + idx] = z[jj];
+                                }
+                            }
+                        }
                     }
-                    float2 Hk = Hs[u];
-                    const float rinv = f1k_rcp(fmaf(Hk.x, Hk.x, Hk.y * Hk.y));
-                    const float2 nn = cmul_conj(y, Hk);
-                    const float2 z = make_float2(nn.x * rinv, nn.y * rinv);
-                    const int d = f1k_decide<BPS_P>(z.x, z.y, lut, qiw);
-                    const float2 q = cmul(y, ipts[d]);
-                    Hs[u] = make_float2(fmaf(al, Hk.x, oma * q.x), fmaf(al, Hk.y, oma * q.y));
-                    decw[posc] = (uint8_t)d;
-                    if (WANT_Z) {
-                        const int idx = cb + posc;
-                        if (idx < psyms && p.hl + idx < z_stride) z_out[(unsigned long long)(unsigned)j * (unsigned long long)z_stride + p.hl + idx] = z;
-                    }
-                    kc = kn;
-                    posc = posn;
-                }
+                };
+                if (off == 0) pay_eq(std::true_type{}); else pay_eq(std::false_type{});
                 __syncwarp();
                 // repack_bits_bb(bps, 8) + additive_scrambler_bb for the bytes this OFDM symbol completes
                 const int b0 = i * sym_bytes;

@@ -44,7 +44,34 @@ static const char *const kSlotNames[K_NSLOTS] = {
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
-struct ofdmx_ctx {
+// Everything that is a function of the PHY parameters (ofdmx_params): the kernel parameter block with its table
+// pointers and the launch configuration derived from it.  ofdmx_create builds the first one, ofdmx_reconfigure
+// builds the next one next to it and swaps (the tables of two consecutive plans live in the two halves of one
+// device arena, so work enqueued under the old plan keeps reading valid tables).
+struct PlanFields {
+    ofdmx_params prm{};             // scalar fields only are used after creation (the pointers are the caller's)
+    KP kp{};
+    std::vector<int> occ_sizes;
+    int hl = 0;
+    int nsw = 2;                    // sync words in front of the header symbol (1: sync_word2=())
+    size_t frame_smem = 0, tx_smem = 0, sync_fast_smem = 0, frame1k_smem = 0, sync_tma_smem = 0;
+    int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
+    bool sync_warp_ok = false;
+    bool frame1kw = false;          // warp-per-frame kernel eligible
+    size_t frame1kw_smem = 0;
+    int frame1kw_warps = FW_WARPS;
+    int frame1kw_dec_all = 0;       // > 0: bits per OFDM symbol not a byte multiple: decisions of the whole packet kept (capacity)
+    int frame1kw_ctas = 1;          // resident CTAs per SM of the warp-per-frame kernel (fft_len < 1024: several)
+    bool tx1kw = false;             // warp-per-packet TX kernel usable
+    size_t tx1kw_smem = 0;
+    const uint16_t *tx_map = nullptr;
+    const float2 *sync_td = nullptr;
+    int frame1kw_dec_off = -1;      // float2 index inside the symbol buffer where the decisions live (-1: own array)
+    uint32_t x_2048 = 0;            // x^(8*2048) mod P
+    int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
+};
+
+struct ofdmx_ctx : PlanFields {
     bool profiling = false;
     std::vector<ProfRec> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
@@ -53,42 +80,40 @@ struct ofdmx_ctx {
     int64_t prof_errors = 0;        // event create / record failures since ofdmx_profile(ctx, 1)
     int device = 0;
     int sm_count = 148;
-    ofdmx_params prm{};
-    KP kp{};
     std::string err;
-    std::vector<void *> tables;     // device allocations owned by the context
-    // derived host copies
-    std::vector<int> occ_sizes;
-    int hl = 0;
+    // table arena: two halves, the plans alternate between them
+    DevBuf arena[2];
+    int arena_cur = 0;
+    static const int STAGE_SLOTS = 8;
+    void *stage_pinned = nullptr;   // pinned host staging of the table images: a ring of STAGE_SLOTS slots, so that the
+    size_t stage_cap = 0;           // host only ever waits for the upload issued STAGE_SLOTS reconfigurations ago
+    int stage_next = 0;
+    cudaEvent_t ev_stage[STAGE_SLOTS] = { nullptr };   // upload out of slot i finished
+    bool stage_used[STAGE_SLOTS] = { false };
+    cudaStream_t cfg_stream = nullptr;   // uploads of table images
+    cudaEvent_t ev_tables = nullptr;     // recorded behind the upload of the current plan's tables
+    cudaEvent_t ev_done[2] = { nullptr, nullptr };   // end of the work that reads arena half i (taken when the plan is left)
+    bool done_valid[2] = { false, false };
+    bool tables_pending = false;         // calls make their stream wait for ev_tables until it has completed
+    cudaStream_t last_stream = nullptr;  // stream of the most recent call (the context is single-owner)
+    bool last_stream_valid = false;
     // workspace
     DevBuf ws;
     DevBuf ws_host;                 // workspace of ofdmx_rx_host (runs on own_stream, concurrently with the caller's stream)
     DevBuf ws_papr;                 // partial sums of ofdmx_papr (may run on another stream than an RX call in flight)
     int64_t launches = 0;
+    int64_t n_dev_allocs = 0;       // cudaMalloc / cudaHostAlloc calls made by this context
+    int64_t n_host_syncs = 0;       // host-blocking synchronisations made by this context
+    int64_t n_reconfigs = 0;
     // host-buffer path
     DevBuf h_samples, h_frames, h_bytes, h_counts;
     cudaStream_t own_stream = nullptr;
-    size_t frame_smem = 0, tx_smem = 0, sync_smem = 0, sync_fast_smem = 0, frame1k_smem = 0, sync_tma_smem = 0;
-    int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
     bool no_tma = false;            // OFDMX_NO_TMA=1: use the plain-load sync kernel
     bool no_warp_sync = false;      // OFDMX_NO_WARP_SYNC=1: fft_len 1024 uses the TMA ring kernel instead of the warp-autonomous one
-    bool sync_warp_ok = false;
     bool emit_all = false;          // ofdmx_set_emit_all: frames_out receives every trigger's record
     bool no_warp_frame = false;     // OFDMX_NO_WARP_FRAME=1: use the CTA-per-frame fft_len-1024 kernel
     bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
-    bool frame1kw = false;          // fft_len 1024 warp-per-frame kernel eligible
-    size_t frame1kw_smem = 0;
-    int frame1kw_warps = FW_WARPS;
-    int frame1kw_dec_all = 0;       // > 0: bits per OFDM symbol not a byte multiple: decisions of the whole packet kept (capacity)
-    int frame1kw_ctas = 1;          // resident CTAs per SM of the warp-per-frame kernel (fft_len < 1024: several)
-    bool tx1kw = false;             // fft_len 1024 warp-per-packet TX kernel usable
     bool no_warp_tx = false;        // OFDMX_NO_WARP_TX=1: generic TX kernel
-    size_t tx1kw_smem = 0;
-    const uint16_t *tx_map = nullptr;
-    const float2 *sync_td = nullptr;
-    int frame1kw_dec_off = -1;      // float2 index inside the symbol buffer where the decisions live (-1: own array)
-    uint32_t x_2048 = 0;            // x^(8*2048) mod P
-    int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
 };
 
 namespace {
@@ -112,15 +137,21 @@ int fail(ofdmx_ctx *ctx, int code, const char *fmt, ...)
             return fail(ctx, OFDMX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));     \
     } while (0)
 
+// Table image under construction: bytes + the pointer fields that have to point into it once it has a device
+// address (offsets are 256-byte aligned).
+struct Stage {
+    std::vector<unsigned char> bytes;
+    std::vector<std::pair<const void **, size_t>> fixups;
+};
+
 template <typename T>
-int upload(ofdmx_ctx *ctx, const std::vector<T> &v, const T **out)
+int upload(Stage &st, const std::vector<T> &v, const T **out)
 {
-    void *d = nullptr;
-    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    CUDA_TRY(ctx, cudaMalloc(&d, bytes));
-    ctx->tables.push_back(d);
-    if (!v.empty()) CUDA_TRY(ctx, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = static_cast<const T *>(d);
+    const size_t off = (st.bytes.size() + 255) / 256 * 256;
+    const size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    st.bytes.resize(off + n, 0);
+    if (!v.empty()) std::memcpy(st.bytes.data() + off, v.data(), v.size() * sizeof(T));
+    st.fixups.emplace_back(reinterpret_cast<const void **>(out), off);
     return 0;
 }
 
@@ -132,6 +163,7 @@ int grow(ofdmx_ctx *ctx, DevBuf &b, size_t bytes)
     b.cap = 0;
     size_t want = bytes + bytes / 8 + 256;
     CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+    ctx->n_dev_allocs++;
     b.cap = want;
     return 0;
 }
@@ -252,7 +284,42 @@ struct Lfsr {
 
 uint32_t h_gf2_mul_x(uint32_t b) { return (b & 1u) ? ((b >> 1) ^ 0xEDB88320u) : (b >> 1); }
 
-int payload_ofdm_syms(const ofdmx_ctx *c, int n_syms)
+struct CrcTables {
+    std::vector<uint32_t> tab, pow, pow64, pow8;
+    uint32_t x_2048;
+};
+const CrcTables &crc_tables()
+{
+    static const CrcTables t = [] {
+        CrcTables r;
+        r.tab.resize(256); r.pow.resize(256); r.pow64.resize(32); r.pow8.resize(65);
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t v = i;
+            for (int k = 0; k < 8; k++) v = (v & 1u) ? ((v >> 1) ^ 0xEDB88320u) : (v >> 1);
+            r.tab[i] = v;
+        }
+        uint32_t x = 0x80000000u;   // x^0
+        for (int j = 255; j >= 0; j--) {
+            r.pow[j] = x;           // x^(128*(255-j))
+            for (int b = 0; b < 128; b++) x = h_gf2_mul_x(x);
+        }
+        x = 0x80000000u;
+        for (int l = 31; l >= 0; l--) {
+            r.pow64[l] = x;         // x^(512*(31-l))
+            for (int b = 0; b < 512; b++) x = h_gf2_mul_x(x);
+        }
+        r.x_2048 = x;               // after 32 steps of 512 bits: x^16384
+        x = 0x80000000u;
+        for (int t2 = 0; t2 <= 64; t2++) {
+            r.pow8[t2] = x;         // x^(8*t)
+            for (int b = 0; b < 8; b++) x = h_gf2_mul_x(x);
+        }
+        return r;
+    }();
+    return t;
+}
+
+int payload_ofdm_syms(const PlanFields *c, int n_syms)
 {
     int cnt = 0, acc = 0, s = 1 % c->prm.n_occ_sets;
     while (acc < n_syms) {
@@ -472,10 +539,12 @@ int ofdmx_frame_size(void) { return (int)sizeof(ofdmx_frame); }
 
 const char *ofdmx_last_error(const ofdmx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
-int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
+extern "C++" {
+// Validates the parameters and builds the plan: derived constants, the table image (stg) and the launch
+// configuration.  Host work only (plus cudaFuncSetAttribute / occupancy queries, which do not touch the device
+// queues): this is what both ofdmx_create and ofdmx_reconfigure run.
+static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
 {
-    if (!prm || !out) return fail(nullptr, OFDMX_ERR_PARAM, "null argument");
-    *out = nullptr;
     const int N = prm->fft_len;
     if (N < 32 || N > 4096 || (N & (N - 1))) return fail(nullptr, OFDMX_ERR_PARAM, "fft_len must be a power of two in 32..4096");
     if (prm->cp_len < 0 || prm->cp_len > N) return fail(nullptr, OFDMX_ERR_PARAM, "cp_len out of range");
@@ -495,16 +564,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         return fail(nullptr, OFDMX_ERR_PARAM, "Modulation not supported.");
     if (prm->max_pkt_bytes < 1 || prm->max_pkt_bytes > 4095) return fail(nullptr, OFDMX_ERR_PARAM, "max_pkt_bytes must be 1..4095");
 
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device)
-        return fail(nullptr, OFDMX_ERR_CUDA, "no CUDA device %d (this library has no CPU fallback)", device);
-
-    ofdmx_ctx *c = new ofdmx_ctx();
-    c->device = device;
     c->prm = *prm;
-    if (int rc = check_device(c)) { delete c; return rc; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
 
     KP &kp = c->kp;
     kp.N = N;
@@ -531,7 +591,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     kp.qiw_p = qiw_p;
 
     int rc = 0;
-    auto bail = [&](int code) { ofdmx_destroy(c); return code; };
+    auto bail = [&](int code) { return code; };
 
     // carrier plan
     std::vector<int> occ_bins, occ_base, occ_size, occ_u;
@@ -644,20 +704,10 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         for (size_t i = 0; i < keystream.size(); i++)
             for (int k = 0; k < 8; k++) keystream[i] ^= (uint8_t)(l.next() << k);
     }
-    // CRC tables
-    std::vector<uint32_t> crc_tab(256), crc_pow(256);
-    for (uint32_t i = 0; i < 256; i++) {
-        uint32_t v = i;
-        for (int k = 0; k < 8; k++) v = (v & 1u) ? ((v >> 1) ^ 0xEDB88320u) : (v >> 1);
-        crc_tab[i] = v;
-    }
-    {
-        uint32_t x = 0x80000000u;   // x^0
-        for (int j = 255; j >= 0; j--) {
-            crc_pow[j] = x;         // x^(128*(255-j))
-            for (int b = 0; b < 128; b++) x = h_gf2_mul_x(x);
-        }
-    }
+    // CRC tables: independent of the parameters, computed once per process (a reconfiguration only copies them)
+    const CrcTables &ct = crc_tables();
+    const std::vector<uint32_t> &crc_tab = ct.tab, &crc_pow = ct.pow, &crc_pow64 = ct.pow64, &crc_pow8 = ct.pow8;
+    c->x_2048 = ct.x_2048;
 
     // reciprocals of the constellation points, position of each union carrier in each set's list
     std::vector<float2> inv_hpts, inv_ppts;
@@ -691,23 +741,6 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     for (int l = 0; l < 24; l++)
         crc8_bit[l] = (uint8_t)(crc8_bytes(l < 12 ? (1u << l) : 0u, l < 12 ? 0u : (1u << (l - 12))) ^ kp.crc8_zero);
 
-    std::vector<uint32_t> crc_pow64(32);
-    {
-        uint32_t x = 0x80000000u;
-        for (int l = 31; l >= 0; l--) {
-            crc_pow64[l] = x;
-            for (int b = 0; b < 512; b++) x = h_gf2_mul_x(x);
-        }
-        c->x_2048 = x;      // after 32 steps of 512 bits: x^16384
-    }
-    std::vector<uint32_t> crc_pow8(65);
-    {
-        uint32_t x = 0x80000000u;
-        for (int t = 0; t <= 64; t++) {
-            crc_pow8[t] = x;
-            for (int b = 0; b < 8; b++) x = h_gf2_mul_x(x);
-        }
-    }
     kp.y1_lo = 0;
     kp.y1_span = 1;
     if (!cv_k.empty()) {
@@ -716,7 +749,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     }
 
 #define UP(vec, field)                                          \
-    if ((rc = upload(c, vec, &kp.field)) != 0) return bail(rc);
+    if ((rc = upload(stg, vec, &kp.field)) != 0) return bail(rc);
     UP(tw, tw) UP(occ_bins, occ_bins) UP(occ_base, occ_base) UP(occ_size, occ_size) UP(occ_u, occ_u)
     UP(pil_flag, pil_flag) UP(pil_val, pil_val) UP(pil_bins, pil_bins) UP(pil_base, pil_base)
     UP(pil_size, pil_size) UP(pil_sym, pil_sym) UP(pil_sym_base, pil_sym_base) UP(sw1, sw1) UP(sw2, sw2)
@@ -732,7 +765,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             fl[i - 1] = (float)(0.5 * (1 + cos(M_PI * i / kp.roll - M_PI)));
             fl[kp.roll - 1 + i - 1] = (float)(0.5 * (1 + cos(M_PI * (kp.roll - i) / kp.roll - M_PI)));
         }
-        if ((rc = upload(c, fl, &kp.roll_flank)) != 0) return bail(rc);
+        if ((rc = upload(stg, fl, &kp.roll_flank)) != 0) return bail(rc);
     }
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
     if (!kp.roll && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
@@ -741,22 +774,29 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
         for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
         for (int q = 0; q < (int)pil_bins.size(); q++) tx_map[pil_bins[q] ^ (N / 2)] = (uint16_t)(TXW_PILOT | q);
         std::vector<float2> sync_td((size_t)2 * kp.D);
-        std::vector<double> cs((size_t)N), sn((size_t)N);
-        for (int k = 0; k < N; k++) { cs[k] = cos(2.0 * M_PI * k / N); sn[k] = sin(2.0 * M_PI * k / N); }
         for (int o = 0; o < 2; o++) {
             const float *sw = o ? prm->sync_word2 : prm->sync_word1;       // shifted order, (re, im)
-            std::vector<double> xr((size_t)N), xi((size_t)N);
-            for (int t = 0; t < N; t++) {
-                double ar = 0.0, ai = 0.0;
-                for (int nn = 0; nn < N; nn++) {
-                    const double vr = sw[2 * (nn ^ (N / 2))], vi = sw[2 * (nn ^ (N / 2)) + 1];
-                    if (vr == 0.0 && vi == 0.0) continue;
-                    const int ph = (nn * t) & (N - 1);
-                    ar += vr * cs[ph] - vi * sn[ph];
-                    ai += vr * sn[ph] + vi * cs[ph];
-                }
-                xr[t] = ar; xi[t] = ai;
+            // unnormalised inverse DFT of the word (natural bin order = shifted index ^ N/2), radix-2 in double
+            std::vector<std::complex<double>> X((size_t)N);
+            for (int nn = 0; nn < N; nn++) X[nn] = std::complex<double>(sw[2 * (nn ^ (N / 2))], sw[2 * (nn ^ (N / 2)) + 1]);
+            for (int i = 1, jrev = 0; i < N; i++) {
+                int bit = N >> 1;
+                for (; jrev & bit; bit >>= 1) jrev ^= bit;
+                jrev ^= bit;
+                if (i < jrev) std::swap(X[i], X[jrev]);
             }
+            for (int len = 2; len <= N; len <<= 1) {
+                const double ang = 2.0 * M_PI / len;
+                for (int i = 0; i < N; i += len)
+                    for (int k = 0; k < len / 2; k++) {
+                        const std::complex<double> w(cos(ang * k), sin(ang * k));
+                        const std::complex<double> u = X[i + k], v = X[i + k + len / 2] * w;
+                        X[i + k] = u + v;
+                        X[i + k + len / 2] = u - v;
+                    }
+            }
+            std::vector<double> xr((size_t)N), xi((size_t)N);
+            for (int t = 0; t < N; t++) { xr[t] = X[t].real(); xi[t] = X[t].imag(); }
             for (int m = 0; m < kp.D; m++) {
                 const int t = (m - kp.cp + N) & (N - 1);
                 float vr = (float)(xr[t] * (double)kp.tx_scale), vi = (float)(xi[t] * (double)kp.tx_scale);
@@ -767,8 +807,8 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
                 sync_td[(size_t)o * kp.D + m] = make_float2(vr, vi);
             }
         }
-        if ((rc = upload(c, tx_map, &c->tx_map)) != 0) return bail(rc);
-        if ((rc = upload(c, sync_td, &c->sync_td)) != 0) return bail(rc);
+        if ((rc = upload(stg, tx_map, &c->tx_map)) != 0) return bail(rc);
+        if ((rc = upload(stg, sync_td, &c->sync_td)) != 0) return bail(rc);
         c->tx1kw = true;
     }
 
@@ -814,8 +854,9 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             c->frame1kw_smem = framew_smem_bytes(N, kp.n_occ_u, kp.y1_span, c->frame1kw_warps, c->frame1kw_dec_off >= 0, c->frame1kw_dec_all);
             // warp-per-frame kernel: fft_len 1024 (register FFT 32x32, <= 4 carrier-offset candidates), fft_len 2048 (two
             // interleaved 1024-point transforms) and fft_len 64 / 128 (register FFT + lane-shuffle FFT)
+            // (carriers are walked in list order: a list that names a carrier twice goes to the CTA-per-frame kernels)
             c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128 || N == 256 || N == 512 || N == 2048) && simple && kp.bps_h == 1
-                          && c->hl >= 32 && c->hl <= 2048
+                          && c->hl >= 32 && c->hl <= 2048 && kp.n_occ_u == occ_size[0]
                           && c->frame1kw_smem <= 227 * 1024;
             if (c->frame1kw) {
                 int occ = 1;
@@ -830,33 +871,142 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
             if (e1 != cudaSuccess || c->tx1kw_smem > 227 * 1024) c->tx1kw = false;
         }
         c->sync_tma_smem = sync_tma_smem_bytes(N);
-        if (cudaFuncSetAttribute(sync_metric_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_tma_smem) != cudaSuccess)
+        if (ofdmx_raise_smem_limit(sync_metric_tma_kernel, c->sync_tma_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s", cudaGetErrorString(cudaGetLastError())));
         {
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sync_metric_tma_kernel, SV_THREADS, c->sync_tma_smem) == cudaSuccess && occ > 0)
                 c->sync_tma_occ = occ;
         }
-        c->sync_warp_ok = (N == 1024) && cudaFuncSetAttribute(sync_metric_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                              SW_WARPS * SW_RING_BYTES) == cudaSuccess;
+        c->sync_warp_ok = (N == 1024) && ofdmx_raise_smem_limit(sync_metric_warp_kernel, SW_WARPS * SW_RING_BYTES) == cudaSuccess;
         c->sync_fast_smem = sync_fast_smem_bytes(N);
-        if (cudaFuncSetAttribute(sync_metric_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
-            || cudaFuncSetAttribute(sync_metric_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
-            || cudaFuncSetAttribute(sync_metric_fast_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
-            || cudaFuncSetAttribute(sync_metric_fast_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
-            || cudaFuncSetAttribute(sync_metric_fast_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sync_fast_smem) != cudaSuccess
-            || cudaFuncSetAttribute(rx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->frame_smem) != cudaSuccess
-            || cudaFuncSetAttribute(tx_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tx_smem) != cudaSuccess)
+        if (ofdmx_raise_smem_limit(sync_metric_fast_kernel<0>, c->sync_fast_smem) != cudaSuccess
+            || ofdmx_raise_smem_limit(sync_metric_fast_kernel<64>, c->sync_fast_smem) != cudaSuccess
+            || ofdmx_raise_smem_limit(sync_metric_fast_kernel<128>, c->sync_fast_smem) != cudaSuccess
+            || ofdmx_raise_smem_limit(sync_metric_fast_kernel<1024>, c->sync_fast_smem) != cudaSuccess
+            || ofdmx_raise_smem_limit(sync_metric_fast_kernel<2048>, c->sync_fast_smem) != cudaSuccess
+            || ofdmx_raise_smem_limit(rx_frame_kernel, c->frame_smem) != cudaSuccess
+            || ofdmx_raise_smem_limit(tx_frame_kernel, c->tx_smem) != cudaSuccess)
             return bail(fail(nullptr, OFDMX_ERR_CUDA, "shared memory configuration failed: %s (is this an sm_100 device?)",
                              cudaGetErrorString(cudaGetLastError())));
     }
+    return OFDMX_OK;
+}
+
+// Gives the table image of `np` a device address in the arena half that the running plan does not use, starts its
+// upload on the configuration stream and makes `np` the context's plan.  No device-wide synchronisation and, once
+// the arena is large enough, no allocation: work enqueued under the previous plan keeps its (by-value) parameter
+// block and its half of the arena; the next call makes its stream wait for the upload event.
+static int commit_plan(ofdmx_ctx *c, PlanFields &np, Stage &stg, bool first)
+{
+    const int h = first ? 0 : 1 - c->arena_cur;
+    const size_t need = std::max<size_t>((stg.bytes.size() + 255) / 256 * 256, 256);
+    if (!first && c->last_stream_valid) {
+        // the plan being left: everything enqueued so far is the last work that reads its half of the arena
+        CUDA_TRY(c, cudaEventRecord(c->ev_done[c->arena_cur], c->last_stream));
+        c->done_valid[c->arena_cur] = true;
+    }
+    // the half being overwritten was read by the plan before the running one: the upload is ordered (on the device)
+    // behind the end of that plan's work; the host goes on
+    if (c->done_valid[h]) CUDA_TRY(c, cudaStreamWaitEvent(c->cfg_stream, c->ev_done[h], 0));
+    if (c->arena[h].cap < need) {
+        // first use of this half, or a plan larger than anything before (capacity grows with head-room)
+        if (c->arena[h].p) {
+            CUDA_TRY(c, cudaStreamSynchronize(c->cfg_stream));
+            if (c->done_valid[h]) CUDA_TRY(c, cudaEventSynchronize(c->ev_done[h]));
+            c->n_host_syncs++;
+            CUDA_TRY(c, cudaFree(c->arena[h].p));
+            c->arena[h] = DevBuf();
+        }
+        const size_t want = std::max<size_t>(2 * need, 1 << 20);
+        CUDA_TRY(c, cudaMalloc(&c->arena[h].p, want));
+        c->n_dev_allocs++;
+        c->arena[h].cap = want;
+    }
+    if (c->stage_cap < need) {
+        if (c->stage_pinned) {
+            CUDA_TRY(c, cudaStreamSynchronize(c->cfg_stream));    // earlier images may still be on their way
+            c->n_host_syncs++;
+            CUDA_TRY(c, cudaFreeHost(c->stage_pinned));
+            c->stage_pinned = nullptr;
+            for (bool &u : c->stage_used) u = false;
+        }
+        const size_t want = std::max<size_t>(2 * need, 1 << 19);
+        CUDA_TRY(c, cudaHostAlloc(&c->stage_pinned, want * ofdmx_ctx::STAGE_SLOTS, cudaHostAllocDefault));
+        c->n_dev_allocs++;
+        c->stage_cap = want;
+    }
+    const int slot = c->stage_next;
+    c->stage_next = (slot + 1) % ofdmx_ctx::STAGE_SLOTS;
+    if (c->stage_used[slot] && cudaEventQuery(c->ev_stage[slot]) != cudaSuccess) {
+        CUDA_TRY(c, cudaEventSynchronize(c->ev_stage[slot]));     // STAGE_SLOTS reconfigurations in flight: back-pressure
+        c->n_host_syncs++;
+    }
+    unsigned char *host = static_cast<unsigned char *>(c->stage_pinned) + (size_t)slot * c->stage_cap;
+    std::memcpy(host, stg.bytes.data(), stg.bytes.size());
+    unsigned char *base = static_cast<unsigned char *>(c->arena[h].p);
+    for (auto &f : stg.fixups) *f.first = base + f.second;
+    CUDA_TRY(c, cudaMemcpyAsync(base, host, stg.bytes.size(), cudaMemcpyHostToDevice, c->cfg_stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_stage[slot], c->cfg_stream));
+    c->stage_used[slot] = true;
+    CUDA_TRY(c, cudaEventRecord(c->ev_tables, c->cfg_stream));
+    static_cast<PlanFields &>(*c) = np;
+    c->arena_cur = h;
+    c->tables_pending = true;
+    return OFDMX_OK;
+}
+
+// every entry point that launches work: the stream waits (device-side) for the current plan's tables
+static int use_stream(ofdmx_ctx *c, cudaStream_t st, bool remember = true)
+{
+    if (c->tables_pending) {
+        if (cudaEventQuery(c->ev_tables) == cudaSuccess) c->tables_pending = false;
+        else CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tables, 0));
+    }
+    if (remember) {         // (the private stream of ofdmx_rx_host is drained before that call returns)
+        c->last_stream = st;
+        c->last_stream_valid = true;
+    }
+    return 0;
+}
+}  // extern "C++"
+
+int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
+{
+    if (!prm || !out) return fail(nullptr, OFDMX_ERR_PARAM, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    // parameter errors are reported before any CUDA call (they surface on a box without a GPU too)
+    PlanFields probe;
+    Stage pstg;
+    const bool have_dev = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > device && cudaSetDevice(device) == cudaSuccess;
+    if (!have_dev) {
+        (void)cudaGetLastError();
+        // parameter validation comes first in build_plan, before its first CUDA call
+        if (build_plan(prm, &probe, pstg) == OFDMX_ERR_PARAM) return OFDMX_ERR_PARAM;
+        return fail(nullptr, OFDMX_ERR_CUDA, "no CUDA device %d (this library has no CPU fallback)", device);
+    }
+    ofdmx_ctx *c = new ofdmx_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int code) { ofdmx_destroy(c); return code; };
+    if (int rc = build_plan(prm, &probe, pstg)) return bail(rc);
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&c->cfg_stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->ev_done[0], cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&c->ev_done[1], cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream / event creation failed"));
+    for (cudaEvent_t &e : c->ev_stage)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream / event creation failed"));
+    if (int rc = commit_plan(c, probe, pstg, true)) { g_err = c->err; return bail(rc); }
     if (const char *fg = getenv("OFDMX_FORCE_GENERIC")) c->force_generic = (fg[0] == '1');
     if (const char *nw = getenv("OFDMX_NO_WARP_FRAME")) c->no_warp_frame = (nw[0] == '1');
     if (const char *nt = getenv("OFDMX_NO_TMA")) c->no_tma = (nt[0] == '1');   // plain-load sync kernel instead of the TMA ring
     if (const char *ns = getenv("OFDMX_NO_WARP_SYNC")) c->no_warp_sync = (ns[0] == '1');
     if (const char *nx = getenv("OFDMX_NO_WARP_TX")) c->no_warp_tx = (nx[0] == '1');
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
-        return bail(fail(nullptr, OFDMX_ERR_CUDA, "stream creation failed"));
     *out = c;
     return OFDMX_OK;
 }
@@ -867,9 +1017,14 @@ void ofdmx_destroy(ofdmx_ctx *c)
     cudaSetDevice(c->device);
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
-    for (void *p : c->tables) cudaFree(p);
-    for (DevBuf *b : { &c->ws, &c->ws_host, &c->ws_papr, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
+    cudaDeviceSynchronize();        // nothing of this context may still be running when its tables go away
+    for (DevBuf *b : { &c->arena[0], &c->arena[1], &c->ws, &c->ws_host, &c->ws_papr, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
         if (b->p) cudaFree(b->p);
+    if (c->stage_pinned) cudaFreeHost(c->stage_pinned);
+    if (c->ev_tables) cudaEventDestroy(c->ev_tables);
+    for (cudaEvent_t e : c->ev_done) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_stage) if (e) cudaEventDestroy(e);
+    if (c->cfg_stream) cudaStreamDestroy(c->cfg_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -942,6 +1097,7 @@ int ofdmx_sync(ofdmx_ctx *c, const float *samples_dev, int64_t n_streams, int64_
     if (int rc = check_device(c)) return rc;
     if (int rc = ofdmx_reserve(c, n_streams, n_samples, max_trig)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = use_stream(c, st)) return rc;
     RxWs w = carve(c->ws.p, n_streams, n_samples, max_trig);
     if (int rc = run_sync(c, w, (const float2 *)samples_dev, n_streams, n_samples, stride, max_trig, counts_dev, st)) return rc;
     // results are bounded by max_trig entries; copy whole arrays (stale tail entries are ignored by n_triggers)
@@ -979,6 +1135,7 @@ static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_
     if (max_frames > 0x7ffffff0LL) return fail(c, OFDMX_ERR_PARAM, "max_frames too large");
     if (int rc = check_device(c)) return rc;
     if (int rc = grow(c, wsbuf, carve(nullptr, n_streams, n_samples, max_frames).total)) return rc;
+    if (int rc = use_stream(c, st, &wsbuf != &c->ws_host)) return rc;
     RxWs w = carve(wsbuf.p, n_streams, n_samples, max_frames);
     const float2 *smp = (const float2 *)samples_dev;
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
@@ -1035,6 +1192,7 @@ int ofdmx_rx_host(ofdmx_ctx *c, const float *samples_host, int64_t n_streams, in
         return rc;
     CUDA_TRY(c, cudaMemcpyAsync(counts_host, c->h_counts.p, sizeof(ofdmx_counts), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->n_host_syncs += 2;
     const int64_t nf = std::min<int64_t>(counts_host->n_frames, max_frames);
     const int64_t ntr = std::min<int64_t>(counts_host->n_triggers, max_frames);
     if (nf > 0)
@@ -1053,6 +1211,7 @@ int ofdmx_tx(ofdmx_ctx *c, const uint8_t *payload_dev, const int64_t *pkt_off_de
     if (n_pkts == 0) return OFDMX_OK;
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = use_stream(c, st)) return rc;
     ofdmx_ctx *ctx_ = c;
     { KT(K_TX_OFF); tx_offsets_kernel<<<1, 1024, 0, st>>>(c->kp, (const long long *)pkt_off_dev, n_pkts, (long long *)sample_off_dev); }
     if (c->tx1kw && !c->no_warp_tx && !c->force_generic) {
@@ -1080,6 +1239,7 @@ int ofdmx_fft(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_syms,
     if (n_syms == 0) return OFDMX_OK;
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = use_stream(c, st)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(n_syms, (int64_t)c->sm_count * 8);
     const size_t sm = (size_t)c->kp.N * 8;
     ofdmx_ctx *ctx_ = c;
@@ -1099,6 +1259,7 @@ int ofdmx_crc32(ofdmx_ctx *c, const uint8_t *bytes_dev, const int64_t *pkt_off_d
     if (n_pkts == 0) return OFDMX_OK;
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = use_stream(c, st)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(n_pkts, (int64_t)c->sm_count * 8);
     ofdmx_ctx *ctx_ = c;
     { KT(K_CRC); crc32_kernel<<<grid, OFDMX_THREADS, 0, st>>>(bytes_dev, (const long long *)pkt_off_dev, n_pkts, crc_out_dev,
@@ -1223,31 +1384,26 @@ int ofdmx_papr(ofdmx_ctx *c, const float *in_dev, int64_t n, float *out3_dev, vo
 int ofdmx_reconfigure(ofdmx_ctx **ctx_io, const ofdmx_params *prm)
 {
     if (!ctx_io || !*ctx_io || !prm) return fail(ctx_io ? *ctx_io : nullptr, OFDMX_ERR_PARAM, "bad ofdmx_reconfigure arguments");
-    ofdmx_ctx *old = *ctx_io, *nw = nullptr;
-    // work enqueued with the old tables must have finished before they are freed
-    if (int rc = check_device(old)) return rc;
-    CUDA_TRY(old, cudaDeviceSynchronize());
-    if (int rc = ofdmx_create(prm, old->device, &nw)) { old->err = g_err; return rc; }
-    // everything that is not a function of the PHY parameters moves over: workspace, pinned staging buffers,
-    // the private stream, the profiling state and the counters
-    std::swap(nw->ws, old->ws);
-    std::swap(nw->ws_host, old->ws_host);
-    std::swap(nw->ws_papr, old->ws_papr);
-    std::swap(nw->h_samples, old->h_samples);
-    std::swap(nw->h_frames, old->h_frames);
-    std::swap(nw->h_bytes, old->h_bytes);
-    std::swap(nw->h_counts, old->h_counts);
-    std::swap(nw->own_stream, old->own_stream);
-    std::swap(nw->prof_pending, old->prof_pending);
-    std::swap(nw->prof_pool, old->prof_pool);
-    nw->profiling = old->profiling;
-    std::memcpy(nw->prof_ms, old->prof_ms, sizeof nw->prof_ms);
-    std::memcpy(nw->prof_calls, old->prof_calls, sizeof nw->prof_calls);
-    nw->launches = old->launches;
-    nw->emit_all = old->emit_all;
-    ofdmx_destroy(old);
-    *ctx_io = nw;
+    ofdmx_ctx *c = *ctx_io;
+    if (int rc = check_device(c)) return rc;
+    PlanFields np;
+    Stage stg;
+    if (int rc = build_plan(prm, &np, stg)) { c->err = g_err; return rc; }     // the running plan is untouched
+    if (int rc = commit_plan(c, np, stg, false)) return rc;
+    c->n_reconfigs++;
     return OFDMX_OK;
+}
+
+int64_t ofdmx_counter(const ofdmx_ctx *c, int which)
+{
+    if (!c) return -1;
+    switch (which) {
+    case OFDMX_CNT_LAUNCHES: return c->launches;
+    case OFDMX_CNT_DEVICE_ALLOCS: return c->n_dev_allocs;
+    case OFDMX_CNT_HOST_SYNCS: return c->n_host_syncs;
+    case OFDMX_CNT_RECONFIGS: return c->n_reconfigs;
+    default: return -1;
+    }
 }
 
 }  // extern "C"

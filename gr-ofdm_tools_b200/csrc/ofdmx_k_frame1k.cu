@@ -6,7 +6,7 @@ template <int B>
 static cudaError_t f1k_conf(size_t smem)
 {
     cudaError_t e = cudaSuccess, e2;
-#define F1K_ATTR(S, Z) e2 = cudaFuncSetAttribute(rx_frame1024_kernel<B, S, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e2 != cudaSuccess) e = e2;
+#define F1K_ATTR(S, Z) e2 = ofdmx_raise_smem_limit(rx_frame1024_kernel<B, S, Z>, smem); if (e2 != cudaSuccess) e = e2;
     F1K_ATTR(true, false) F1K_ATTR(true, true) F1K_ATTR(false, false) F1K_ATTR(false, true)
 #undef F1K_ATTR
     return e;

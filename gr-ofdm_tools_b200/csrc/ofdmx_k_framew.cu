@@ -12,8 +12,8 @@
 template <int B>
 static cudaError_t fw_conf(size_t smem, int threads, int *occ)
 {
-    cudaError_t e = cudaFuncSetAttribute(rx_framew_kernel<OFDMX_FW_N, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(rx_framew_kernel<OFDMX_FW_N, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ofdmx_raise_smem_limit(rx_framew_kernel<OFDMX_FW_N, B, false>, smem);
+    cudaError_t e2 = ofdmx_raise_smem_limit(rx_framew_kernel<OFDMX_FW_N, B, true>, smem);
     if (e == cudaSuccess) e = e2;
     if (e == cudaSuccess && occ) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rx_framew_kernel<OFDMX_FW_N, B, false>, threads, smem);
     return e;

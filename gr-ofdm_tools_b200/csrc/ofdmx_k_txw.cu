@@ -11,7 +11,7 @@
 
 cudaError_t TXW_CAT(ofdmx_txw_configure_, OFDMX_TXW_N)(int bps, size_t smem)
 {
-#define TXW_ATTR(B) case B: return cudaFuncSetAttribute(tx_framew_kernel<OFDMX_TXW_N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define TXW_ATTR(B) case B: return ofdmx_raise_smem_limit(tx_framew_kernel<OFDMX_TXW_N, B>, smem);
     switch (bps) {
     TXW_ATTR(1) TXW_ATTR(2) TXW_ATTR(3) TXW_ATTR(4) TXW_ATTR(6)
     default: return cudaErrorInvalidValue;

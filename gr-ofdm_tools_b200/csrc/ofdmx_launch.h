@@ -9,6 +9,23 @@
 
 #pragma GCC visibility push(hidden)     // internal: not exported from libofdmx.so
 
+#include <map>
+#include <mutex>
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process-wide: several contexts (or two plans of
+// one context) with different needs share it, so it only ever grows -- a launch may use less than the limit.
+template <typename F>
+static inline cudaError_t ofdmx_raise_smem_limit(F *func, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<const void *, size_t> high;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &h = high[(const void *)func];
+    if (bytes <= h) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) h = bytes;
+    return e;
+}
+
 // ---- rx_framew_kernel<NFFT, BPS, WANT_Z> (ofdmx_frame1024w.cuh): one warp per frame
 struct FwArgs {
     KP kp;

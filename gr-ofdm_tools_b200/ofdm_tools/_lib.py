@@ -13,6 +13,7 @@ OK, ERR_PARAM, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM = 0, -1, -2, -3, -4
 F_HDR_OK, F_CRC_OK, F_COMPLETE, F_ACCEPTED, F_HDR_SEEN, F_OVERSIZE = 1, 2, 4, 8, 16, 32
 ABI_VERSION = 4
 AGC2_ABS_RATE, IIR_OLDSTYLE = 1, 1
+CNT_LAUNCHES, CNT_DEVICE_ALLOCS, CNT_HOST_SYNCS, CNT_RECONFIGS = 0, 1, 2, 3
 
 
 class Params(C.Structure):
@@ -66,6 +67,7 @@ SYMBOLS = {
     "ofdmx_iir_ccd": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P, _I32, _I64, _P, _I32, _P]),
     "ofdmx_papr": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ofdmx_reconfigure": (C.c_int, [_P, _P]),
+    "ofdmx_counter": (_I64, [_P, C.c_int]),
 }
 
 _lib = None

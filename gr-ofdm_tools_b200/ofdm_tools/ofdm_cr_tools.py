@@ -48,6 +48,30 @@ def spectrum_enforcer(fft_len, spectrum_constraint_fft, lobe_len):
     return occupied_carriers, pilot_carriers, _pilot_symbols, sync_word1.tolist(), sync_word2.tolist()
 
 
+def find_nearest_l(lst, value):
+    """Nearest entry of a list (python/ofdm_cr_tools.py:451-452); the first one wins a tie."""
+    return min(lst, key=lambda x: abs(x - value))
+
+
+def spectrum_translator(spectrum_constraint_hz, fc, sf, fft_len, canc_bins):
+    """Hz -> FFT bins (python/ofdm_cr_tools.py:455-469): every constrained frequency is snapped to the nearest bin
+    centre of an fft_len-point grid of sample rate `sf` around `fc`, and canc_bins / 2 bins on either side of it
+    are put on the list that spectrum_enforcer removes from the carrier plan.  Same output as the reference,
+    element for element (bins as floats, the centre bin listed twice) -- cognitive_engine_mac.generate_sync_data
+    (python/cognitive_engine_mac.py:278-285) feeds it straight into spectrum_enforcer."""
+    resolution = float(sf) / float(fft_len)                       # Hz per bin
+    grid_hz = [(k - fft_len // 2) * resolution + fc for k in range(fft_len)]
+    half = canc_bins // 2 if isinstance(canc_bins, int) else canc_bins / 2
+    out = []
+    for f in spectrum_constraint_hz:
+        centre = (find_nearest_l(grid_hz, f) - fc) / resolution
+        x = 0
+        while x < half:
+            out.extend((centre + x, centre - x))
+            x += 1
+    return out
+
+
 # ---- MAC framing either side of the PHY (SURVEY.md 8(f) rank 3) -----------------------------------
 # Host-side byte-string helpers, as in the reference; bytes in / bytes out (the reference is Python 2 str).
 from . import crc as _crc  # noqa: E402

@@ -217,6 +217,11 @@ class OfdmPhy(object):
     def launch_count(self):
         return _lib.load().ofdmx_launch_count(self.ctx)
 
+    def counter(self, which):
+        """Life-time counters of the context (ofdmx_counter): _lib.CNT_LAUNCHES / CNT_DEVICE_ALLOCS /
+        CNT_HOST_SYNCS / CNT_RECONFIGS."""
+        return int(_lib.load().ofdmx_counter(self.ctx, int(which)))
+
     def set_emit_all(self, enable=True):
         """RX then returns one record per plateau trigger (see ofdmx_set_emit_all)."""
         _lib.check(_lib.load().ofdmx_set_emit_all(self.ctx, int(bool(enable))), self.ctx)

@@ -222,11 +222,22 @@ int ofdmx_papr(ofdmx_ctx *ctx, const float *in_dev, int64_t n, float *out3_dev, 
 
 /* Run-time reconfiguration: what cognitive_engine_mac does to the radios when
  * spectrum_enforcer hands it a new carrier plan and sync words (python/cognitive_engine_mac.py:278-285,
- * python/ofdm_cr_tools.py:348-378).  Replaces the PHY tables of *ctx_io by those of prm and keeps everything that
- * does not depend on them (workspace, pinned staging buffers, private stream, profiling state, counters), so the
- * next call runs without a new allocation.  Waits for the work already enqueued.  On success *ctx_io holds the
- * (new) handle; on failure the old context is untouched and still valid. */
+ * python/ofdm_cr_tools.py:348-378).  Swaps the PHY tables of the context at a call boundary WITHOUT draining the
+ * device: the new table image is built on the host, uploaded on a side stream into the half of the context's table
+ * arena that the running plan does not use, and the next call makes its stream wait for that upload (an event).
+ * Work already enqueued keeps running on the old tables.  No cudaDeviceSynchronize; no allocation once the arena
+ * (sized with head-room at creation) holds the plan; everything that does not depend on the parameters (workspace,
+ * staging buffers, streams, profiling state, counters) is kept.  The handle stays the same (*ctx_io is kept for
+ * source compatibility).  On failure the running plan is untouched. */
 int ofdmx_reconfigure(ofdmx_ctx **ctx_io, const ofdmx_params *prm);
+
+/* Life-time counters of a context (ofdmx_launch_count is OFDMX_CNT_LAUNCHES): lets a caller -- and the tests --
+ * assert that a steady-state call or a reconfiguration neither allocated nor blocked the host. */
+#define OFDMX_CNT_LAUNCHES      0   /* kernels launched */
+#define OFDMX_CNT_DEVICE_ALLOCS 1   /* cudaMalloc / cudaHostAlloc calls */
+#define OFDMX_CNT_HOST_SYNCS    2   /* host-blocking synchronisations (ofdmx_rx_host: 2 per call by design) */
+#define OFDMX_CNT_RECONFIGS     3   /* successful ofdmx_reconfigure calls */
+int64_t ofdmx_counter(const ofdmx_ctx *ctx, int which);
 
 #ifdef __cplusplus
 }

@@ -163,3 +163,23 @@ def test_segment_plan_and_stream_shards():
     assert plan[0][:3] == (0, 0, 250000) and plan[3][2] == 1000000 and plan[3][3] == 1000000
     for (l0, a, b, l1), nxt in zip(plan, plan[1:]):
         assert b == nxt[1] and l1 >= b + 9864 + 1096 and nxt[0] == nxt[1] - (1024 + 2 * 72 + 2)
+
+
+def test_spectrum_translator_matches_the_reference_formula():
+    """spectrum_translator (python/ofdm_cr_tools.py:455-469) against an independent evaluation of the reference's
+    formula, and through spectrum_enforcer: the constrained bins disappear from the carrier plan."""
+    from ofdm_tools import ofdm_cr_tools as T
+    fc, sf, n = 2.4e9, 1.0e6, 128
+    hz = [fc + 120e3, fc - 310e3, fc + 499e3]
+    got = T.spectrum_translator(hz, fc, sf, n, 8)
+    grid = np.linspace(-n / 2, n / 2 - 1, n) * (sf / n) + fc
+    want = []
+    for f in hz:
+        b = (grid[np.argmin(np.abs(grid - f))] - fc) / (sf / n)
+        for x in range(4):
+            want += [b + x, b - x]
+    assert got == want and len(got) == 24
+    occ, pil, pls, s1, s2 = T.spectrum_enforcer(n, got, 10)
+    assert not (set(int(b) for b in got) & set(occ[0])) and len(s1) == len(s2) == n
+    assert T.spectrum_translator([], fc, sf, n, 8) == []
+    assert T.find_nearest_l([1, 5, 9], 6) == 5

@@ -551,7 +551,8 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
     if (prm->rolloff < 0 || prm->rolloff > prm->cp_len)
         return fail(nullptr, OFDMX_ERR_PARAM, "cyclic prefixer: rolloff len must smaller than the cyclic prefix.");
     if (prm->n_occ_sets < 1 || !prm->occ_sizes || !prm->occ_carriers) return fail(nullptr, OFDMX_ERR_PARAM, "occupied_carriers missing");
-    if (!prm->sync_word1 || !prm->sync_word2) return fail(nullptr, OFDMX_ERR_PARAM, "Length of sync sequence(s) must be FFT length.");
+    if (!prm->sync_word1) return fail(nullptr, OFDMX_ERR_PARAM, "Length of sync sequence(s) must be FFT length.");
+    const int nsw = prm->sync_word2 ? 2 : 1;      // sync_word2 == NULL: the single-sync-word mode (sync_word2=())
     std::vector<float2> hpts, ppts;
     std::vector<uint8_t> lut_h, lut_p;
     float qiw_h = 1.f, qiw_p = 1.f;
@@ -649,28 +650,48 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             return bail(fail(nullptr, OFDMX_ERR_PARAM, "pilot carriers and -symbols do not match."));
 
     // sync words, chanest tables
-    std::vector<float2> sw1(N), sw2(N), inv_sw2(N), cv_conj;
+    std::vector<float2> sw1(N), sw2(N, make_float2(0.f, 0.f)), inv_sw2(N), cv_conj;
     std::vector<int> cv_k;
     int first = 0, last = N - 1;
     for (int k = 0; k < N; k++) {
         sw1[k] = make_float2(prm->sync_word1[2 * k], prm->sync_word1[2 * k + 1]);
-        sw2[k] = make_float2(prm->sync_word2[2 * k], prm->sync_word2[2 * k + 1]);
+        if (nsw == 2) sw2[k] = make_float2(prm->sync_word2[2 * k], prm->sync_word2[2 * k + 1]);
     }
-    for (int k = 0; k < N; k++) if (sw2[k].x != 0.f || sw2[k].y != 0.f) { first = k; break; }
-    for (int k = N - 1; k >= 0; k--) if (sw2[k].x != 0.f || sw2[k].y != 0.f) { last = k; break; }
+    // ofdm_chanest_vcvc: d_ref_sym = sync word 2, or sync word 1 when there is only one
+    const std::vector<float2> &ref = (nsw == 2) ? sw2 : sw1;
+    for (int k = 0; k < N; k++) if (ref[k].x != 0.f || ref[k].y != 0.f) { first = k; break; }
+    for (int k = N - 1; k >= 0; k--) if (ref[k].x != 0.f || ref[k].y != 0.f) { last = k; break; }
+    kp.nsw = nsw;
+    kp.interp = 0;
+    if (nsw == 1 && first + 1 < N && sw1[first + 1].x == 0.f && sw1[first + 1].y == 0.f) {
+        // [UPSTREAM ofdm_chanest_vcvc_impl ctor] a sync word on every second carrier: taps are interpolated
+        if (last + 1 < N) last++;
+        kp.interp = 1;
+    }
+    kp.first_act = first;
+    kp.last_act = last;
     for (int k = 0; k < N; k++) {
-        std::complex<double> a(sw1[k].x, sw1[k].y), b(sw2[k].x, sw2[k].y);
+        std::complex<double> a(sw1[k].x, sw1[k].y), b(sw2[k].x, sw2[k].y), r(ref[k].x, ref[k].y);
         inv_sw2[k] = make_float2(0.f, 0.f);
-        if (b != 0.0) {
-            std::complex<double> iv = 1.0 / b;
+        if (r != 0.0) {
+            std::complex<double> iv = 1.0 / r;
             inv_sw2[k] = make_float2((float)iv.real(), (float)iv.imag());
         }
-        if (a != 0.0) {
+        if (nsw == 2 && a != 0.0) {
             std::complex<double> cv = b / a;
             if (cv != 0.0) {
                 cv_k.push_back(k);
                 cv_conj.push_back(make_float2((float)cv.real(), (float)-cv.imag()));
             }
+        }
+    }
+    if (nsw == 1) {
+        // d_known_symbol_diffs[i] = |sw1[i] - sw1[i+2]|^2 for i = first, first+2, ... < last-2 (and < N-2); the non-zero
+        // ones go to the (cv_k, cv_conj.x) tables the offset search walks
+        for (int i = first; i < last - 2 && i < N - 2; i += 2) {
+            const double dr = (double)sw1[i].x - sw1[i + 2].x, di = (double)sw1[i].y - sw1[i + 2].y;
+            const float v = (float)(dr * dr + di * di);
+            if (v != 0.f) { cv_k.push_back(i); cv_conj.push_back(make_float2(v, 0.f)); }
         }
     }
     kp.n_cv = (int)cv_k.size();
@@ -684,7 +705,7 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
     kp.gneg = gneg;
     kp.gpos = gpos;
     for (int k : cv_k)
-        if (k + gneg < 0 || k + gpos >= N) return bail(fail(nullptr, OFDMX_ERR_PARAM, "sync words inconsistent with carrier offset range"));
+        if (nsw == 2 && (k + gneg < 0 || k + gpos >= N)) return bail(fail(nullptr, OFDMX_ERR_PARAM, "sync words inconsistent with carrier offset range"));
 
     // twiddles
     std::vector<float2> tw(N);
@@ -768,7 +789,7 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
         if ((rc = upload(stg, fl, &kp.roll_flank)) != 0) return bail(rc);
     }
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
-    if (!kp.roll && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
+    if (nsw == 2 && !kp.roll && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
         && kp.bps_h == 1 && c->hl >= 32) {
         std::vector<uint16_t> tx_map((size_t)N, (uint16_t)TXW_EMPTY);
         for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
@@ -817,7 +838,7 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
         c->frame_smem = (size_t)N * 8 * 4 + 64 + N + align_up(c->hl, 16) + align_up(kp.max_pkt_syms, 16)
                         + align_up(kp.max_pkt_bytes, 16) + 16;
         c->tx_smem = (size_t)N * 8 + 64 + align_up(kp.max_pkt_bytes + 8, 16) + align_up(c->hl, 16) + 16 + (size_t)kp.roll * 8;
-        if (N == 1024) {
+        if (N == 1024 && nsw == 2) {
             c->frame1k_warps = std::max(4, std::min(F1K_MAXW, 3 + kp.max_frame_syms));
             c->frame1k_smem = frame1024_smem_bytes(c->frame1k_warps, kp.n_occ_u, c->hl, kp.max_pkt_syms, kp.max_pkt_bytes);
             const cudaError_t e1 = ofdmx_f1k_configure(kp.bps_p, c->frame1k_smem);
@@ -856,7 +877,7 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             // interleaved 1024-point transforms) and fft_len 64 / 128 (register FFT + lane-shuffle FFT)
             // (carriers are walked in list order: a list that names a carrier twice goes to the CTA-per-frame kernels)
             c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128 || N == 256 || N == 512 || N == 2048) && simple && kp.bps_h == 1
-                          && c->hl >= 32 && c->hl <= 2048 && kp.n_occ_u == occ_size[0]
+                          && c->hl >= 32 && c->hl <= 2048 && kp.n_occ_u == occ_size[0] && nsw == 2
                           && c->frame1kw_smem <= 227 * 1024;
             if (c->frame1kw) {
                 int occ = 1;
@@ -1075,7 +1096,7 @@ int64_t ofdmx_tx_frame_samples(const ofdmx_ctx *c, int64_t payload_bytes)
     if (!c || payload_bytes < 0) return -1;
     const int64_t lp = payload_bytes + (c->kp.crc_mode ? 4 : 0);
     const int64_t ns = (lp * 8 + c->kp.bps_p - 1) / c->kp.bps_p;
-    return (int64_t)(3 + payload_ofdm_syms(c, (int)ns)) * c->kp.D + (c->kp.roll ? c->kp.roll - 1 : 0);
+    return (int64_t)(c->kp.nsw + 1 + payload_ofdm_syms(c, (int)ns)) * c->kp.D + (c->kp.roll ? c->kp.roll - 1 : 0);
 }
 
 int ofdmx_reserve(ofdmx_ctx *c, int64_t n_streams, int64_t n_samples, int64_t max_frames)

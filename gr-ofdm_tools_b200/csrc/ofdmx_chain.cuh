@@ -39,8 +39,8 @@ chain_next_kernel(const KP p, const long long *__restrict__ trig, const int *__r
         else if (!(f.flags & OFDMX_F_HDR_OK)) resume = f.trigger + 1;   // header CRC failed
         else if (!(f.flags & OFDMX_F_COMPLETE)) nx = b;           // demux stalls waiting for the payload
         else
-            resume = (f.frame_syms > 0) ? f.trigger + (long long)(3 + f.frame_syms) * p.D - p.holdoff
-                                        : f.trigger + 3LL * p.D;
+            resume = (f.frame_syms > 0) ? f.trigger + (long long)(p.nsw + 1 + f.frame_syms) * p.D - p.holdoff
+                                        : f.trigger + (long long)(p.nsw + 1) * p.D;
         if (nx < 0) {
             int lo = i + 1, hi = b;
             while (lo < hi) {

@@ -54,6 +54,10 @@ struct KP {
     const uint32_t *crc_pow8;    // [65] x^(8*t) mod P (warp CRC tail shift)
     int y1_lo, y1_span;          // shifted-bin range of sync symbol 1 that the offset search reads
     int pil_in_occ;              // some pilot carrier is also in occupied_carriers (equaliser pilot branch reachable)
+    int nsw;                     // sync words in front of the header symbol: 2, or 1 (sync_word2=(): ofdm_chanest_vcvc
+                                 // estimates the carrier offset by correlating |Y1[k]-Y1[k+2]|^2 with the known
+                                 // differences (cv_k / cv_conj.x) and takes the taps from sync word 1, interpolated)
+    int interp, first_act, last_act;   // single-word mode: d_interpolate and the active range of ofdm_chanest_vcvc
     float qiw_h, qiw_p;          // constellation_rect: 1 / sector width of the header / payload QAM table
                                  // (0.5 (side - 1) without normalisation; divided by the scale factor otherwise)
 };

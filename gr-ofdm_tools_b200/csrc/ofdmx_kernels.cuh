@@ -346,16 +346,57 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
         ofdmx_frame rec;
         rec.trigger = t; rec.cfo = cfo[j]; rec.stream = st; rec.flags = 0; rec.pkt_len = 0; rec.pkt_num = 0;
         rec.frame_syms = 0; rec.carr_offset = 0; rec.slot = (uint32_t)j;
-        if (t + 3LL * D > n) {   // header never completes in this buffer
+        const int pre = p.nsw + 1;       // OFDM symbols in front of the payload
+        if (t + (long long)pre * D > n) {   // header never completes in this buffer
             if (tid == 0) spec[j] = rec;
             continue;
         }
         // ---- sync symbols -> Y1 (bufA), Y2 (bufB)
         load_symbol(sm.bufA, p, r, n, t + p.cp, j, jend, trig, cfo);
-        load_symbol(sm.bufB, p, r, n, t + D + p.cp, j, jend, trig, cfo);
+        if (p.nsw == 2) load_symbol(sm.bufB, p, r, n, t + D + p.cp, j, jend, trig, cfo);
         __syncthreads();
         fft_smem<false>(sm.bufA, N, p.logN, p.tw);
-        fft_smem<false>(sm.bufB, N, p.logN, p.tw);
+        if (p.nsw == 2) fft_smem<false>(sm.bufB, N, p.logN, p.tw);
+        if (p.nsw == 1) {
+            // ---- ofdm_chanest_vcvc with one sync symbol [UPSTREAM get_carr_offset, "Correlate" branch]:
+            //      new_diffs[i] = |Y1[i] - Y1[i+2]|^2 (shifted order), sum_j known_diffs[j] * new_diffs[j+g], first maximum
+            float *nd = reinterpret_cast<float *>(sm.bufB);
+            for (int i = tid; i < N; i += blockDim.x) {
+                float v = 0.f;
+                if (i < N - 2) {
+                    const float2 a = ysh(sm.bufA, i, N), b = ysh(sm.bufA, i + 2, N);
+                    const float dr = a.x - b.x, di = a.y - b.y;
+                    v = dr * dr + di * di;
+                }
+                nd[i] = v;
+            }
+            __syncthreads();
+            float best = 0.f;
+            int bestg = 0;
+            const int ng = (p.gpos - p.gneg) / 2 + 1;
+            for (int gi = wid; gi < ng; gi += OFDMX_THREADS / 32) {
+                const int g = p.gneg + 2 * gi;
+                float acc = 0.f;
+                for (int c = lane; c < p.n_cv; c += 32) {
+                    const int k = p.cv_k[c] + g;
+                    if (k >= 0 && k < N) acc += p.cv_conj[c].x * nd[k];
+                }
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (acc > best) { best = acc; bestg = g; }
+            }
+            if (lane == 0) { wbest[wid] = best; wbestg[wid] = bestg; }
+            __syncthreads();
+            if (tid == 0) {
+                float b = 0.f;
+                int g = 0;
+                for (int w = 0; w < OFDMX_THREADS / 32; w++) {
+                    const float v = wbest[w];
+                    if (v > b || (v == b && v > 0.f && wbestg[w] < g)) { b = v; g = wbestg[w]; }
+                }
+                s_off = g;
+            }
+            __syncthreads();
+        } else {
         // ---- ofdm_chanest_vcvc: integer carrier offset (Schmidl & Cox second stage)
         {
             float best = 0.f;
@@ -391,18 +432,30 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
             }
             __syncthreads();
         }
+        }
         const int off = s_off;
-        // ---- channel taps H[k] = Y2[k+off] / sw2[k]
-        for (int k = tid; k < N; k += blockDim.x) {
-            const int src = k + off;
-            float2 hv = make_float2(0.f, 0.f);
-            const float2 inv = p.inv_sw2[k];
-            if (src >= 0 && src < N && (inv.x != 0.f || inv.y != 0.f)) hv = cmul(ysh(sm.bufB, src, N), inv);
-            sm.H[k] = hv;
+        // ---- channel taps H[k] = Y_ref[k+off] / ref[k]  (ref = sync word 2, or sync word 1 in the single-word mode)
+        {
+            const float2 *yref = (p.nsw == 2) ? sm.bufB : sm.bufA;
+            for (int k = tid; k < N; k += blockDim.x) {
+                const int src = k + off;
+                float2 hv = make_float2(0.f, 0.f);
+                const float2 inv = p.inv_sw2[k];
+                if (src >= 0 && src < N && (inv.x != 0.f || inv.y != 0.f)) hv = cmul(ysh(yref, src, N), inv);
+                sm.H[k] = hv;
+            }
+            __syncthreads();
+            if (p.nsw == 1 && p.interp) {
+                // sync word 1 occupies every second carrier: the taps in between copy their left neighbour
+                // [UPSTREAM get_chan_taps, d_interpolate]
+                for (int i = p.first_act + 1 + 2 * tid; i < p.last_act; i += 2 * blockDim.x) sm.H[i] = sm.H[i - 1];
+                __syncthreads();
+                if (tid == 0) sm.H[p.last_act] = sm.H[p.last_act - 1];
+            }
         }
         __syncthreads();
         // ---- header symbol
-        load_symbol(sm.bufA, p, r, n, t + 2LL * D + p.cp, j, jend, trig, cfo);
+        load_symbol(sm.bufA, p, r, n, t + (long long)p.nsw * D + p.cp, j, jend, trig, cfo);
         __syncthreads();
         fft_smem<false>(sm.bufA, N, p.logN, p.tw);
         equalize_symbol(sm.bufA, p, sm, off, 1, 0, p.bps_h, p.hpts, p.lut_h, want_z);
@@ -455,7 +508,7 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
             continue;
         }
         rec.flags |= OFDMX_F_HDR_OK;
-        if (t + (long long)(3 + fsyms) * D > n) {
+        if (t + (long long)(pre + fsyms) * D > n) {
             // payload never completes in this buffer
             if (tid == 0) spec[j] = rec;
             continue;
@@ -472,7 +525,7 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
         int pset = p.n_pil_sets ? 1 % p.n_pil_sets : 0;
         int set = 1 % p.n_occ_sets;
         for (int i = 0; i < fsyms; i++) {
-            load_symbol(sm.bufA, p, r, n, t + (long long)(3 + i) * D + p.cp, j, jend, trig, cfo);
+            load_symbol(sm.bufA, p, r, n, t + (long long)(pre + i) * D + p.cp, j, jend, trig, cfo);
             __syncthreads();
             fft_smem<false>(sm.bufA, N, p.logN, p.tw);
             equalize_symbol(sm.bufA, p, sm, off, i + 1, pset, p.bps_p, p.ppts, p.lut_p, want_z);
@@ -544,7 +597,7 @@ tx_offsets_kernel(const KP p, const long long *__restrict__ pkt_off, long long n
         if (idx < n_pkts) {
             const int lp = (int)(pkt_off[idx + 1] - pkt_off[idx]) + (p.crc_mode ? 4 : 0);
             const int ns = (lp * 8 + p.bps_p - 1) / p.bps_p;
-            v = 3 + tx_payload_ofdm_syms(p, ns);     // OFDM symbols of this frame
+            v = p.nsw + 1 + tx_payload_ofdm_syms(p, ns);     // OFDM symbols of this frame
         }
         int total;
         const int ex = block_excl_scan(v, wt, total);
@@ -599,19 +652,19 @@ tx_frame_kernel(const KP p, const uint8_t *__restrict__ payload, const long long
         for (int m = tid; m < lp; m += blockDim.x) pb[m] ^= p.keystream[m];   // additive_scrambler_bb
         __syncthreads();
         const int ns = (lp * 8 + p.bps_p - 1) / p.bps_p;       // repack_bits_bb(8, bps, key, False)
-        const int n_ofdm = 3 + tx_payload_ofdm_syms(p, ns);
+        const int n_ofdm = p.nsw + 1 + tx_payload_ofdm_syms(p, ns);
         const long long base = sample_off[pk];
         if (base + (long long)n_ofdm * p.D + nfl > cap) continue;
         int sym_base = 0, set = 0;
         for (int o = 0; o < n_ofdm; o++) {
             // ofdm_carrier_allocator_cvc: sync words, then data on occupied bins, pilots on top
-            if (o < 2) {
+            if (o < p.nsw) {
                 const float2 *sw = (o == 0) ? p.sw1 : p.sw2;
                 for (int ks = tid; ks < N; ks += blockDim.x) buf[bitrev(ks ^ (N >> 1), p.logN)] = sw[ks];
             } else {
                 for (int k = tid; k < N; k += blockDim.x) buf[k] = make_float2(0.f, 0.f);
                 __syncthreads();
-                const int di = o - 2;
+                const int di = o - p.nsw;
                 const int b0 = p.occ_base[set], sz = p.occ_size[set];
                 for (int q = tid; q < sz; q += blockDim.x) {
                     const int idx = sym_base + q;

@@ -36,11 +36,12 @@ def plan_segments(n_samples, world, fft_len, cp_len, max_frame_samples):
     return out
 
 
-def demux_chain(records, fft_len, cp_len, holdoff, n_samples):
+def demux_chain(records, fft_len, cp_len, holdoff, n_samples, n_sync_words=2):
     """The header_payload_demux acceptance rule over per-trigger records of ONE stream,
     sorted by trigger: returns the boolean mask of the frames the flowgraph emits.  Same rule as the
     device chain kernels (csrc/ofdmx_chain.cuh); used on the host to stitch segments."""
     D = fft_len + cp_len
+    pre = n_sync_words + 1                          # OFDM symbols in front of the payload
     emit = np.zeros(len(records), bool)
     pos = 0
     for i, f in enumerate(records):
@@ -48,20 +49,20 @@ def demux_chain(records, fft_len, cp_len, holdoff, n_samples):
         if t < pos:
             continue
         fl = int(f["flags"])
-        if t + 3 * D > n_samples or not (fl & _lib.F_HDR_SEEN):
+        if t + pre * D > n_samples or not (fl & _lib.F_HDR_SEEN):
             break                                   # demux waits for header samples that never come
         if not (fl & _lib.F_HDR_OK):
             pos = t + 1
             continue
         L = int(f["frame_syms"])
-        if t + (3 + L) * D > n_samples or not (fl & _lib.F_COMPLETE):
+        if t + (pre + L) * D > n_samples or not (fl & _lib.F_COMPLETE):
             break                                   # demux waits for payload samples that never come
         emit[i] = True
-        pos = t + (3 + L) * D - holdoff if L > 0 else t + 3 * D
+        pos = t + (pre + L) * D - holdoff if L > 0 else t + pre * D
     return emit
 
 
-def merge_segments(seg_records, plan, fft_len, cp_len, holdoff, n_samples):
+def merge_segments(seg_records, plan, fft_len, cp_len, holdoff, n_samples, n_sync_words=2):
     """Stitch per-segment emit-all records (triggers relative to each segment's load_start) into the
     frame list of the unsplit stream.  seg_records[r]: FRAME_DTYPE array from rank r (every trigger);
     plan: plan_segments(...).  Returns (records with absolute triggers, owner rank per record)."""
@@ -74,7 +75,7 @@ def merge_segments(seg_records, plan, fft_len, cp_len, holdoff, n_samples):
         owner.append(np.full(int(keep.sum()), r, np.int32))
     allrec = np.concatenate(owned) if owned else np.zeros(0)
     allown = np.concatenate(owner) if owner else np.zeros(0, np.int32)
-    emit = demux_chain(allrec, fft_len, cp_len, holdoff, n_samples)
+    emit = demux_chain(allrec, fft_len, cp_len, holdoff, n_samples, n_sync_words)
     out = allrec[emit].copy()
     out["flags"] |= _lib.F_ACCEPTED
     return out, allown[emit]
@@ -93,7 +94,7 @@ def rx_segmented(phy, samples, n_segments, max_pkt_bytes=None):
     finally:
         phy.set_emit_all(False)
     recs, own = merge_segments([s.frames for s in segs], plan, phy.fft_len, phy.cp_len,
-                               phy.params.demux_holdoff, n)
+                               phy.params.demux_holdoff, n, phy.n_sync_words)
     payloads = []
     for f, r in zip(recs, own):
         nb = int(f["pkt_len"])

@@ -90,8 +90,8 @@ class _ofdm_base(object):
         if sync_word2 is None:
             self.sync_word2 = _make_sync_word2(fft_len, occupied_carriers, pilot_carriers)
         else:
-            if len(sync_word2) != fft_len:
-                # includes sync_word2=(): the one-sync-word mode of the stock blocks is not built
+            # sync_word2=() selects the one-sync-word mode, as in the reference (:174-183, :311-321)
+            if len(sync_word2) and len(sync_word2) != fft_len:
                 raise ValueError("Length of sync sequence(s) must be FFT length.")
             self.sync_word2 = list(sync_word2)
         self.scramble_seed = 0x7f if scramble_bits else 0x00
@@ -121,7 +121,7 @@ class ofdm_tx(_ofdm_base):
         self.rolloff = rolloff
         self._setup(fft_len, cp_len, occupied_carriers, pilot_carriers, pilot_symbols, bps_header,
                     bps_payload, sync_word1, sync_word2, scramble_bits, rolloff=int(rolloff), **phy_kwargs)
-        self.sync_words = [self.sync_word1, self.sync_word2]
+        self.sync_words = [self.sync_word1] + ([self.sync_word2] if len(self.sync_word2) else [])
         self._pkt_num = 0
 
     def work(self, packets):

@@ -114,9 +114,11 @@ class OfdmPhy(object):
             raise ValueError("Length of sync sequence(s) must be FFT length.")
         if sync_word2 is None:
             sync_word2 = _make_sync_word2(fft_len, self.occupied_carriers, self.pilot_carriers)
-        elif len(sync_word2) != self.fft_len:
-            # the single-sync-word mode (sync_word2=()) of ofdm_chanest_vcvc is not built
+        elif len(sync_word2) not in (0, self.fft_len):
             raise ValueError("Length of sync sequence(s) must be FFT length.")
+        # sync_word2=(): one sync word, two OFDM symbols before the payload (python/ofdm_txrx_modules.py:174-183,
+        # 311-329); the library takes a NULL sync_word2 for it
+        self.n_sync_words = 2 if len(sync_word2) else 1
         self.sync_word1 = np.asarray(sync_word1, dtype=np.complex64)
         self.sync_word2 = np.asarray(sync_word2, dtype=np.complex64)
         self.bps_header, self.bps_payload = int(bps_header), int(bps_payload)
@@ -140,7 +142,7 @@ class OfdmPhy(object):
         p.n_occ_sets, p.occ_sizes, p.occ_carriers = len(self.occupied_carriers), k[0].ctypes.data, k[1].ctypes.data
         p.n_pilot_sets, p.pilot_sizes, p.pilot_carriers = len(self.pilot_carriers), k[2].ctypes.data, k[3].ctypes.data
         p.n_pilot_sym_sets, p.pilot_sym_sizes, p.pilot_symbols = len(self.pilot_symbols), k[4].ctypes.data, k[5].ctypes.data
-        p.sync_word1, p.sync_word2 = k[6].ctypes.data, k[7].ctypes.data
+        p.sync_word1, p.sync_word2 = k[6].ctypes.data, (k[7].ctypes.data if self.n_sync_words == 2 else None)
         p.bps_header, p.bps_payload = self.bps_header, self.bps_payload
         p.scramble_header = int(scramble_bits if scramble_header is None else scramble_header)
         p.scramble_seed = 0x7F if scramble_bits else 0x00
@@ -283,7 +285,7 @@ class OfdmPhy(object):
 
     # ------------------------------------------------------------------ RX
     def default_max_frames(self, n_streams, n):
-        return int(n_streams * (n // (3 * (self.fft_len + self.cp_len)) + 4))
+        return int(n_streams * (n // ((self.n_sync_words + 1) * (self.fft_len + self.cp_len)) + 4))
 
     def rx_buffers(self, max_frames, device, want_z=False, max_pkt_syms=None):
         """Pre-allocated output buffers for rx_enqueue (reusable across calls)."""

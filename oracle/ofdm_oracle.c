@@ -379,6 +379,10 @@ static inline int shifted_bin(int c, int n)
     return (c + n / 2) % n;
 }
 
+/* sync words in front of the header symbol: sync_word2 == NULL is sync_word2=() of the reference constructors
+ * (python/ofdm_txrx_modules.py:174-183,311-321): one sync word, header_payload_demux(n_sync_words + 1 = 2, ...) */
+static int n_sync_words(const orc_params *p) { return p->sync_word2 ? 2 : 1; }
+
 static int check_params(const orc_params *p)
 {
     int n = p->fft_len;
@@ -408,7 +412,7 @@ int64_t orc_tx_frame_samples(const orc_params *p, int64_t payload_bytes)
 {
     int64_t lp = payload_bytes + (p->crc_mode ? 4 : 0);
     int64_t ns = (lp * 8 + p->bps_payload - 1) / p->bps_payload;
-    return (int64_t)(3 + alloc_payload_ofdm_syms(p, (int)ns)) * (p->fft_len + p->cp_len)
+    return (int64_t)(n_sync_words(p) + 1 + alloc_payload_ofdm_syms(p, (int)ns)) * (p->fft_len + p->cp_len)
            + (p->rolloff > 1 ? p->rolloff - 1 : 0);
 }
 
@@ -465,7 +469,8 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
         uint8_t *chunks = (uint8_t *)malloc((size_t)ns_max);
         int64_t ns = orc_repack(buf, lp, 8, p->bps_payload, 0, chunks);
         int n_pay = alloc_payload_ofdm_syms(p, (int)ns);
-        int n_ofdm = 3 + n_pay;
+        const int nsw = n_sync_words(p);
+        int n_ofdm = nsw + 1 + n_pay;
         sample_off[pk] = pos;
         if (pos + (int64_t)n_ofdm * (n + cp) + nfl > cap_samples) { rc = -2; }
         int64_t sym_idx = 0; /* index into concatenated header+payload symbols */
@@ -474,10 +479,10 @@ int orc_tx(const orc_params *p, const uint8_t *payload, const int64_t *pkt_off, 
             for (int k = 0; k < n; k++) fd[k] = 0;
             if (o == 0) {
                 for (int k = 0; k < n; k++) fd[k] = p->sync_word1[2 * k] + I * p->sync_word1[2 * k + 1];
-            } else if (o == 1) {
+            } else if (o == 1 && nsw == 2) {
                 for (int k = 0; k < n; k++) fd[k] = p->sync_word2[2 * k] + I * p->sync_word2[2 * k + 1];
             } else {
-                int di = o - 2; /* data OFDM symbol index, header = 0 */
+                int di = o - nsw; /* data OFDM symbol index, header = 0 */
                 for (int k = 0; k < p->occ_sizes[set]; k++) {
                     int64_t tot = hl + ns;
                     if (sym_idx >= tot) break;
@@ -715,6 +720,55 @@ static void rx_symbol(const rx_ctx *c, int64_t i0, cd *out)
 
 /* digital.ofdm_chanest_vcvc(sw1, sw2, 1[, 0, max_carr_offset]) python/ofdm_txrx_modules.py:341,
  * python/ofdm_radio_hier.py:106.  [UPSTREAM ofdm_chanest_vcvc_impl.cc get_carr_offset/get_chan_taps] */
+/* One sync symbol: [UPSTREAM ofdm_chanest_vcvc_impl.cc, restated from memory -- parity unpinned]
+ *   ctor:  d_ref_sym = sync_symbol1; first/last active = first/last non-zero entry of it; if sync_symbol1[first+1] == 0
+ *          { last++; d_interpolate = true; };  d_known_symbol_diffs[i] = |s1[i] - s1[i+2]|^2 for
+ *          i = first, first+2, ... while i < last-2 && i < N-2
+ *   get_carr_offset ("Correlate"): new_diffs[i] = |Y1[i] - Y1[i+2]|^2 (i < N-2); for g (even, in range):
+ *          sum = sum_j known[j] * new_diffs[j+g] over j with known[j] != 0; first strict maximum wins
+ *          (indices j+g outside [0, N) are read out of bounds upstream; taken as 0 here)
+ *   get_chan_taps: taps[i-off] = Y1[i] / s1[i-off] where s1 != 0; with d_interpolate taps[i] = taps[i-1] for
+ *          i = first+1, first+3, ... < last and taps[last] = taps[last-1] */
+static int chanest_single(const rx_ctx *c, const cd *y1, cd *taps)
+{
+    const int n = c->p->fft_len;
+    int first = 0, last = n - 1, interp = 0;
+    for (int i = 0; i < n; i++) if (c->sw1[i] != 0) { first = i; break; }
+    for (int i = n - 1; i >= 0; i--) if (c->sw1[i] != 0) { last = i; break; }
+    if (first + 1 < n && c->sw1[first + 1] == 0) { if (last + 1 < n) last++; interp = 1; }
+    int gneg = -first, gpos = n - last - 1;
+    if (c->p->max_carr_offset != -1) {
+        if (-c->p->max_carr_offset > gneg) gneg = -c->p->max_carr_offset;
+        if (c->p->max_carr_offset < gpos) gpos = c->p->max_carr_offset;
+    }
+    if (gneg % 2) gneg++;
+    if (gpos % 2) gpos--;
+    double *nd = (double *)calloc((size_t)n, sizeof(double));
+    for (int i = 0; i < n - 2; i++) { cd d = y1[i] - y1[i + 2]; nd[i] = creal(d) * creal(d) + cimag(d) * cimag(d); }
+    double best = 0;
+    int off = 0;
+    for (int g = gneg; g <= gpos; g += 2) {
+        double sum = 0;
+        for (int i = first; i < last - 2 && i < n - 2; i += 2) {
+            cd d = c->sw1[i] - c->sw1[i + 2];
+            float kd = (float)(creal(d) * creal(d) + cimag(d) * cimag(d));
+            if (kd != 0.f && i + g >= 0 && i + g < n) sum += (double)kd * nd[i + g];
+        }
+        if (sum > best) { best = sum; off = g; }
+    }
+    free(nd);
+    for (int k = 0; k < n; k++) taps[k] = 0;
+    int ls = 0, le = n;
+    if (off > 0) ls = off; else if (off < 0) le = n + off;
+    for (int i = ls; i < le; i++)
+        if (c->sw1[i - off] != 0) taps[i - off] = y1[i] / c->sw1[i - off];
+    if (interp) {
+        for (int i = first + 1; i < last; i += 2) taps[i] = taps[i - 1];
+        taps[last] = taps[last - 1];
+    }
+    return off;
+}
+
 static int chanest(const rx_ctx *c, const cd *y1, const cd *y2, cd *taps)
 {
     const int n = c->p->fft_len;
@@ -842,7 +896,7 @@ static void rx_ctx_init(rx_ctx *cp, const orc_params *p, const float *r, int64_t
     }
     for (int k = 0; k < n; k++) {
         c.sw1[k] = p->sync_word1[2 * k] + I * p->sync_word1[2 * k + 1];
-        c.sw2[k] = p->sync_word2[2 * k] + I * p->sync_word2[2 * k + 1];
+        c.sw2[k] = p->sync_word2 ? p->sync_word2[2 * k] + I * p->sync_word2[2 * k + 1] : 0;
     }
 
 #undef c
@@ -866,12 +920,15 @@ static void decode_trigger(const rx_ctx *c, int64_t ti, int hl, uint8_t *dst, in
     const int n = p->fft_len, D = n + p->cp_len;
     const int64_t t = c->trig[ti];
     memset(o, 0, sizeof *o);
-    if (t + 3 * (int64_t)D > c->n_samp) { o->status = 2; return; }
+    const int nsw = n_sync_words(p), pre = nsw + 1;      /* symbols in front of the payload */
+    if (t + pre * (int64_t)D > c->n_samp) { o->status = 2; return; }
     cd *y = (cd *)malloc(sizeof(cd) * (size_t)n * 3), *H = (cd *)malloc(sizeof(cd) * (size_t)n);
     cd *zh = (cd *)malloc(sizeof(cd) * (size_t)n);
     uint8_t *hbits = (uint8_t *)malloc((size_t)hl);
-    for (int j = 0; j < 3; j++) rx_symbol(c, t + (int64_t)j * D + p->cp_len, y + (size_t)j * n);
-    int off = chanest(c, y, y + n, H);
+    /* y[0], y[1]: sync symbols (y[1] unused with one sync word); y[2]: header symbol */
+    for (int j = 0; j < nsw; j++) rx_symbol(c, t + (int64_t)j * D + p->cp_len, y + (size_t)j * n);
+    rx_symbol(c, t + (int64_t)nsw * D + p->cp_len, y + (size_t)2 * n);
+    int off = (nsw == 2) ? chanest(c, y, y + n, H) : chanest_single(c, y, H);
     frame_equalize(c, y + 2 * n, 1, off, H, p->bps_header, 0, zh);
     /* header serializer: set 0, all carriers; constellation_decoder_cb(header const) */
     for (int k = 0; k < hl; k++) {
@@ -884,7 +941,7 @@ static void decode_trigger(const rx_ctx *c, int64_t ti, int hl, uint8_t *dst, in
     o->off = off;
     if (!ok) { o->status = 1; goto done; }
     o->plen = plen; o->pnum = pnum; o->psyms = psyms; o->fsyms = fsyms;
-    if (t + (int64_t)(3 + fsyms) * D > c->n_samp) { o->status = 2; goto done; }
+    if (t + (int64_t)(pre + fsyms) * D > c->n_samp) { o->status = 2; goto done; }
     o->status = 3;
     o->crc_ok = 1;
     if (zo)
@@ -896,7 +953,7 @@ static void decode_trigger(const rx_ctx *c, int64_t ti, int hl, uint8_t *dst, in
         cd *pf = (cd *)malloc(sizeof(cd) * (size_t)n * (size_t)fsyms);
         cd *pz = (cd *)malloc(sizeof(cd) * (size_t)n * (size_t)fsyms);
         for (int i = 0; i < fsyms; i++)
-            rx_symbol(c, t + (int64_t)(3 + i) * D + p->cp_len, pf + (size_t)i * n);
+            rx_symbol(c, t + (int64_t)(pre + i) * D + p->cp_len, pf + (size_t)i * n);
         frame_equalize(c, pf, fsyms, off, H, p->bps_payload, 1, pz);
         /* ofdm_serializer_vcc(fft_len, occupied, frame_key, packet_len_key, 1) +
          * constellation_decoder_cb + repack_bits_bb(bps, 8, key, True) + descrambler */
@@ -966,13 +1023,14 @@ static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
             decode_trigger(&c, ti, hl, spec_bytes + ti * byte_stride, byte_stride, NULL, 0, &spec[ti]);
     }
     int64_t nf = 0, pos = 0, ti = 0;
+    const int pre = n_sync_words(p) + 1;
     uint8_t *scratch = (uint8_t *)malloc((size_t)(byte_stride > 0 ? byte_stride : 1));
     /* digital.header_payload_demux(3, fft_len, cp_len, key, "", True) state machine
      * (python/ofdm_txrx_modules.py:328-334,382) [UPSTREAM header_payload_demux_impl.cc] */
     while (ti < *n_trig) {
         int64_t t = trig[ti];
         if (t < pos) { ti++; continue; }
-        if (t + 3 * (int64_t)D > n_samp) break; /* header never completes */
+        if (t + pre * (int64_t)D > n_samp) break; /* header never completes */
         trig_dec dd, *d = &dd;
         const int full = nf >= max_frames;                     /* no room: decode into the scratch slot, then fail */
         uint8_t *dst = full ? scratch : bytes_out + nf * byte_stride;
@@ -994,8 +1052,8 @@ static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
         f->slot = (uint32_t)nf;
         if (d->crc_ok) f->flags |= ORC_F_CRC_OK;
         nf++;
-        if (d->fsyms > 0) pos = t + (int64_t)(3 + d->fsyms) * D - p->demux_holdoff;
-        else pos = t + 3 * (int64_t)D;
+        if (d->fsyms > 0) pos = t + (int64_t)(pre + d->fsyms) * D - p->demux_holdoff;
+        else pos = t + pre * (int64_t)D;
         ti++;
     }
     free(spec); free(spec_bytes); free(scratch);
@@ -1025,7 +1083,7 @@ int orc_rx_all(const orc_params *p, const float *r, int64_t n_samp, orc_frame *r
         orc_frame *f = &recs[ti];
         memset(f, 0, sizeof *f);
         f->trigger = trig[ti]; f->cfo = cfo[ti]; f->slot = (uint32_t)ti;
-        if (trig[ti] + 3 * (int64_t)D > n_samp) continue;
+        if (trig[ti] + (n_sync_words(p) + 1) * (int64_t)D > n_samp) continue;
         trig_dec d;
         decode_trigger(&c, ti, hl, bytes_out + ti * byte_stride, byte_stride, NULL, 0, &d);
         f->flags = ORC_F_HDR_SEEN;

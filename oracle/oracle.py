@@ -174,8 +174,9 @@ class Oracle:
             sync_word1 = make_sync_word1(fft_len, self.occ, self.pil)
         if sync_word2 is None:
             sync_word2 = make_sync_word2(fft_len, self.occ, self.pil)
-        if len(sync_word1) != fft_len or len(sync_word2) != fft_len:
+        if len(sync_word1) != fft_len or len(sync_word2) not in (0, fft_len):
             raise ValueError("Length of sync sequence(s) must be FFT length.")
+        self.n_sync_words = 2 if len(sync_word2) else 1      # sync_word2=(): python/ofdm_txrx_modules.py:174-183
         self.sw1 = np.asarray(sync_word1, dtype=np.complex64)
         self.sw2 = np.asarray(sync_word2, dtype=np.complex64)
         self.bps_header, self.bps_payload = int(bps_header), int(bps_payload)
@@ -192,7 +193,7 @@ class Oracle:
         p.n_occ_sets, p.occ_sizes, p.occ_carriers = len(self.occ), k[0].ctypes.data, k[1].ctypes.data
         p.n_pilot_sets, p.pilot_sizes, p.pilot_carriers = len(self.pil), k[2].ctypes.data, k[3].ctypes.data
         p.n_pilot_sym_sets, p.pilot_sym_sizes, p.pilot_symbols = len(self.pls), k[4].ctypes.data, k[5].ctypes.data
-        p.sync_word1, p.sync_word2 = k[6].ctypes.data, k[7].ctypes.data
+        p.sync_word1, p.sync_word2 = k[6].ctypes.data, (k[7].ctypes.data if self.n_sync_words == 2 else None)
         p.bps_header, p.bps_payload = self.bps_header, self.bps_payload
         p.scramble_header = int(scramble_bits if scramble_header is None else scramble_header)
         p.scramble_seed = 0x7F if scramble_bits else 0x00
@@ -264,7 +265,7 @@ class Oracle:
         s = np.ascontiguousarray(samples, np.complex64)
         n = s.shape[0]
         D = self.fft_len + self.cp_len
-        max_frames = max_frames or (n // (3 * D) + 4)
+        max_frames = max_frames or (n // ((self.n_sync_words + 1) * D) + 4)
         max_trig = max(16, n // max(1, self.cp_len) + 16)
         recs = np.zeros(max_frames, FRAME_DTYPE)
         by = np.zeros((max_frames, byte_stride), np.uint8)

@@ -183,3 +183,40 @@ def test_spectrum_translator_matches_the_reference_formula():
     assert not (set(int(b) for b in got) & set(occ[0])) and len(s1) == len(s2) == n
     assert T.spectrum_translator([], fc, sf, n, 8) == []
     assert T.find_nearest_l([1, 5, 9], 6) == 5
+
+
+def test_single_sync_word_mode_oracle_roundtrip():
+    """sync_word2=() (python/ofdm_txrx_modules.py:174-183,311-329): one preamble symbol, two OFDM symbols before
+    the payload, carrier offset from the |Y[k]-Y[k+2]|^2 correlation, taps from sync word 1 (interpolated).  The
+    oracle decodes its own bursts on a channel with a fractional and an integer carrier offset; the facades accept
+    the empty word and size their frames accordingly.
+
+    Two properties of the upstream algorithm shape the configurations: the taps of carriers outside sync word 1's
+    span stay zero (so the plans below end on odd carriers, which sync word 1 covers), and the difference metric is
+    blind when the FFT window sits fft_len/8 inside the prefix (cp_len/2 = 8 at fft_len 64: a quarter turn between
+    carriers k and k+2), so the fft_len 64 case pins max_carr_offset to 0 and the integer offsets are exercised at
+    fft_len 1024 / cp_len 72."""
+    from ofdm_tools import ofdm_tx, ofdm_rx
+    rng = np.random.default_rng(8)
+    occ64 = [[k for k in cm.OCC64[0] if abs(k) != 26]]
+    occ1k = [[k for k in cm.cfg_c3()["occupied_carriers"][0] if abs(k) != 302]]
+    for cfg, plen, cfo, kw in ((cm.cfg_c1(2, True, 1, sync_word2=(), occupied_carriers=occ64, max_carr_offset=0), 96, 0.15, {}),
+                               (cm.cfg_c3(sync_word2=(), occupied_carriers=occ1k), 700, 2.15, dict(fft_len=1024)),
+                               (cm.cfg_c3(sync_word2=(), occupied_carriers=occ1k), 700, -1.9, dict(fft_len=1024))):
+        orc = cm.make_oracle(cfg)
+        D = cfg["fft_len"] + cfg["cp_len"]
+        assert orc.n_sync_words == 1 and orc.frame_samples(plen) % D == 0
+        two = cm.make_oracle(dict(cfg, sync_word2=None))
+        assert orc.frame_samples(plen) == two.frame_samples(plen) - D          # one preamble symbol less
+        pk = cm.rand_packets(rng, 3, plen)
+        s, off = orc.tx(pk)
+        x = cm.channel(cm.split_frames(s, off), rng, gaps=(100, 500), snr_db=30.0, cfo=cfo, lead=300, tail=3000, **kw)
+        ref = orc.rx(x, want_z=False)
+        assert orc.payloads(ref) == pk
+        assert np.all(ref["frames"]["carr_offset"] == int(round(cfo / 2.0)) * 2)
+    t = ofdm_tx(sync_word2=())
+    assert len(t.sync_words) == 1 and t.phy.n_sync_words == 1 and not t.phy.params.sync_word2
+    r = ofdm_rx(sync_word2=())
+    assert r.phy.n_sync_words == 1
+    with pytest.raises(ValueError, match="Length of sync sequence"):
+        ofdm_rx(sync_word2=[0] * 10)

@@ -360,3 +360,37 @@ def test_reconfigure_at_a_call_boundary_without_draining():
 def phy_frame_dtype():
     from ofdm_tools.phy import FRAME_DTYPE
     return FRAME_DTYPE
+
+
+@pytest.mark.parametrize("which,cfo", [("c1", 0.2), ("c3", 0.3), ("c3", 2.2), ("c3", -1.8), ("radio", 0.1)])
+def test_single_sync_word_mode(which, cfo):
+    """sync_word2=(): TX and RX through the library against the oracle (frame sizes, samples, triggers, carrier
+    offsets, header fields, bytes, pre-decision symbols), with fractional and integer carrier offsets.  (Carrier
+    plans end on carriers sync word 1 covers, and fft_len 64 / 128 pin max_carr_offset to 0: see
+    tests/test_host.py::test_single_sync_word_mode_oracle_roundtrip.)"""
+    rng = np.random.default_rng(55)
+    if which == "c1":
+        occ = [[k for k in cm.OCC64[0] if abs(k) != 26]]
+        cfg, plen, kw = cm.cfg_c1(2, True, 1, sync_word2=(), occupied_carriers=occ, max_carr_offset=0), 96, {}
+    elif which == "c3":
+        occ = [[k for k in cm.cfg_c3()["occupied_carriers"][0] if abs(k) != 302]]
+        cfg, plen, kw = cm.cfg_c3(sync_word2=(), occupied_carriers=occ), 1500, dict(fft_len=1024, taps=cm.MULTIPATH)
+    else:
+        base = cm.cfg_radio128(4)
+        occ = [[k for k in base["occupied_carriers"][0] if k != -54]]
+        cfg, plen, kw = dict(base, sync_word2=(), occupied_carriers=occ, max_carr_offset=0), 200, dict(fft_len=128)
+    orc, phy = cm.make_oracle(cfg), cm.make_phy(cfg)
+    assert phy.n_sync_words == 1 and phy.frame_samples(plen) == orc.frame_samples(plen)
+    pk = cm.rand_packets(rng, 5, plen)
+    s_ref, off_ref = orc.tx(pk)
+    s_gpu, off_gpu = phy.tx(pk)
+    assert np.array_equal(off_gpu.cpu().numpy(), off_ref)
+    assert cm.rel_evm(s_gpu.cpu().numpy(), s_ref) < 1e-5
+    stream = cm.channel(cm.split_frames(s_ref, off_ref), rng, gaps=(0, 700), snr_db=35.0, cfo=cfo, lead=400, tail=4000, **kw)
+    res, ref = _compare_rx(cfg, stream)
+    assert res.payloads() == pk
+    assert np.all(res.frames["carr_offset"] == int(round(cfo / 2.0)) * 2)
+    # the segment stitcher and the stream adaptor know about the shorter preamble
+    from ofdm_tools import dist
+    recs, pay = dist.rx_segmented(cm.make_phy(cfg), _to_dev(stream), 3, max_pkt_bytes=plen + 4)
+    assert pay == pk and np.array_equal(recs["trigger"], res.frames["trigger"])

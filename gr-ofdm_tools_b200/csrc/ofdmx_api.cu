@@ -35,12 +35,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "(unused)", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -101,6 +101,8 @@ struct ofdmx_ctx : PlanFields {
     DevBuf ws;
     DevBuf ws_host;                 // workspace of ofdmx_rx_host (runs on own_stream, concurrently with the caller's stream)
     DevBuf ws_papr;                 // partial sums of ofdmx_papr (may run on another stream than an RX call in flight)
+    DevBuf ws_agc;                  // span bookkeeping of ofdmx_agc2 (entry / exit gains, re-run flags)
+    bool no_agc_spans = false;      // OFDMX_NO_AGC_SPANS=1: always one lane per stream
     int64_t launches = 0;
     int64_t n_dev_allocs = 0;       // cudaMalloc / cudaHostAlloc calls made by this context
     int64_t n_host_syncs = 0;       // host-blocking synchronisations made by this context
@@ -1028,6 +1030,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     if (const char *nt = getenv("OFDMX_NO_TMA")) c->no_tma = (nt[0] == '1');   // plain-load sync kernel instead of the TMA ring
     if (const char *ns = getenv("OFDMX_NO_WARP_SYNC")) c->no_warp_sync = (ns[0] == '1');
     if (const char *nx = getenv("OFDMX_NO_WARP_TX")) c->no_warp_tx = (nx[0] == '1');
+    if (const char *na = getenv("OFDMX_NO_AGC_SPANS")) c->no_agc_spans = (na[0] == '1');
     *out = c;
     return OFDMX_OK;
 }
@@ -1039,7 +1042,7 @@ void ofdmx_destroy(ofdmx_ctx *c)
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     cudaDeviceSynchronize();        // nothing of this context may still be running when its tables go away
-    for (DevBuf *b : { &c->arena[0], &c->arena[1], &c->ws, &c->ws_host, &c->ws_papr, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
+    for (DevBuf *b : { &c->arena[0], &c->arena[1], &c->ws, &c->ws_host, &c->ws_papr, &c->ws_agc, &c->h_samples, &c->h_frames, &c->h_bytes, &c->h_counts })
         if (b->p) cudaFree(b->p);
     if (c->stage_pinned) cudaFreeHost(c->stage_pinned);
     if (c->ev_tables) cudaEventDestroy(c->ev_tables);
@@ -1297,8 +1300,47 @@ int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_stre
     if (n_streams == 0 || n == 0) return OFDMX_OK;
     if (int rc = check_device(c)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((n_streams + 32 * AGC_WARPS - 1) / (32 * AGC_WARPS));
     ofdmx_ctx *ctx_ = c;
+    const int abs_rate = (flags & OFDMX_AGC2_ABS_RATE) ? 1 : 0;
+    // Few streams: cut every stream into spans that run in parallel from a warm-up, accepted only when their entry
+    // gain equals the predecessor's exit gain bit for bit (ofdmx_cond.cuh).  Needs separate in / out buffers (a
+    // re-run reads the input again) and spans several warm-up lengths long.
+    {
+        // spans of >= 16 K samples (the usual warm-up is 10-15 K for a tracked signal); the warm-up of a row is chosen
+        // on the device from the level in front of it and capped at 4 spans
+        long long min_span = 16384;
+        if (const char *e = getenv("OFDMX_AGC_SPAN")) min_span = std::max(1024LL, atoll(e));
+        const long long lanes = (long long)c->sm_count * 16 * 32;
+        const bool disjoint = (out_dev + 2 * ((n_streams - 1) * stride + n) <= in_dev) || (in_dev + 2 * ((n_streams - 1) * stride + n) <= out_dev);
+        long long spans = std::min<long long>(lanes / n_streams, n / min_span);
+        if (disjoint && spans >= 8 && !c->no_agc_spans) {
+            const long long span = ((n + spans - 1) / spans + 31) / 32 * 32;
+            const long long warm = 4 * span;
+            spans = (n + span - 1) / span;
+            const long long rows = n_streams * spans;
+            const int rounds = 6;
+            if (int rc = grow(c, c->ws_agc, (size_t)rows * 12 + 256)) return rc;
+            float *entry = (float *)c->ws_agc.p, *exitg = entry + rows;
+            int *need = (int *)(exitg + rows), *n_open = need + rows;
+            const unsigned grid = (unsigned)((rows + 32 * AGC_WARPS - 1) / (32 * AGC_WARPS));
+            const unsigned vgrid = (unsigned)std::min<long long>((rows + 255) / 256, (long long)c->sm_count * 4);
+            CUDA_TRY(c, cudaMemsetAsync(n_open, 0, sizeof(int) * 16, st));
+            { KT(K_AGC2); agc2_span_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
+                (int)spans, span, (int)warm, attack, decay, reference, max_gain, gain_io_dev, 1.0f, entry, exitg, need, 0, abs_rate); }
+            for (int r = 0; r < rounds; r++) {
+                { KT(K_AGC2_AUX); agc2_verify_kernel<<<vgrid, 256, 0, st>>>((int)n_streams, (int)spans, entry, exitg, need, n_open + r); }
+                { KT(K_AGC2); agc2_span_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
+                    (int)spans, span, (int)warm, attack, decay, reference, max_gain, gain_io_dev, 1.0f, entry, exitg, need, 1, abs_rate); }
+            }
+            { KT(K_AGC2_AUX); agc2_verify_kernel<<<vgrid, 256, 0, st>>>((int)n_streams, (int)spans, entry, exitg, need, n_open + rounds); }
+            { KT(K_AGC2_AUX); agc2_mopup_kernel<<<(unsigned)((n_streams + 63) / 64), 64, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride,
+                (int)n_streams, (int)spans, span, attack, decay, reference, max_gain, entry, exitg, n_open + rounds, abs_rate); }
+            { KT(K_AGC2_AUX); agc2_final_kernel<<<(unsigned)((n_streams + 255) / 256), 256, 0, st>>>((int)n_streams, (int)spans, exitg, gain_io_dev); }
+            CUDA_TRY(c, cudaGetLastError());
+            return OFDMX_OK;
+        }
+    }
+    const unsigned grid = (unsigned)((n_streams + 32 * AGC_WARPS - 1) / (32 * AGC_WARPS));
     { KT(K_AGC2); agc2_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,
                                                       attack, decay, reference, max_gain, gain_io_dev,
                                                       (flags & OFDMX_AGC2_ABS_RATE) ? 1 : 0); }

@@ -65,6 +65,169 @@ agc2_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// agc2_cc on FEW streams: time-parallel spans with a bit-exact acceptance test.
+//
+// The gain recurrence is contractive while the loop tracks a signal (two gain trajectories fed the same samples
+// approach each other by a factor 1 - rate |x| per sample), so in float32 a trajectory started `warm` samples early
+// from a guessed gain normally becomes IDENTICAL, bit for bit, to the true one before its span begins.  "Normally" is
+// not a proof, so it is checked: span k is accepted only if the gain it had when it entered its span equals the exit
+// gain of span k-1 bit for bit -- identical state and identical input give an identical future, so an accepted chain
+// from the exact first span IS the sequential result.  Spans that fail are re-run from their predecessor's exit gain
+// (agc2_span_kernel with repair = 1), a few rounds of that are enqueued, and what is still open afterwards is walked
+// sequentially (agc2_mopup_kernel) -- so the output always equals the sequential recurrence; only the time varies.
+//   row r = (stream s, span k): samples [k*span - (k ? warm : 0), min(n, (k+1)*span)), output written from k*span on.
+//   entry[r] / exitg[r]: gain before the first / after the last sample of the span; need[r]: row has to be (re)run.
+// Same 32 x 32 tile transposes as agc2_kernel (rows are spans of one stream, `span` samples apart).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float agc2_step(float2 &x, float g, float attack, float decay, float reference, float max_gain,
+                                           int abs_rate)
+{
+    const float re = __fmul_rn(x.x, g), im = __fmul_rn(x.y, g);
+    x = make_float2(re, im);
+    const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+    const float tmp = __fadd_rn(-reference, mag);
+    const float rate = ((abs_rate ? fabsf(tmp) : tmp) > g) ? attack : decay;
+    g = __fsub_rn(g, __fmul_rn(tmp, rate));
+    if (g < 0.0f) g = 10e-5f;
+    if (max_gain > 0.0f && g > max_gain) g = max_gain;
+    return g;
+}
+
+__global__ void __launch_bounds__(AGC_WARPS * 32)
+agc2_span_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, long long stride, int n_streams,
+                 int spans, long long span, int warm, float attack, float decay, float reference, float max_gain,
+                 const float *__restrict__ gain_io, float guess, float *__restrict__ entry, float *__restrict__ exitg,
+                 int *__restrict__ need, int repair, int abs_rate)
+{
+    __shared__ float2 tile[AGC_WARPS][32][33];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long rows = (long long)n_streams * spans;
+    const long long r0 = ((long long)blockIdx.x * AGC_WARPS + w) * 32;
+    if (r0 >= rows) return;
+    const long long row = r0 + lane;
+    const bool live = row < rows;
+    const int s = live ? (int)(row / spans) : 0, k = live ? (int)(row - (long long)s * spans) : 0;
+    bool run = live;
+    if (repair) run = live && k > 0 && need[row] != 0;
+    if (!__any_sync(0xffffffffu, run)) return;
+    const long long a = (long long)k * span;                       // first sample of the span
+    // warm-up length of this row: the loop forgets its state at 1 - decay |x| per sample, so ~24 time constants
+    // 1 / (decay E|x|) take a gain error of order one below float resolution (plus a margin for the last bits to
+    // coincide); E|x| is sampled from the 256 samples in front of the span.  Capped at `warm`: a row whose loop
+    // barely contracts (weak signal, zero gap) will fail the acceptance test and be repaired instead.
+    int skip = 0;
+    if (!repair && k > 0 && run) {
+        const float2 *q = in + (long long)s * stride + a;
+        float m = 0.f;
+        const int cnt = (int)min(64LL, a / 4);
+        for (int i = 1; i <= cnt; i++) { const float2 v = q[-4 * i]; m += fabsf(v.x) + fabsf(v.y); }
+        m = (cnt > 0) ? m * 0.75f / (float)cnt : 0.f;              // |re| + |im| ~ 1.3 |x|
+        const float tau = 1.0f / fmaxf(decay * m, 1e-9f);
+        const float want = fminf(24.0f * tau + 1536.0f, (float)warm);
+        skip = (int)min((long long)want, a);
+        skip = (skip + 31) & ~31;                                  // keep 256-byte alignment of the row start
+        if (skip > a) skip = (int)a;
+    }
+    const long long first = a - skip, len = min(span, n - a) + skip;
+    float g = 1.0f;
+    if (run) g = (k == 0 || !repair) ? gain_io[s] : exitg[row - 1];      // warm-up guess: the gain the call was entered with
+    if (run && repair) entry[row] = g;
+    const float2 *src = in + (long long)s * stride + first;
+    float2 *dst = out + (long long)s * stride + first;
+    // per-lane geometry differs (the first span has no warm-up): lanes exchange it by shuffles inside the tile loops
+    long long maxlen = run ? len : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    for (long long i0 = 0; i0 < maxlen; i0 += 32) {
+        // load: row rr of the tile = 32 consecutive samples of lane rr's range
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr++) {
+            const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)src, rr);
+            const long long ln = __shfl_sync(0xffffffffu, run ? len : 0, rr);
+            float2 v = make_float2(0.f, 0.f);
+            if (i0 + lane < ln) v = __ldcs(reinterpret_cast<const float2 *>(sp) + i0 + lane);
+            tile[w][rr][lane] = v;
+        }
+        __syncwarp();
+        if (run) {
+            const int nc = (int)min((long long)32, len - i0);
+#pragma unroll 4
+            for (int q = 0; q < nc; q++) {
+                if (!repair && i0 + q == skip) entry[row] = g;     // gain on entering the span proper
+                float2 x = tile[w][lane][q];
+                g = agc2_step(x, g, attack, decay, reference, max_gain, abs_rate);
+                tile[w][lane][q] = x;
+            }
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr++) {
+            const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)dst, rr);
+            const long long ln = __shfl_sync(0xffffffffu, run ? len : 0, rr);
+            const int sk = __shfl_sync(0xffffffffu, skip, rr);
+            if (i0 + lane < ln && i0 + lane >= sk) __stcs(reinterpret_cast<float2 *>(dp) + i0 + lane, tile[w][rr][lane]);
+        }
+        __syncwarp();
+    }
+    if (run) {
+        if (!repair && len <= skip) entry[row] = g;
+        exitg[row] = g;
+    }
+}
+
+// need[r] = the span's entry gain differs (bitwise) from its predecessor's exit gain; counts them per stream.
+__global__ void agc2_verify_kernel(int n_streams, int spans, const float *__restrict__ entry, const float *__restrict__ exitg,
+                                   int *__restrict__ need, int *__restrict__ n_open)
+{
+    const long long rows = (long long)n_streams * spans;
+    int cnt = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(r % spans);
+        int nd = 0;
+        if (k > 0) nd = __float_as_uint(entry[r]) != __float_as_uint(exitg[r - 1]);
+        need[r] = nd;
+        cnt += nd;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_open, cnt);
+}
+
+// What is still open after the repair rounds: one lane per stream walks from the first open span, span by span, from
+// its predecessor's exit gain, and stops as soon as a span's new exit gain equals the stored one with the rest of the
+// chain consistent.  Plain sequential agc2 from there: slow, exact, and normally not needed (n_open == 0 -> return).
+__global__ void agc2_mopup_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, long long stride,
+                                  int n_streams, int spans, long long span, float attack, float decay, float reference,
+                                  float max_gain, float *__restrict__ entry, float *__restrict__ exitg,
+                                  const int *__restrict__ n_open, int abs_rate)
+{
+    if (*n_open == 0) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const long long r0 = (long long)s * spans;
+    for (int k = 1; k < spans; k++) {
+        if (__float_as_uint(entry[r0 + k]) == __float_as_uint(exitg[r0 + k - 1])) continue;
+        float g = exitg[r0 + k - 1];
+        entry[r0 + k] = g;
+        const long long a = (long long)k * span, e = min(n, a + span);
+        const float2 *src = in + (long long)s * stride;
+        float2 *dst = out + (long long)s * stride;
+        for (long long i = a; i < e; i++) {
+            float2 x = src[i];
+            g = agc2_step(x, g, attack, decay, reference, max_gain, abs_rate);
+            dst[i] = x;
+        }
+        exitg[r0 + k] = g;
+    }
+}
+
+// final gains back to gain_io
+__global__ void agc2_final_kernel(int n_streams, int spans, const float *__restrict__ exitg, float *__restrict__ gain_io)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_streams) gain_io[s] = exitg[(long long)s * spans + spans - 1];
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // filter.iir_filter_ccd(fftaps, fbtaps, oldstyle=False): the out-of-band TX filter of ofdm_radio_hier
 // (python/ofdm_radio_hier.py:83-84,93,232-237; python/sync_radio_hier.py:73,165) -- SURVEY.md 8(f) rank 2.
 // [UPSTREAM gr-filter iir_filter<gr_complex, gr_complex, double, gr_complexd>::filter]:

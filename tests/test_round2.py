@@ -394,3 +394,43 @@ def test_single_sync_word_mode(which, cfo):
     from ofdm_tools import dist
     recs, pay = dist.rx_segmented(cm.make_phy(cfg), _to_dev(stream), 3, max_pkt_bytes=plen + 4)
     assert pay == pk and np.array_equal(recs["trigger"], res.frames["trigger"])
+
+
+@pytest.mark.parametrize("n_streams,n,kind", [(1, 3000000, "ofdm"), (3, 1500000, "levels"), (1, 2000000, "gaps"), (2, 1200000, "weak")])
+def test_agc2_time_parallel_spans_are_bit_exact(n_streams, n, kind):
+    """ofdmx_agc2 on few long streams: spans run in parallel from a warm-up and are accepted only when their entry gain
+    equals the predecessor's exit gain bit for bit, failing spans are re-run -- the output and the final gains must
+    equal the sequential recurrence (the oracle) exactly, whatever the signal does: steady OFDM-like input, level
+    jumps, zero gaps (no contraction while the gain ramps), and a weak signal whose loop barely contracts (the
+    warm-ups do not converge: everything is repaired / walked sequentially, still exact)."""
+    import time
+    import oracle as O
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((n_streams, n)) + 1j * rng.standard_normal((n_streams, n))).astype(np.complex64) * 0.2
+    if kind == "levels":
+        for i, a in enumerate((1.0, 30.0, 0.03, 4.0, 0.5, 200.0)):
+            x[:, i * n // 6:(i + 1) * n // 6] *= a
+    elif kind == "gaps":
+        x[:, n // 5: n // 5 + 300000] = 0
+        x[:, n // 2: n // 2 + 5000] = 0
+        x[:, 3 * n // 4:] *= 50.0
+    elif kind == "weak":
+        x *= 1e-3
+    phy = cm.make_phy(cm.cfg_c1())
+    xd = _to_dev(x)
+    ref, gref = O.agc2(x)
+    y, g = phy.agc2(xd)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    y, g = phy.agc2(xd)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert np.array_equal(y.cpu().numpy(), ref), "span-parallel agc2 differs from the sequential recurrence"
+    assert np.array_equal(g.cpu().numpy(), np.atleast_1d(gref).astype(np.float32))
+    # continuing the stream in a second call (gain carried) stays exact, also with the fabsf rate rule
+    k = n // 2 + 77
+    ya, ga = phy.agc2(xd[:, :k].contiguous(), abs_rate=True)
+    yb, ga = phy.agc2(xd[:, k:].contiguous(), gain=ga, abs_rate=True)
+    r2, g2 = O.agc2(x, abs_rate=True)
+    assert np.array_equal(torch.cat([ya, yb], 1).cpu().numpy(), r2) and np.array_equal(ga.cpu().numpy(), np.atleast_1d(g2).astype(np.float32))
+    print("agc2 %s: %d x %d samples in %.2f ms = %.2f Gsamples/s" % (kind, n_streams, n, dt * 1e3, n_streams * n / dt / 1e9))

@@ -401,7 +401,8 @@ def run_rx_config(cid, C, args, dev, world, rank, dist, clock_sampler=None, with
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms, best, med = float(tmax[0]), float(tmax[6]), float(tmax[7])
         launches, n_all = int(t[1]), int(t[2])
-        gate["full_size"].update(frames_sent=int(t[5]), frames_found=int(t[3]), crc_ok=int(t[4]) if phy.crc_mode else None)
+        gate["full_size"].update(frames_sent=int(t[5]), frames_found=int(t[3]), crc_ok=int(t[4]) if phy.crc_mode else None,
+                                 records="%d on rank 0" % len(fr), payload_equal_to_sent="%d on rank 0" % n_same)
     else:
         best, med, n_all = float(np.min(per)), float(np.median(per)), n
     value = n_all * args.steps / (ms * 1e-3) / 1e6
@@ -414,6 +415,18 @@ def run_rx_config(cid, C, args, dev, world, rank, dist, clock_sampler=None, with
         xh_np = xh.numpy()
         r = phy.rx_host(xh_np, max_frames=max_frames)       # warm (allocates the staging buffers)
         assert len(r.frames) == len(fr)
+        # the box's host-to-device ceiling for this shape: the bare pinned copy, all ranks at once (what bounds e2e)
+        xd = torch.empty_like(x)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            xd.copy_(xh, non_blocking=True)
+        torch.cuda.synchronize()
+        tc = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        h2d_ceiling = 8 * n / float(tc[0]) / 1e9
+        del xd
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -426,7 +439,11 @@ def run_rx_config(cid, C, args, dev, world, rank, dist, clock_sampler=None, with
         d2h = 16 + 32 * len(r.frames) + r.n_triggers * phy.byte_stride
         e2e = {"value": n_all / float(te[0]) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n,
                "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-               "h2d_gbs_per_rank": 8 * n / float(te[0]) / 1e9, "api": "ofdmx_rx_host (C ABI, pinned host input)"}
+               "h2d_gbs_per_rank": 8 * n / float(te[0]) / 1e9, "api": "ofdmx_rx_host (C ABI, pinned host input)",
+               "bare_pinned_h2d_copy_gbs_per_rank": h2d_ceiling,
+               "note": "bare_pinned_h2d_copy = cudaMemcpyAsync of the same pinned buffer alone, all ranks concurrently "
+                       "(max over ranks): the box's host-to-device ceiling for this shape; e2e cannot exceed "
+                       "8 B/sample / that"}
         del xh, xh_np
     # ---- the hier-block surface: analog.agc2_cc in front of the receiver (ofdm_radio_hier.rx / ofdm_tx_rx_hier.rx with
     # their default agc=True, python/ofdm_radio_hier.py:180-181), headline configuration only

@@ -103,6 +103,8 @@ struct ofdmx_ctx : PlanFields {
     DevBuf ws_papr;                 // partial sums of ofdmx_papr (may run on another stream than an RX call in flight)
     DevBuf ws_agc;                  // span bookkeeping of ofdmx_agc2 (entry / exit gains, re-run flags)
     bool no_agc_spans = false;      // OFDMX_NO_AGC_SPANS=1: always one lane per stream
+    float2 *h_taps = nullptr;       // ofdmx_set_debug_taps
+    long long h_stride = 0;
     int64_t launches = 0;
     int64_t n_dev_allocs = 0;       // cudaMalloc / cudaHostAlloc calls made by this context
     int64_t n_host_syncs = 0;       // host-blocking synchronisations made by this context
@@ -592,6 +594,8 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
     kp.roll_flank = nullptr;
     kp.qiw_h = qiw_h;
     kp.qiw_p = qiw_p;
+    kp.h_taps = nullptr;
+    kp.h_stride = 0;
 
     int rc = 0;
     auto bail = [&](int code) { return code; };
@@ -1091,6 +1095,14 @@ int ofdmx_set_emit_all(ofdmx_ctx *c, int enable)
     return OFDMX_OK;
 }
 
+int ofdmx_set_debug_taps(ofdmx_ctx *c, float *h_taps_dev, int64_t h_stride)
+{
+    if (!c || (h_taps_dev && h_stride < 1)) return fail(c, OFDMX_ERR_PARAM, "bad ofdmx_set_debug_taps arguments");
+    c->h_taps = (float2 *)h_taps_dev;
+    c->h_stride = h_taps_dev ? h_stride : 0;
+    return OFDMX_OK;
+}
+
 int ofdmx_header_len(const ofdmx_ctx *c) { return c ? c->hl : 0; }
 int64_t ofdmx_launch_count(const ofdmx_ctx *c) { return c ? c->launches : 0; }
 
@@ -1164,13 +1176,19 @@ static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_
     const float2 *smp = (const float2 *)samples_dev;
     if (int rc = run_sync(c, w, smp, n_streams, n_samples, stride, max_frames, counts_dev, st)) return rc;
     ofdmx_ctx *ctx_ = c;
-    if (c->frame1kw && !c->force_generic && !c->no_warp_frame) {
+    KP kp_call = c->kp;
+    kp_call.h_taps = c->h_taps;
+    kp_call.h_stride = c->h_stride;
+    if (c->h_taps && c->h_stride < c->kp.N) return fail(c, OFDMX_ERR_CAPACITY, "debug taps: stride < fft_len");
+    // (the channel-tap debug output exists in the warp-per-frame kernel's tapped variant and in the any-fft_len kernel)
+    const bool taps_generic = c->h_taps && !(c->frame1kw && z_out);
+    if (c->frame1kw && !c->force_generic && !c->no_warp_frame && !taps_generic) {
         KT(K_FRAME1KW);
-        FwArgs fa{ c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out, byte_stride,
+        FwArgs fa{ kp_call, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out, byte_stride,
                    (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all };
         if (!ofdmx_fw_launch(c->kp.N, c->kp.bps_p, (unsigned)(c->sm_count * c->frame1kw_ctas), c->frame1kw_warps * 32, c->frame1kw_smem, st, fa))
             return fail(c, OFDMX_ERR_PARAM, "no warp-per-frame kernel for this configuration");
-    } else if (c->frame1k_warps > 0 && !c->force_generic) {
+    } else if (c->frame1k_warps > 0 && !c->force_generic && !taps_generic) {
         KT(K_FRAME1K);
         const bool simple = (c->kp.n_occ_sets == 1 && c->kp.n_pil_sets <= 1 && !c->kp.pil_in_occ);
         F1kArgs fa{ c->kp, c->frame1k_warps, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec,
@@ -1179,7 +1197,7 @@ static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_
     } else {
         KT(K_FRAME);
         rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
-            c->kp, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
+            kp_call, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
             byte_stride, (float2 *)z_out, z_stride);
     }
     { KT(K_CHAIN_NEXT); chain_next_kernel<<<w.nblk, CH_T, 0, st>>>(c->kp, w.trig, w.trig_stream, w.spec, w.stream_start, w.n_trig,

@@ -58,6 +58,8 @@ struct KP {
                                  // estimates the carrier offset by correlating |Y1[k]-Y1[k+2]|^2 with the known
                                  // differences (cv_k / cv_conj.x) and takes the taps from sync word 1, interpolated)
     int interp, first_act, last_act;   // single-word mode: d_interpolate and the active range of ofdm_chanest_vcvc
+    float2 *h_taps;              // debug tap (ofdmx_set_debug_taps): the channel taps ofdm_chanest_vcvc hands to the
+    long long h_stride;          // equaliser (tag ofdm_sync_chan_taps), fft_len complex per trigger slot, shifted order
     float qiw_h, qiw_p;          // constellation_rect: 1 / sector width of the header / payload QAM table
                                  // (0.5 (side - 1) without normalisation; divided by the scale factor otherwise)
 };

@@ -321,6 +321,10 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                     if (src >= 0 && src < N) Hk = cmul(ybin(src ^ HALF), p.inv_sw2[k]);
                     Hs[u] = Hk;
                 }
+                if (WANT_Z && p.h_taps) {     // debug tap (taps of the occupied carriers; this kernel computes no others)
+                    __syncwarp();
+                    for (int u = lane; u < nu; u += 32) p.h_taps[(long long)j * p.h_stride + s_bin[u]] = Hs[u];
+                }
             } else if (sidx == 2) {
                 // header symbol: frame equaliser (offset shift + phase fix) + simpledfe with the BPSK header
                 float2 pc = make_float2(1.f, 0.f), rot = make_float2(1.f, 0.f);

@@ -454,6 +454,8 @@ rx_frame_kernel(const KP p, const float2 *__restrict__ samples, long long n, lon
             }
         }
         __syncthreads();
+        if (p.h_taps)        // debug tap: ofdm_sync_chan_taps as the header equaliser receives it
+            for (int k = tid; k < N; k += blockDim.x) p.h_taps[(long long)j * p.h_stride + k] = sm.H[k];
         // ---- header symbol
         load_symbol(sm.bufA, p, r, n, t + (long long)p.nsw * D + p.cp, j, jend, trig, cfo);
         __syncthreads();

@@ -54,6 +54,7 @@ SYMBOLS = {
     "ofdmx_tx": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _I64, _P, _P]),
     "ofdmx_rx": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P]),
     "ofdmx_set_emit_all": (C.c_int, [_P, C.c_int]),
+    "ofdmx_set_debug_taps": (C.c_int, [_P, _P, _I64]),
     "ofdmx_rx_host": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "ofdmx_sync": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _I64, _P, _P]),
     "ofdmx_profile": (C.c_int, [_P, C.c_int]),

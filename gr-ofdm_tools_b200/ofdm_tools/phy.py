@@ -224,6 +224,18 @@ class OfdmPhy(object):
         CNT_HOST_SYNCS / CNT_RECONFIGS."""
         return int(_lib.load().ofdmx_counter(self.ctx, int(which)))
 
+    def set_debug_taps(self, taps=None):
+        """Channel-estimate debug tap (ofdmx_set_debug_taps): `taps` is a zeroed cuda complex64 [max_frames, >= fft_len]
+        tensor that later rx calls fill with the initial channel taps of every trigger slot (shifted bin order, the
+        ofdm_sync_chan_taps tag of the reference chain); None switches the tap off."""
+        if taps is None:
+            _lib.check(_lib.load().ofdmx_set_debug_taps(self.ctx, None, 0), self.ctx)
+            self._taps = None
+            return
+        assert taps.is_cuda and taps.dim() == 2 and taps.stride(1) == 1 and taps.shape[1] >= self.fft_len
+        self._taps = taps
+        _lib.check(_lib.load().ofdmx_set_debug_taps(self.ctx, taps.data_ptr(), taps.stride(0)), self.ctx)
+
     def set_emit_all(self, enable=True):
         """RX then returns one record per plateau trigger (see ofdmx_set_emit_all)."""
         _lib.check(_lib.load().ofdmx_set_emit_all(self.ctx, int(bool(enable))), self.ctx)

@@ -157,6 +157,22 @@ int ofdmx_rx(ofdmx_ctx *ctx, const float *samples_dev, int64_t n_streams, int64_
  * frames.  Used to resolve the demux state exactly across the seams of a stream split over several GPUs. */
 int ofdmx_set_emit_all(ofdmx_ctx *ctx, int enable);
 
+/* Per-stage debug taps (the reference taps its chain with file sinks behind debug_log, python/ofdm_cr_tools.py:1297-1298,
+ * 1346-1348,1414-1416,1461-1467,1513-1520).  Stage by stage, what this library offers:
+ *   tx signal                      -> the output of ofdmx_tx;   post-allocator symbols -> ofdmx_fft(forward) of it
+ *   sync detect / frequency offset -> ofdmx_sync (trigger indices, arg(P) per trigger)
+ *   channel estimate               -> ofdmx_set_debug_taps: ofdmx_rx then writes the taps ofdm_chanest_vcvc hands to the
+ *                                     equaliser (tag ofdm_sync_chan_taps: fft_len complex, shifted order) for every
+ *                                     trigger whose header was seen, at h_taps_dev[slot * h_stride ..), up to one unit
+ *                                     phasor per frame (the NCO phase reference restarts at every trigger; it cancels
+ *                                     in y / H); zero the buffer
+ *                                     first -- the warp-per-frame kernel fills the occupied carriers only (it runs when
+ *                                     z_out is given as well; otherwise the any-fft_len kernel serves the call)
+ *   pre-decision symbols (post-eq) -> z_out of ofdmx_rx;   integer offset / header fields -> ofdmx_set_emit_all records
+ *   post-demod bytes               -> bytes_out of ofdmx_rx
+ * h_taps_dev == NULL switches the tap off.  h_stride in complex items, >= fft_len. */
+int ofdmx_set_debug_taps(ofdmx_ctx *ctx, float *h_taps_dev, int64_t h_stride);
+
 /* Same call with HOST buffers (pinned or pageable): copies in, runs, copies records, counts and
  * the used payload slots back, and synchronises.  This is the call a GNU Radio work() makes. */
 int ofdmx_rx_host(ofdmx_ctx *ctx, const float *samples_host, int64_t n_streams, int64_t n_samples,

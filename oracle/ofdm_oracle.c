@@ -680,6 +680,7 @@ typedef struct {
     cd *pil_val;            /* [n_pilot_sets][N] */
     int *occ_base;
     cd sw1[4096], sw2[4096];
+    const float *z_base;    /* z_out of the call (locates the frame ordinal for the taps tap) */
 } rx_ctx;
 
 /* NCO phase at delayed-stream item i: analog.frequency_modulator_fc(-2.0/fft_len) driven by the
@@ -913,6 +914,10 @@ static void rx_ctx_free(rx_ctx *c)
  * 3 header-side symbols lie inside the buffer. */
 typedef struct { int status, off, plen, pnum, psyms, fsyms, crc_ok; int64_t nbytes; } trig_dec;
 
+static float *g_taps_out = NULL;      /* debug tap of orc_rx (set by orc_set_taps_out): N complex per emitted frame */
+
+void orc_set_taps_out(float *taps) { g_taps_out = taps; }
+
 static void decode_trigger(const rx_ctx *c, int64_t ti, int hl, uint8_t *dst, int64_t byte_stride,
                            float *zo, int64_t z_stride, trig_dec *o)
 {
@@ -929,6 +934,10 @@ static void decode_trigger(const rx_ctx *c, int64_t ti, int hl, uint8_t *dst, in
     for (int j = 0; j < nsw; j++) rx_symbol(c, t + (int64_t)j * D + p->cp_len, y + (size_t)j * n);
     rx_symbol(c, t + (int64_t)nsw * D + p->cp_len, y + (size_t)2 * n);
     int off = (nsw == 2) ? chanest(c, y, y + n, H) : chanest_single(c, y, H);
+    if (g_taps_out && zo) { /* (zo identifies the output slot: taps go to the same frame ordinal) */
+        float *tp = g_taps_out + ((zo - c->z_base) / (2 * z_stride)) * 2 * (int64_t)n;
+        for (int k = 0; k < n; k++) { tp[2 * k] = (float)creal(H[k]); tp[2 * k + 1] = (float)cimag(H[k]); }
+    }
     frame_equalize(c, y + 2 * n, 1, off, H, p->bps_header, 0, zh);
     /* header serializer: set 0, all carriers; constellation_decoder_cb(header const) */
     for (int k = 0; k < hl; k++) {
@@ -1009,6 +1018,7 @@ static int rx_impl(const orc_params *p, const float *r, int64_t n_samp,
 
     rx_ctx c;
     rx_ctx_init(&c, p, r, n_samp, trig, cfo, *n_trig);
+    c.z_base = z_out;
 
     /* Per-trigger decode (header, then payload) is a pure function of the trigger: the float32-sync baseline
      * decodes every trigger speculatively on all host threads and then walks the demux state machine over the

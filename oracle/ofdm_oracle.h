@@ -96,6 +96,9 @@ int      orc_decide(int bps, double re, double im);
 /* the same with the constellation_rect normalisation switch (0 none, 1 amplitude) */
 int      orc_constellation_n(int bps, int norm, float *points);
 int      orc_decide_n(int bps, int norm, double re, double im);
+/* debug tap: orc_rx (with z_out given) also writes the channel taps ofdm_chanest_vcvc hands to the equaliser, fft_len
+ * complex (shifted order) per emitted frame ordinal; NULL switches it off.  Not thread-safe (test use). */
+void     orc_set_taps_out(float *taps);
 int      orc_rx_all(const orc_params *p, const float *r, int64_t n_samp, orc_frame *recs, int64_t max_recs,
                     uint8_t *bytes_out, int64_t byte_stride, int64_t *n_recs);
 /* OpenMP team size used by the parallel loops (0: leave as is); returns the team size in effect.  The

@@ -261,7 +261,7 @@ class Oracle:
         k = min(nt.value, max_trig)
         return (trig[:k].copy(), cfo[:k].copy(), det) if want_detect else (trig[:k].copy(), cfo[:k].copy())
 
-    def rx(self, samples, max_frames=None, byte_stride=4096, want_z=True, max_pkt_syms=None):
+    def rx(self, samples, max_frames=None, byte_stride=4096, want_z=True, max_pkt_syms=None, want_taps=False):
         s = np.ascontiguousarray(samples, np.complex64)
         n = s.shape[0]
         D = self.fft_len + self.cp_len
@@ -274,14 +274,21 @@ class Oracle:
         trig = np.zeros(max_trig, np.int64)
         cfo = np.zeros(max_trig, np.float32)
         nf, nt = C.c_int64(), C.c_int64()
-        rc = self.L.orc_rx(self._pp, _ptr(s), n, _ptr(recs), max_frames, _ptr(by), byte_stride,
-                           _ptr(z) if want_z else None, zs, C.byref(nf), _ptr(trig), _ptr(cfo),
-                           max_trig, C.byref(nt))
+        taps = np.zeros((max_frames, self.fft_len), np.complex64) if (want_taps and want_z) else None
+        self.L.orc_set_taps_out.argtypes = [C.c_void_p]
+        self.L.orc_set_taps_out(_ptr(taps) if taps is not None else None)
+        try:
+            rc = self.L.orc_rx(self._pp, _ptr(s), n, _ptr(recs), max_frames, _ptr(by), byte_stride,
+                               _ptr(z) if want_z else None, zs, C.byref(nf), _ptr(trig), _ptr(cfo),
+                               max_trig, C.byref(nt))
+        finally:
+            self.L.orc_set_taps_out(None)
         if rc:
             raise RuntimeError("orc_rx failed: %d" % rc)
         k = nf.value
         return {"frames": recs[:k].copy(), "bytes": by[:k], "z": z[:k] if want_z else None,
-                "triggers": trig[:nt.value].copy(), "cfo": cfo[:nt.value].copy()}
+                "triggers": trig[:nt.value].copy(), "cfo": cfo[:nt.value].copy(),
+                "taps": taps[:k] if taps is not None else None}
 
     def rx_all(self, samples, byte_stride=4096):
         """One record per raw plateau trigger, each decoded on its own (the counterpart of ofdmx_set_emit_all):

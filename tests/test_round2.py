@@ -434,3 +434,43 @@ def test_agc2_time_parallel_spans_are_bit_exact(n_streams, n, kind):
     r2, g2 = O.agc2(x, abs_rate=True)
     assert np.array_equal(torch.cat([ya, yb], 1).cpu().numpy(), r2) and np.array_equal(ga.cpu().numpy(), np.atleast_1d(g2).astype(np.float32))
     print("agc2 %s: %d x %d samples in %.2f ms = %.2f Gsamples/s" % (kind, n_streams, n, dt * 1e3, n_streams * n / dt / 1e9))
+
+
+@pytest.mark.parametrize("which", ["c1", "c3", "radio"])
+def test_channel_estimate_debug_tap(which):
+    """ofdmx_set_debug_taps: the taps ofdm_chanest_vcvc hands to the equaliser (ofdm_sync_chan_taps) against the
+    oracle's, from the warp-per-frame kernel (occupied carriers) and from the any-fft_len kernel (every bin of the
+    reference tag), on a multipath channel with an integer carrier offset."""
+    import os
+    rng = np.random.default_rng(61)
+    cfg, plen, kw = {"c1": (cm.cfg_c1(2, True, 1), 96, {}), "c3": (cm.cfg_c3(), 1500, dict(fft_len=1024)),
+                     "radio": (cm.cfg_radio128(4), 200, dict(fft_len=128))}[which]
+    orc = cm.make_oracle(cfg)
+    pk, fr = _frames(cfg, rng, 4, plen)
+    x = cm.channel(fr, rng, gaps=(0, 500), snr_db=35.0, cfo=2.2 if which != "c1" else 0.2, taps=cm.MULTIPATH, lead=400, tail=4000, **kw)
+    ref = orc.rx(x, want_z=True, want_taps=True, byte_stride=4096)
+    assert len(ref["frames"]) == 4
+    occ = [(c + cfg["fft_len"]) % cfg["fft_len"] for c in cfg["occupied_carriers"][0]]
+    occ_sh = [(b + cfg["fft_len"] // 2) % cfg["fft_len"] for b in occ]
+    for force in ("0", "1"):
+        os.environ["OFDMX_FORCE_GENERIC"] = force
+        try:
+            phy = cm.make_phy(cfg, max_pkt_bytes=plen + 4)
+            taps = torch.zeros((16, cfg["fft_len"]), dtype=torch.complex64, device=_dev())
+            phy.set_debug_taps(taps)
+            res = phy.rx(_to_dev(x), max_frames=16, want_z=True)
+            phy.set_debug_taps(None)
+        finally:
+            os.environ.pop("OFDMX_FORCE_GENERIC", None)
+        assert np.array_equal(res.frames["trigger"], ref["frames"]["trigger"])
+        th = taps.cpu().numpy()
+        for i, f in enumerate(res.frames):
+            got, want = th[int(f["slot"])], ref["taps"][i]
+            # the taps carry the frame's NCO phase reference (the oracle accumulates the oscillator phase over the
+            # whole stream, the kernels restart it at every trigger; it cancels in y / H): compare up to that phasor
+            ph = np.vdot(got[occ_sh], want[occ_sh])
+            got = got * (ph / abs(ph))
+            assert cm.rel_evm(got[occ_sh], want[occ_sh]) < 1e-4
+            if force == "1":
+                assert cm.rel_evm(got, want) < 1e-4          # pilots and every other bin of the tag as well
+        assert np.abs(ref["taps"][0][occ_sh]).min() > 0

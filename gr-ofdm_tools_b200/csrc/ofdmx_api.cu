@@ -795,12 +795,14 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
         if ((rc = upload(stg, fl, &kp.roll_flank)) != 0) return bail(rc);
     }
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
-    if (nsw == 2 && !kp.roll && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
+    if (nsw == 2 && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
         && kp.bps_h == 1 && c->hl >= 32) {
         std::vector<uint16_t> tx_map((size_t)N, (uint16_t)TXW_EMPTY);
         for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
         for (int q = 0; q < (int)pil_bins.size(); q++) tx_map[pil_bins[q] ^ (N / 2)] = (uint16_t)(TXW_PILOT | q);
-        std::vector<float2> sync_td((size_t)2 * kp.D);
+        const int nfl = kp.roll ? kp.roll - 1 : 0;
+        std::vector<float2> sync_td((size_t)2 * kp.D + nfl);
+        std::vector<double> tlr((size_t)std::max(nfl, 1), 0.0), tli((size_t)std::max(nfl, 1), 0.0);   // prefixer delay line (double)
         for (int o = 0; o < 2; o++) {
             const float *sw = o ? prm->sync_word2 : prm->sync_word1;       // shifted order, (re, im)
             // unnormalised inverse DFT of the word (natural bin order = shifted index ^ N/2), radix-2 in double
@@ -826,14 +828,26 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             for (int t = 0; t < N; t++) { xr[t] = X[t].real(); xi[t] = X[t].imag(); }
             for (int m = 0; m < kp.D; m++) {
                 const int t = (m - kp.cp + N) & (N - 1);
-                float vr = (float)(xr[t] * (double)kp.tx_scale), vi = (float)(xi[t] * (double)kp.tx_scale);
+                double sr = xr[t], si = xi[t];
+                if (m < nfl) {       // ofdm_cyclic_prefixer flanks: out = x * up + delay; float32 flanks as in the kernels
+                    const double up = (double)(float)(0.5 * (1 + cos(M_PI * (m + 1) / kp.roll - M_PI)));
+                    sr = sr * up + tlr[m];
+                    si = si * up + tli[m];
+                }
+                float vr = (float)(sr * (double)kp.tx_scale), vi = (float)(si * (double)kp.tx_scale);
                 if (kp.tx_clip > 0.f) {
                     vr = vr < -kp.tx_clip ? -kp.tx_clip : (vr > kp.tx_clip ? kp.tx_clip : vr);
                     vi = vi < -kp.tx_clip ? -kp.tx_clip : (vi > kp.tx_clip ? kp.tx_clip : vi);
                 }
                 sync_td[(size_t)o * kp.D + m] = make_float2(vr, vi);
             }
+            for (int m = 0; m < nfl; m++) {      // delay line left by this symbol: first body samples x down flank
+                const double dn = (double)(float)(0.5 * (1 + cos(M_PI * (kp.roll - (m + 1)) / kp.roll - M_PI)));
+                tlr[m] = xr[m] * dn;
+                tli[m] = xi[m] * dn;
+            }
         }
+        for (int m = 0; m < nfl; m++) sync_td[(size_t)2 * kp.D + m] = make_float2((float)tlr[m], (float)tli[m]);
         if ((rc = upload(stg, tx_map, &c->tx_map)) != 0) return bail(rc);
         if ((rc = upload(stg, sync_td, &c->sync_td)) != 0) return bail(rc);
         c->tx1kw = true;
@@ -893,7 +907,7 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             }
         }
         if (c->tx1kw) {
-            c->tx1kw_smem = txw_smem_bytes(N, kp.max_pkt_bytes, TXW_WARPS);
+            c->tx1kw_smem = txw_smem_bytes(N, kp.max_pkt_bytes, TXW_WARPS, kp.roll);
             const cudaError_t e1 = (c->tx1kw_smem <= 227 * 1024) ? ofdmx_txw_configure(N, kp.bps_p, c->tx1kw_smem) : cudaErrorInvalidValue;
             if (e1 != cudaSuccess || c->tx1kw_smem > 227 * 1024) c->tx1kw = false;
         }

@@ -24,10 +24,16 @@
 
 // inverse FFT of the lane-distributed spectrum v (bin 32 a + lane) + ofdm_cyclic_prefixer(rolloff 0) +
 // multiply_const(tx_scale) + clipper, stored to dst[0 .. fft_len + cp)
-template <int NFFT>
+// With rolloff (nfl = rolloff_len - 1 > 0; ofdm_cyclic_prefixer, python/ofdm_txrx_modules.py:247-253): the first nfl samples
+// of the prefixed symbol are x * up + tail, where tail (per warp, shared memory) holds the first nfl body samples of the
+// previous symbol times the down flank; this symbol's own first body samples replace it afterwards.  Same unfused float
+// operations as the CTA-per-packet kernel.
+template <int NFFT, bool ROLL>
 __device__ __forceinline__ void tx_ifft_store(float2 (&v)[NFFT / 32], float2 *__restrict__ Tw, const float2 *__restrict__ tws,
-                                              const LaneTw &ltw, float2 *__restrict__ dst, int cp, float sc, float clip, int lane)
+                                              const LaneTw &ltw, float2 *__restrict__ dst, int cp, float sc, float clip, int lane,
+                                              int nfl_arg, const float *__restrict__ flank, float2 *__restrict__ tail)
 {
+    const int nfl = ROLL ? nfl_arg : 0;      // compile-time zero without rolloff: the flank code disappears
     auto finish = [&](float2 x) {
         float2 w = make_float2(x.x * sc, x.y * sc);
         if (clip > 0.f) {
@@ -54,12 +60,36 @@ __device__ __forceinline__ void tx_ifft_store(float2 (&v)[NFFT / 32], float2 *__
         }
         fft32_inv(v);
         // straight from the registers: lane = k1, v[q] = x[k1 + 32 brev5(q)]
+        if (!ROLL) {                  // rectangular prefix: the hot loop carries nothing of the flank logic
 #pragma unroll
-        for (int q = 0; q < 32; q++) {
-            const int t = lane + 32 * brev5(q);
-            const float2 w = finish(v[q]);
-            dst[cp + t] = w;
-            if (t >= NFFT - cp) dst[t - (NFFT - cp)] = w;
+            for (int q = 0; q < 32; q++) {
+                const int t = lane + 32 * brev5(q);
+                const float2 w = finish(v[q]);
+                dst[cp + t] = w;
+                if (t >= NFFT - cp) dst[t - (NFFT - cp)] = w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+                const int t = lane + 32 * brev5(q);
+                const float2 w = finish(v[q]);
+                dst[cp + t] = w;
+                if (t >= NFFT - cp) {
+                    const int m = t - (NFFT - cp);
+                    if (m < nfl) {        // up flank + the delay line of the previous symbol
+                        const float up = flank[m];
+                        const float2 tl = tail[m];
+                        dst[m] = finish(make_float2(__fadd_rn(__fmul_rn(v[q].x, up), tl.x), __fadd_rn(__fmul_rn(v[q].y, up), tl.y)));
+                    } else dst[m] = w;
+                }
+            }
+            __syncwarp();             // every old tail value has been consumed
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+                const int t = lane + 32 * brev5(q);
+                if (t < nfl) { const float dn = flank[nfl + t]; tail[t] = make_float2(__fmul_rn(v[q].x, dn), __fmul_rn(v[q].y, dn)); }
+            }
+            __syncwarp();
         }
     } else {
         // inverse transform = conj(forward(conj X)): fft_len/32-point FFT in registers, twiddles, 32-point FFT across
@@ -78,11 +108,24 @@ __device__ __forceinline__ void tx_ifft_store(float2 (&v)[NFFT / 32], float2 *__
             Tw[k1 + R * k2] = make_float2(x.x, -x.y);
         }
         __syncwarp();
-        for (int m = lane; m < NFFT + cp; m += 32) dst[m] = finish(Tw[(m - cp + NFFT) & (NFFT - 1)]);
+        for (int m = lane; m < NFFT + cp; m += 32) {
+            float2 x = Tw[(m - cp + NFFT) & (NFFT - 1)];
+            if (m < nfl) {
+                const float up = flank[m];
+                const float2 tl = tail[m];
+                x = make_float2(__fadd_rn(__fmul_rn(x.x, up), tl.x), __fadd_rn(__fmul_rn(x.y, up), tl.y));
+            }
+            dst[m] = finish(x);
+        }
+        if (nfl > 0) {
+            __syncwarp();
+            for (int m = lane; m < nfl; m += 32) { const float dn = flank[nfl + m]; const float2 h = Tw[m]; tail[m] = make_float2(__fmul_rn(h.x, dn), __fmul_rn(h.y, dn)); }
+            __syncwarp();
+        }
     }
 }
 
-template <int NFFT, int BPS_P>
+template <int NFFT, int BPS_P, bool ROLL>
 __global__ void __launch_bounds__(TXW_WARPS * 32, 1)
 tx_framew_kernel(const KP p, const uint8_t *__restrict__ payload, const long long *__restrict__ pkt_off,
                      long long n_pkts, int first_num, float2 *__restrict__ out, long long cap,
@@ -100,9 +143,12 @@ tx_framew_kernel(const KP p, const uint8_t *__restrict__ payload, const long lon
     uint8_t *hmask = reinterpret_cast<uint8_t *>(map + NFFT);     // [NFFT] header scrambling mask (zero padded)
     constexpr int TSLOT = (NFFT == 1024) ? F1K_SLOT : NFFT;       // float2 per warp buffer
     const size_t shared_bytes = NFFT * 8 + 64 * 8 + 256 * 4 + 32 * 4 + NFFT * 2 + NFFT;
-    unsigned char *wbase = smem_raw + shared_bytes + (size_t)wid * ((size_t)TSLOT * 8 + pb_bytes);
+    const int nfl = (ROLL && p.roll) ? p.roll - 1 : 0;            // flank samples of the cyclic prefixer (0: rectangular)
+    const size_t tail_bytes = ((size_t)nfl * 8 + 15) & ~(size_t)15;
+    unsigned char *wbase = smem_raw + shared_bytes + (size_t)wid * ((size_t)TSLOT * 8 + pb_bytes + tail_bytes);
     float2 *Tw = reinterpret_cast<float2 *>(wbase);               // TSLOT
     uint8_t *pb = reinterpret_cast<uint8_t *>(Tw + TSLOT);        // packet bytes (+ CRC), 16-byte aligned
+    float2 *tail = reinterpret_cast<float2 *>(pb + pb_bytes);     // [nfl] delay line of the prefixer
 
     for (int i = tid; i < NFFT; i += NTH) {
         const int k1 = i >> 5, b = i & 31;
@@ -156,9 +202,11 @@ tx_framew_kernel(const KP p, const uint8_t *__restrict__ payload, const long lon
         const int ns = (lp * 8 + BPS_P - 1) / BPS_P;                   // repack_bits_bb(8, bps, key, False)
         const int n_ofdm = 3 + (ns + size0 - 1) / size0;
         const long long base = sample_off[pk];
-        if (base + (long long)n_ofdm * D > cap) continue;
-        // ---- sync symbols: constants of the configuration
+        if (base + (long long)n_ofdm * D + nfl > cap) continue;
+        // ---- sync symbols: constants of the configuration (flanks applied; the delay line they leave follows them)
         for (int m = lane; m < 2 * D; m += 32) out[base + m] = __ldg(&sync_td[m]);
+        for (int m = lane; m < nfl; m += 32) tail[m] = __ldg(&sync_td[2 * D + m]);
+        __syncwarp();
         // ---- header and payload symbols
         for (int o = 2; o < n_ofdm; o++) {
             constexpr int R = NFFT / 32;                       // IFFT inputs per lane: bins 32 a + lane
@@ -192,14 +240,26 @@ tx_framew_kernel(const KP p, const uint8_t *__restrict__ payload, const long lon
                 v[a] = val;
             }
             float2 *dst = out + base + (long long)o * D;
-            tx_ifft_store<NFFT>(v, Tw, tws, ltw, dst, cp, sc, clip, lane);
+            tx_ifft_store<NFFT, ROLL>(v, Tw, tws, ltw, dst, cp, sc, clip, lane, nfl, p.roll_flank, tail);
         }
+        // packet mode: the delay line is flushed behind the last symbol
+        for (int m = lane; m < nfl; m += 32) {
+            const float2 tl = tail[m];
+            float2 w = make_float2(tl.x * sc, tl.y * sc);
+            if (clip > 0.f) {
+                w.x = w.x < -clip ? -clip : (w.x > clip ? clip : w.x);
+                w.y = w.y < -clip ? -clip : (w.y > clip ? clip : w.y);
+            }
+            out[base + (long long)n_ofdm * D + m] = w;
+        }
+        __syncwarp();
     }
 }
 
 static inline size_t tx1024w_pb_bytes(int max_pkt_bytes) { return ((size_t)max_pkt_bytes + 8 + 15) & ~(size_t)15; }
-static inline size_t txw_smem_bytes(int nfft, int max_pkt_bytes, int warps)
+static inline size_t txw_smem_bytes(int nfft, int max_pkt_bytes, int warps, int roll)
 {
     const size_t tslot = (nfft == 1024) ? (size_t)F1K_SLOT : (size_t)nfft;
-    return (size_t)(nfft * 8 + 64 * 8 + 256 * 4 + 32 * 4 + nfft * 2 + nfft) + (size_t)warps * (tslot * 8 + tx1024w_pb_bytes(max_pkt_bytes));
+    const size_t tail = roll ? (((size_t)(roll - 1) * 8 + 15) & ~(size_t)15) : 0;
+    return (size_t)(nfft * 8 + 64 * 8 + 256 * 4 + 32 * 4 + nfft * 2 + nfft) + (size_t)warps * (tslot * 8 + tx1024w_pb_bytes(max_pkt_bytes) + tail);
 }

@@ -474,3 +474,32 @@ def test_channel_estimate_debug_tap(which):
             if force == "1":
                 assert cm.rel_evm(got, want) < 1e-4          # pilots and every other bin of the tag as well
         assert np.abs(ref["taps"][0][occ_sh]).min() > 0
+
+
+@pytest.mark.parametrize("which,roll", [("c3", 18), ("c3", 72), ("c1", 4), ("radio", 8), ("c3", 2)])
+def test_rolloff_on_the_warp_tx_kernel(monkeypatch, which, roll):
+    """ofdm_cyclic_prefixer with rolloff_len > 0 on the warp-per-packet TX kernel (sync_transmit_path uses cp_len/4,
+    python/ofdm_cr_tools.py:1093): offsets exact and samples within 1e-5 of the peak against the oracle and against the
+    CTA-per-packet kernel, with scaling and clipper behind it, ragged packet lengths; the bursts decode."""
+    rng = np.random.default_rng(roll)
+    cfg, plen = {"c3": (cm.cfg_c3(), 1500), "c1": (cm.cfg_c1(2, True, 1), 96), "radio": (cm.cfg_radio128(4), 200)}[which]
+    kw = dict(cfg, rolloff=roll, tx_scale=0.01, tx_clip=0.6 if which == "c3" else 0.25)   # (clips the 16-QAM peaks mildly)
+    orc = cm.make_oracle(kw)
+    pk = cm.rand_packets(rng, 6, plen) + [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (1, plen // 3, plen - 1)]
+    so, oo = orc.tx(pk)
+    outs = {}
+    for name, env in (("warp", "0"), ("cta", "1")):
+        monkeypatch.setenv("OFDMX_NO_WARP_TX", env)
+        phy = cm.make_phy(kw)
+        phy.profile(True)
+        s, off = phy.tx(pk)
+        used = set(phy.profile_read())
+        assert ("tx_framew_kernel" in used) == (name == "warp"), used
+        assert np.array_equal(off.cpu().numpy(), oo)
+        outs[name] = s.cpu().numpy()
+        assert outs[name].shape == so.shape and np.abs(outs[name] - so).max() <= 1e-5 * np.abs(so).max(), name
+    assert np.abs(outs["warp"] - outs["cta"]).max() <= 2e-6 * np.abs(so).max()
+    monkeypatch.setenv("OFDMX_NO_WARP_TX", "0")
+    x = cm.channel(cm.split_frames(outs["warp"], oo), rng, gaps=(300, 700), tail=4000, snr_db=40.0, fft_len=cfg["fft_len"], scale=100.0)
+    got = cm.make_phy(kw).rx(_to_dev(x)).payloads()
+    assert got == pk

@@ -40,6 +40,8 @@ def stage_tx(args, torch, cm, dev, peak):
     plen = {"c3": 1500, "c1": 96, "radio128": 350}[args.plan]
     cfg = {"c3": cm.cfg_c3, "c1": lambda: cm.cfg_c1(2, False, 0), "radio128": lambda: cm.cfg_radio128(4, 1, 1)}[args.plan]()
     cfg["tx_scale"] = 0.01
+    if args.rolloff:
+        cfg["rolloff"] = args.rolloff
     phy = cm.make_phy(cfg, max_pkt_bytes=plen + 4)
     rng = np.random.default_rng(3)
     nf = args.frames
@@ -155,6 +157,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", default="agc2", choices=["agc2", "tx", "rx_small"])
     ap.add_argument("--frames", type=int, default=65536)
+    ap.add_argument("--rolloff", type=int, default=0, help="tx stage: ofdm_cyclic_prefixer rolloff_len")
     ap.add_argument("--plan", default="c3", choices=["c3", "c1", "radio128"], help="tx stage: carrier plan (c3 = BASELINE config[2])")
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--samples", type=int, default=64 * 880)

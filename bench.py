@@ -312,7 +312,7 @@ def run_rx_config(cid, C, args, dev, world, rank, dist, clock_sampler=None, with
     from ofdm_tools import OfdmPhy
     from ofdm_tools import dist as odist
     local = dev.index
-    n_streams_all = C["streams"]
+    n_streams_all = args.streams if (args.streams and C["streams"] > 1) else C["streams"]
     if C["scaling"] == "strong":
         mine = odist.shard_streams(n_streams_all, rank, world)
         n_streams = len(mine)
@@ -752,6 +752,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[0, 1, 2, 3, 4], help="BASELINE.json configs[i]; 2 = the headline")
     ap.add_argument("--frames", type=int, default=0, help="config 2 only: frames per GPU (default 65536 = 646 M samples = 5.2 GB)")
+    ap.add_argument("--streams", type=int, default=0, help="configs 1 and 3 only: number of streams (default: as stated)")
     ap.add_argument("--search-samples", type=int, default=0, help="config 4 only: samples per GPU (default 1e9)")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames in the CPU sample (default: per configuration)")
     ap.add_argument("--ref-samples", type=int, default=1 << 23, help="--impl reference --config 4: samples per step")

@@ -6,6 +6,7 @@
 #include "ofdmx_sync_tma.cuh"
 #include "ofdmx_frame1024.cuh"
 #include "ofdmx_frame1024w.cuh"
+#include "ofdmx_frame2048p.cuh"
 #include "ofdmx_cond.cuh"
 #include "ofdmx_sync_warp.cuh"
 #include "ofdmx_tx1024w.cuh"
@@ -35,12 +36,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_FRAMEP, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "(unused)", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel", "rx_framep_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -69,6 +70,10 @@ struct PlanFields {
     int frame1kw_dec_off = -1;      // float2 index inside the symbol buffer where the decisions live (-1: own array)
     uint32_t x_2048 = 0;            // x^(8*2048) mod P
     int frame1k_warps = 0;          // > 0: fft_len 1024 fast path with this many warps per CTA
+    bool framep = false;            // fft_len 2048: pair-of-warps-per-frame kernel eligible
+    size_t framep_smem = 0;
+    int framep_hsz = 0;
+    const uint16_t *pair_tab = nullptr;
 };
 
 struct ofdmx_ctx : PlanFields {
@@ -103,6 +108,7 @@ struct ofdmx_ctx : PlanFields {
     DevBuf ws_papr;                 // partial sums of ofdmx_papr (may run on another stream than an RX call in flight)
     DevBuf ws_agc;                  // span bookkeeping of ofdmx_agc2 (entry / exit gains, re-run flags)
     bool no_agc_spans = false;      // OFDMX_NO_AGC_SPANS=1: always one lane per stream
+    bool no_pair_frame = false;     // OFDMX_NO_PAIR_FRAME=1: fft_len 2048 on the one-warp-per-frame kernel
     float2 *h_taps = nullptr;       // ofdmx_set_debug_taps
     long long h_stride = 0;
     int64_t launches = 0;
@@ -899,6 +905,29 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             c->frame1kw = ((N == 1024 && ngc <= 4 && c->frame1kw_dec_all == 0) || N == 64 || N == 128 || N == 256 || N == 512 || N == 2048) && simple && kp.bps_h == 1
                           && c->hl >= 32 && c->hl <= 2048 && kp.n_occ_u == occ_size[0] && nsw == 2
                           && c->frame1kw_smem <= 227 * 1024;
+            // fft_len 2048: the same plans on the pair-of-warps kernel (bits per OFDM symbol a byte multiple)
+            if (N == 2048 && nsw == 2 && simple && kp.bps_h == 1 && c->hl >= 32 && kp.n_occ_u == occ_size[0] && ngc <= 4
+                && c->frame1kw_dec_all == 0) {
+                std::vector<uint16_t> lists[2][3];
+                for (int q = 0; q < occ_size[0]; q++) {
+                    const int ks = occ_bins[occ_base[0] + q], kn = ks ^ (N / 2), h = kn & 1;
+                    lists[h][0].push_back((uint16_t)(kn >> 1));
+                    lists[h][1].push_back((uint16_t)q);
+                    lists[h][2].push_back((uint16_t)ks);
+                }
+                const int nh = (int)std::max(lists[0][0].size(), lists[1][0].size());
+                std::vector<uint16_t> tab((size_t)4 + 6 * (size_t)nh, 0);
+                tab[0] = (uint16_t)lists[0][0].size(); tab[1] = (uint16_t)lists[1][0].size(); tab[2] = (uint16_t)nh;
+                for (int h = 0; h < 2; h++)
+                    for (int a = 0; a < 3; a++)
+                        std::copy(lists[h][a].begin(), lists[h][a].end(), tab.begin() + 4 + (size_t)(3 * h + a) * nh);
+                c->framep_hsz = (std::max(nh, kp.y1_span / 2 + 2) + 1) & ~1;
+                c->framep_smem = framep_smem_bytes(kp.n_occ_u, nh, c->framep_hsz);
+                if (c->framep_smem <= 227 * 1024 && nh > 0 && ofdmx_fp_configure(kp.bps_p, c->framep_smem) == cudaSuccess) {
+                    if ((rc = upload(stg, tab, &c->pair_tab)) != 0) return bail(rc);
+                    c->framep = true;
+                }
+            }
             if (c->frame1kw) {
                 int occ = 1;
                 const cudaError_t e1 = ofdmx_fw_configure(N, kp.bps_p, c->frame1kw_smem, c->frame1kw_warps * 32, &occ);
@@ -1049,6 +1078,7 @@ int ofdmx_create(const ofdmx_params *prm, int device, ofdmx_ctx **out)
     if (const char *ns = getenv("OFDMX_NO_WARP_SYNC")) c->no_warp_sync = (ns[0] == '1');
     if (const char *nx = getenv("OFDMX_NO_WARP_TX")) c->no_warp_tx = (nx[0] == '1');
     if (const char *na = getenv("OFDMX_NO_AGC_SPANS")) c->no_agc_spans = (na[0] == '1');
+    if (const char *np2 = getenv("OFDMX_NO_PAIR_FRAME")) c->no_pair_frame = (np2[0] == '1');
     *out = c;
     return OFDMX_OK;
 }
@@ -1196,7 +1226,13 @@ static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_
     if (c->h_taps && c->h_stride < c->kp.N) return fail(c, OFDMX_ERR_CAPACITY, "debug taps: stride < fft_len");
     // (the channel-tap debug output exists in the warp-per-frame kernel's tapped variant and in the any-fft_len kernel)
     const bool taps_generic = c->h_taps && !(c->frame1kw && z_out);
-    if (c->frame1kw && !c->force_generic && !c->no_warp_frame && !taps_generic) {
+    if (c->framep && !c->force_generic && !c->no_warp_frame && !c->no_pair_frame && !(c->h_taps && !z_out)) {
+        KT(K_FRAMEP);
+        FwArgs fa{ kp_call, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out, byte_stride,
+                   (float2 *)z_out, z_stride, c->x_2048, -1, 0 };
+        if (!ofdmx_fp_launch(c->kp.bps_p, (unsigned)c->sm_count, c->framep_smem, st, fa, c->pair_tab, c->framep_hsz))
+            return fail(c, OFDMX_ERR_PARAM, "no pair-of-warps frame kernel for this configuration");
+    } else if (c->frame1kw && !c->force_generic && !c->no_warp_frame && !taps_generic) {
         KT(K_FRAME1KW);
         FwArgs fa{ kp_call, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out, byte_stride,
                    (float2 *)z_out, z_stride, c->x_2048, c->frame1kw_dec_off, c->frame1kw_dec_all };

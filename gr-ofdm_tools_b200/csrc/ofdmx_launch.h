@@ -54,6 +54,10 @@ bool ofdmx_fw_launch(int nfft, int bps, unsigned grid, unsigned threads, size_t 
 OFDMX_FW_DECL(64) OFDMX_FW_DECL(128) OFDMX_FW_DECL(256) OFDMX_FW_DECL(512) OFDMX_FW_DECL(1024) OFDMX_FW_DECL(2048)
 #undef OFDMX_FW_DECL
 
+// ---- rx_framep_kernel<BPS, WANT_Z> (ofdmx_frame2048p.cuh): fft_len 2048, a pair of warps per frame
+cudaError_t ofdmx_fp_configure(int bps, size_t smem);
+bool ofdmx_fp_launch(int bps, unsigned grid, size_t smem, cudaStream_t st, const FwArgs &a, const uint16_t *pair_tab, int hsz);
+
 // ---- rx_frame1024_kernel<BPS, SIMPLE, WANT_Z> (ofdmx_frame1024.cuh): one CTA per frame, fft_len 1024
 struct F1kArgs {
     KP kp;

@@ -14,7 +14,7 @@ CSRC = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
 LIBDIR = os.path.normpath(os.path.join(_HERE, "..", "lib"))
 OBJDIR = os.path.join(LIBDIR, "obj")
 # (object name, source, extra defines)
-UNITS = [("api", "ofdmx_api.cu", []), ("frame1k", "ofdmx_k_frame1k.cu", [])] + \
+UNITS = [("api", "ofdmx_api.cu", []), ("frame1k", "ofdmx_k_frame1k.cu", []), ("framep", "ofdmx_k_framep.cu", [])] + \
         [("framew_%d" % n, "ofdmx_k_framew.cu", ["-DOFDMX_FW_N=%d" % n]) for n in (1024, 2048, 64, 128, 256, 512)] + \
         [("txw_%d" % n, "ofdmx_k_txw.cu", ["-DOFDMX_TXW_N=%d" % n]) for n in (1024, 64, 128, 256, 512)]
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

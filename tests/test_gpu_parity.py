@@ -535,7 +535,7 @@ def test_tx_warp_kernel_small_fft(monkeypatch, which, bps):
 
 
 @pytest.mark.parametrize("bps,int_off", [(2, 0), (4, 2), (6, -2)])
-def test_warp_frame_kernel_fft2048(bps, int_off):
+def test_warp_frame_kernel_fft2048(monkeypatch, bps, int_off):
     """Warp-per-frame receiver at fft_len 2048 (two interleaved 1024-point register transforms recombined in the bin
     accessor): ragged lengths, integer carrier offsets, multipath; records, bytes and equalised symbols against the
     oracle."""
@@ -548,9 +548,17 @@ def test_warp_frame_kernel_fft2048(bps, int_off):
                         fft_len=2048, taps=cm.MULTIPATH)
     res, ref = _compare_rx(cfg, stream)
     phy = cm.make_phy(cfg)
-    assert "rx_framew_kernel" in _kernels_used(phy, lambda: phy.rx(_to_dev(stream)))
+    # default at fft_len 2048: the pair-of-warps-per-frame kernel (byte-multiple symbols), else one warp per frame
+    used = _kernels_used(phy, lambda: phy.rx(_to_dev(stream)))
+    assert ("rx_framep_kernel" in used) if (1200 * bps) % 8 == 0 else ("rx_framew_kernel" in used), used
     assert res.payloads() == pk
     assert np.all(res.frames["carr_offset"] == int_off)
+    # and the one-warp-per-frame kernel on the same input
+    monkeypatch.setenv("OFDMX_NO_PAIR_FRAME", "1")
+    res1, _ = _compare_rx(cfg, stream)
+    phy1 = cm.make_phy(cfg)
+    assert "rx_framew_kernel" in _kernels_used(phy1, lambda: phy1.rx(_to_dev(stream)))
+    assert res1.payloads() == pk
 
 
 @pytest.mark.parametrize("which,n_streams,n", [("c1", 1, 50000), ("c1", 4, 3000), ("c1", 1, 33333), ("radio128", 1, 60000),

@@ -9,6 +9,7 @@
 #include "ofdmx_frame2048p.cuh"
 #include "ofdmx_cond.cuh"
 #include "ofdmx_sync_warp.cuh"
+#include "ofdmx_sync_warpn.cuh"
 #include "ofdmx_tx1024w.cuh"
 #include "ofdmx_chain.cuh"
 #include "ofdmx_launch.h"
@@ -36,12 +37,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_FRAMEP, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_FRAMEP, K_SYNC_WARPN, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "(unused)", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel", "rx_framep_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel", "rx_framep_kernel", "sync_metric_warpn_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -455,6 +456,27 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         KT(K_SYNC_WARP);
         sync_metric_warp_kernel<<<grid, SW_WARPS * 32, SW_WARPS * SW_RING_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr,
                                                                                       w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total);
+    } else if (kp.N <= 512 && ctx->sync_warp_ok && !ctx->no_warp_sync && !ctx->no_tma && (reinterpret_cast<uintptr_t>(samples) & 15) == 0
+               && (n_streams == 1 || (stride & 1) == 0) && (n_samples / SW_TILE + 2) * n_streams < 0x7fffffffLL) {
+        // fft_len 32 .. 512: the short-window warp-autonomous kernel (one warm-up tile per span)
+        const long long tiles = (n_samples + SW_TILE - 1) / SW_TILE;
+        const long long warps = (long long)ctx->sm_count * SW_WARPS;
+        long long span = (tiles * n_streams + 4 * warps - 1) / (4 * warps);
+        span = std::max<long long>(8, std::min<long long>(span, 1024));
+        const long long spans = (tiles + span - 1) / span;
+        const long long total = spans * n_streams;
+        const unsigned grid = (unsigned)std::min<long long>((total + SW_WARPS - 1) / SW_WARPS, (long long)ctx->sm_count);
+        KT(K_SYNC_WARPN);
+#define SWN(NN) sync_metric_warpn_kernel<NN><<<grid, SW_WARPS * 32, SW_WARPS * SW_RING_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr, \
+                                                                                              w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total)
+        switch (kp.N) {
+        case 32: SWN(32); break;
+        case 64: SWN(64); break;
+        case 128: SWN(128); break;
+        case 256: SWN(256); break;
+        default: SWN(512); break;
+        }
+#undef SWN
     } else if (!ctx->no_tma && make_sample_map(&tmap, samples, n_streams, n_samples, stride)) {
         // TMA path: 3-D map {32 floats, rows of 16 samples, streams}; whole rows only (the kernel patches the tail)
         const long long tiles = (n_samples + SV_T - 1) / SV_T;
@@ -948,7 +970,19 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sync_metric_tma_kernel, SV_THREADS, c->sync_tma_smem) == cudaSuccess && occ > 0)
                 c->sync_tma_occ = occ;
         }
-        c->sync_warp_ok = (N == 1024) && ofdmx_raise_smem_limit(sync_metric_warp_kernel, SW_WARPS * SW_RING_BYTES) == cudaSuccess;
+        c->sync_warp_ok = false;
+        {
+            const size_t wb = SW_WARPS * SW_RING_BYTES;
+            switch (N) {
+            case 32: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<32>, wb) == cudaSuccess; break;
+            case 64: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<64>, wb) == cudaSuccess; break;
+            case 128: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<128>, wb) == cudaSuccess; break;
+            case 256: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<256>, wb) == cudaSuccess; break;
+            case 512: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<512>, wb) == cudaSuccess; break;
+            case 1024: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warp_kernel, wb) == cudaSuccess; break;
+            default: break;
+            }
+        }
         c->sync_fast_smem = sync_fast_smem_bytes(N);
         if (ofdmx_raise_smem_limit(sync_metric_fast_kernel<0>, c->sync_fast_smem) != cudaSuccess
             || ofdmx_raise_smem_limit(sync_metric_fast_kernel<64>, c->sync_fast_smem) != cudaSuccess

@@ -564,10 +564,9 @@ def test_warp_frame_kernel_fft2048(monkeypatch, bps, int_off):
 @pytest.mark.parametrize("which,n_streams,n", [("c1", 1, 50000), ("c1", 4, 3000), ("c1", 1, 33333), ("radio128", 1, 60000),
                                                ("radio128", 3, 5000), ("c1", 2, 40)])
 def test_sync_kernel_variants_small_fft(monkeypatch, which, n_streams, n):
-    """fft_len 64 / 128: TMA ring sync kernel (default there) vs plain-load kernel vs oracle, frames at the very start, in
-    the middle and cut off at the end, several streams: identical triggers and CFO.  (A warp-autonomous variant for
-    these sizes was built and verified with this test, but measured no faster than the TMA ring kernel on the dense
-    short frames of these configurations -- the sliding pass is rarely skipped -- and was not kept.)"""
+    """fft_len 64 / 128: short-window warp-autonomous sync kernel (default) vs TMA ring kernel vs plain-load kernel vs
+    oracle, frames at the very start, in the middle and cut off at the end, several streams: identical triggers and
+    CFO."""
     cfg = cm.cfg_c1(2, False, 0) if which == "c1" else cm.cfg_radio128(2, 1, 1)
     rng = np.random.default_rng(n + n_streams)
     orc = cm.make_oracle(cfg)

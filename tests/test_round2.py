@@ -503,3 +503,53 @@ def test_rolloff_on_the_warp_tx_kernel(monkeypatch, which, roll):
     x = cm.channel(cm.split_frames(outs["warp"], oo), rng, gaps=(300, 700), tail=4000, snr_db=40.0, fft_len=cfg["fft_len"], scale=100.0)
     got = cm.make_phy(kw).rx(_to_dev(x)).payloads()
     assert got == pk
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fft_len,n_streams,n", [(32, 1, 70001), (64, 2, 90000), (128, 1, 50000), (256, 3, 60002), (512, 1, 150000),
+                                                 (512, 2, 700), (64, 1, 511), (256, 1, 16 * 8 * 512 + 5)])
+def test_short_window_warp_sync_kernel(monkeypatch, fft_len, n_streams, n):
+    """fft_len 32 .. 512: the short-window warp-autonomous Schmidl & Cox kernel (default) vs the TMA ring kernel vs the
+    oracle: identical triggers and CFO.  Streams with frames at both ends, a 40 dB louder burst directly in front of a
+    quiet frame (every partial window sum must stay local), stretches of exact zeros, odd lengths, spans that end
+    inside the last tile."""
+    rng = np.random.default_rng(fft_len + n)
+    cfg = _plan(fft_len, {32: 20, 64: 48, 128: 96, 256: 200, 512: 400}[fft_len], 1)
+    orc = cm.make_oracle(cfg)
+    pk = cm.rand_packets(rng, 2, 24)
+    s_ref, off_ref = orc.tx(pk)
+    fr = cm.split_frames(s_ref, off_ref)
+    xs = []
+    for s in range(n_streams):
+        x = 0.02 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        L = len(fr[0])
+        for o in (0, n // 3 + 7 * s, 2 * n // 3 + 1, n - L // 2):
+            if 0 <= o < n:
+                m = min(L, n - o)
+                x[o:o + m] += fr[s % 2][:m]
+        o = n // 2
+        if o + 3 * L < 2 * n // 3:
+            x[o:o + L] += 100.0 * fr[0][:L]                  # loud burst ...
+            x[o + L:o + 2 * L] += fr[1][:L]                  # ... a normal frame right behind it
+            x[o + 2 * L + 40:o + 2 * L + 40 + 3 * fft_len] = 0.0   # exact zeros: R == 0 must not detect
+        xs.append(x.astype(np.complex64))
+    x = np.stack(xs)
+    res = {}
+    for name, env in (("warp", {}), ("ring", {"OFDMX_NO_WARP_SYNC": "1"})):
+        monkeypatch.setenv("OFDMX_NO_WARP_SYNC", env.get("OFDMX_NO_WARP_SYNC", "0"))
+        phy = cm.make_phy(cfg)
+        res[name] = phy.sync(_to_dev(x if n_streams > 1 else x[0]))
+        if n >= 512:
+            from test_gpu_parity import _kernels_used
+            used = _kernels_used(phy, lambda: phy.sync(_to_dev(x if n_streams > 1 else x[0])))
+            assert ("sync_metric_warpn_kernel" in used) == (name == "warp"), used
+    ref_t, ref_s, ref_c = [], [], []
+    for s in range(n_streams):
+        t, c = orc.sync(x[s])
+        ref_t += list(t); ref_c += list(c); ref_s += [s] * len(t)
+    assert len(ref_t) >= (2 if n > 20 * fft_len else 0)
+    for name in ("warp", "ring"):
+        trig, cfo, st = res[name]
+        assert np.array_equal(trig, np.array(ref_t, np.int64)), name
+        assert np.array_equal(st, np.array(ref_s)), name
+        np.testing.assert_allclose(cfo, np.array(ref_c, np.float32), atol=2e-6, rtol=0)

@@ -120,7 +120,7 @@ struct ofdmx_ctx : PlanFields {
     DevBuf h_samples, h_frames, h_bytes, h_counts;
     cudaStream_t own_stream = nullptr;
     bool no_tma = false;            // OFDMX_NO_TMA=1: use the plain-load sync kernel
-    bool no_warp_sync = false;      // OFDMX_NO_WARP_SYNC=1: fft_len 1024 uses the TMA ring kernel instead of the warp-autonomous one
+    bool no_warp_sync = false;      // OFDMX_NO_WARP_SYNC=1: the TMA ring kernel instead of the warp-autonomous ones
     bool emit_all = false;          // ofdmx_set_emit_all: frames_out receives every trigger's record
     bool no_warp_frame = false;     // OFDMX_NO_WARP_FRAME=1: use the CTA-per-frame fft_len-1024 kernel
     bool force_generic = false;     // OFDMX_FORCE_GENERIC=1: always use the any-fft_len frame kernel
@@ -443,19 +443,25 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
     ofdmx_ctx *ctx_ = ctx;
     CUDA_TRY(ctx, cudaMemsetAsync(w.blocksum, 0, sizeof(int) * (size_t)(w.nb + 1), st));   // per-block trigger counts (plateau_kernel)
     CUtensorMap tmap;
-    if (kp.N == 1024 && ctx->sync_warp_ok && !ctx->no_warp_sync && !ctx->no_tma && (reinterpret_cast<uintptr_t>(samples) & 15) == 0
+    if ((kp.N == 1024 || kp.N == 2048) && ctx->sync_warp_ok && !ctx->no_warp_sync && !ctx->no_tma && (reinterpret_cast<uintptr_t>(samples) & 15) == 0
         && (n_streams == 1 || (stride & 1) == 0) && (n_samples / SW_TILE + 2) * n_streams < 0x7fffffffLL) {
-        // fft_len 1024: warp-autonomous streaming (no block barriers), spans of tiles of 512 samples per warp
-        const long long tiles = (n_samples + SW_TILE - 1) / SW_TILE;
-        const long long warps = (long long)ctx->sm_count * SW_WARPS;
+        // fft_len 1024 / 2048: warp-autonomous streaming (no block barriers), spans of tiles of fft_len/2 samples per warp
+        const int C = kp.N / 64, wpc = SW_WARPS * 16 / C;                  // chunk size, warps per CTA
+        const long long tile = 32LL * C;
+        const long long tiles = (n_samples + tile - 1) / tile;
+        const long long warps = (long long)ctx->sm_count * wpc;
         long long span = (tiles * n_streams + 4 * warps - 1) / (4 * warps);
         span = std::max<long long>(16, std::min<long long>(span, 1024));
         const long long spans = (tiles + span - 1) / span;
         const long long total = spans * n_streams;
-        const unsigned grid = (unsigned)std::min<long long>((total + SW_WARPS - 1) / SW_WARPS, (long long)ctx->sm_count);
+        const unsigned grid = (unsigned)std::min<long long>((total + wpc - 1) / wpc, (long long)ctx->sm_count);
         KT(K_SYNC_WARP);
-        sync_metric_warp_kernel<<<grid, SW_WARPS * 32, SW_WARPS * SW_RING_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr,
-                                                                                      w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total);
+        if (C == 16)
+            sync_metric_warp_kernel<16><<<grid, wpc * 32, SW_SMEM_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr,
+                                                                              w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total);
+        else
+            sync_metric_warp_kernel<32><<<grid, wpc * 32, SW_SMEM_BYTES, st>>>(samples, n_samples, stride, (float)kp.thr, kp.thr,
+                                                                              w.detmask, w.trigmask, w.wps, (int)tiles, (int)span, (int)spans, (int)total);
     } else if (kp.N <= 512 && ctx->sync_warp_ok && !ctx->no_warp_sync && !ctx->no_tma && (reinterpret_cast<uintptr_t>(samples) & 15) == 0
                && (n_streams == 1 || (stride & 1) == 0) && (n_samples / SW_TILE + 2) * n_streams < 0x7fffffffLL) {
         // fft_len 32 .. 512: the short-window warp-autonomous kernel (one warm-up tile per span)
@@ -979,7 +985,8 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
             case 128: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<128>, wb) == cudaSuccess; break;
             case 256: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<256>, wb) == cudaSuccess; break;
             case 512: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warpn_kernel<512>, wb) == cudaSuccess; break;
-            case 1024: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warp_kernel, wb) == cudaSuccess; break;
+            case 1024: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warp_kernel<16>, wb) == cudaSuccess; break;
+            case 2048: c->sync_warp_ok = ofdmx_raise_smem_limit(sync_metric_warp_kernel<32>, wb) == cudaSuccess; break;
             default: break;
             }
         }

@@ -1,4 +1,4 @@
-// ofdmx_sync_warp.cuh -- K2, fft_len 1024: Schmidl & Cox metric with WARP-AUTONOMOUS streaming.
+// ofdmx_sync_warp.cuh -- K2, fft_len 1024 and 2048: Schmidl & Cox metric with WARP-AUTONOMOUS streaming.
 //
 // The TMA ring kernel (ofdmx_sync_tma.cuh) spends a fifth of its warp time at block barriers: eight warps
 // share a 4096-sample tile, exchange chunk totals through shared memory and scan them as a block.  For
@@ -14,14 +14,19 @@
 // error bound, chunk-level rejection, exact float64 re-evaluation of the samples inside the uncertainty band --
 // the detect bits are exact whatever the summation order.
 //
-// Preconditions (host): fft_len == 1024, sample pointer 16-byte aligned, even stream stride.
+// The kernel is a template of the chunk size C (samples per lane and tile): C = 16 is fft_len 1024 (tiles of 512
+// samples, 4 KB slots, 14 warps per SM), C = 32 is fft_len 2048 (tiles of 1024 samples, 8 KB slots, 7 warps per SM --
+// the same 56 KB of samples in flight per SM); fft_len is always 64 C, so the tile is half a window in both.
+//
+// Preconditions (host): fft_len == 64 C, sample pointer 16-byte aligned, even stream stride.
 #pragma once
 #include "ofdmx_sync.cuh"
 
 #define SW_WARPS 14
-#define SW_TILE 512                    // samples per warp tile
+#define SW_TILE 512                    // samples per warp tile (C = 16)
 #define SW_SLOT_BYTES 4096
 #define SW_RING_BYTES (4 * SW_SLOT_BYTES)
+#define SW_SMEM_BYTES (SW_WARPS * SW_RING_BYTES)   // per CTA, whatever C: warps per CTA = SW_WARPS * 16 / C
 
 // byte offset, inside a warp's ring, of 16-byte unit q of row `row` of slot `slot` (rows are 128 bytes = 16
 // samples; units XOR-swizzled by the row so that 16-byte reads of one row per lane are conflict free)
@@ -57,20 +62,68 @@ __device__ __forceinline__ void sw_fill(unsigned char *ring, int slot, const flo
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(SW_WARPS * 32, 1)
+// ---- chunk size C: rows of 8 C bytes, slots of 256 C bytes, tiles of 32 C samples
+template <int C>
+__device__ __forceinline__ int swc_unit(int slot, int row, int q) { return slot * (256 * C) + row * (8 * C) + ((q ^ (row & 7)) << 4); }
+
+// fill slot `slot` with tile k of the stream (samples [32 C k, 32 C (k + 1))); out-of-range samples become zeros.
+// Unit u = 32 i + lane of the tile (i < C/2) lands in row u / (C/2), unit u % (C/2), swizzled by the row.  For
+// C = 16 this is sw_fill; for C = 32 the row is 2 i + lane/16, so the swizzled offset depends on i through i % 4:
+// four per-lane offsets (offs[]) are computed once and an interior tile costs one address add per copy.
+template <int C>
+__device__ __forceinline__ void swc_fill(unsigned char *ring, int slot, const float2 *__restrict__ r, long long n, int k,
+                                         int full_tiles, int lane, const int (&offs)[4])
+{
+    constexpr int TILE = 32 * C, NCP = C / 2;              // copies of 16 bytes per lane
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ring) + slot * (256 * C);
+    // i -> destination: C = 16: offs[i & 1] + (i >> 1) * 1024 (8 rows of 128 bytes per pair of copies);
+    //                   C = 32: offs[i & 3] + (i >> 2) * 2048 (8 rows of 256 bytes per four copies)
+    if (k >= 0 && k < full_tiles) {
+        const float2 *src = r + (long long)k * TILE + 2 * lane;
+#pragma unroll
+        for (int i = 0; i < NCP; i++)
+            sw_cp_async16(d0 + (C == 16 ? (i >> 1) * 1024 + offs[i & 1] : (i >> 2) * 2048 + offs[i & 3]), src + 64 * i, 16);
+    } else {
+        const long long base = (long long)k * TILE;
+#pragma unroll 1
+        for (int i = 0; i < NCP; i++) {
+            const long long idx = base + 64 * i + 2 * lane;
+            int bytes = 0;
+            if (idx >= 0 && idx < n) bytes = (idx + 1 < n) ? 16 : 8;
+            sw_cp_async16(d0 + (C == 16 ? (i >> 1) * 1024 + offs[i & 1] : (i >> 2) * 2048 + offs[i & 3]), r + (bytes ? idx : 0), bytes);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(SW_WARPS * 16 / C * 32, 1)
 sync_metric_warp_kernel(const float2 *__restrict__ samples, long long n, long long stride, float thr_f, double thr_d,
                         uint32_t *__restrict__ detmask, uint32_t *__restrict__ trigmask, long long wps,
                         int tiles_per_stream, int span, int spans_per_stream, int total_spans)
 {
+    static_assert(C == 16 || C == 32, "chunk of 16 (fft_len 1024) or 32 (fft_len 2048) samples");
+    constexpr int TILE = 32 * C, LT = (C == 16) ? 9 : 10, NU = C / 2, ROWB = 8 * C, SLOTB = 256 * C, N = 64 * C;
+    constexpr unsigned FULL = (C == 32) ? 0xffffffffu : 0xffffu;
     extern __shared__ __align__(128) unsigned char sw_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char *ring = sw_smem + (size_t)wid * SW_RING_BYTES;
+    unsigned char *ring = sw_smem + (size_t)wid * (4 * SLOTB);
     const float thr4 = 0.25f * thr_f;
     const int gw = blockIdx.x * (blockDim.x >> 5) + wid, nw = gridDim.x * (blockDim.x >> 5);
-    const int full_tiles = (int)(n / SW_TILE);             // tiles that lie completely inside the stream
+    const int full_tiles = (int)(n / TILE);                // tiles that lie completely inside the stream
     const int sown = (lane & 7) << 4;                      // swizzle of this lane's row
-    const int off_e = ((lane >> 3) << 7) + (((lane & 7) ^ (lane >> 3)) << 4);              // rows 8j + lane/8
-    const int off_o = (((lane >> 3) + 4) << 7) + (((lane & 7) ^ ((lane >> 3) + 4)) << 4);  // rows 8j + 4 + lane/8
+    int offs[4];
+    if (C == 16) {
+        offs[0] = ((lane >> 3) << 7) + (((lane & 7) ^ (lane >> 3)) << 4);              // rows 8j + lane/8
+        offs[1] = (((lane >> 3) + 4) << 7) + (((lane & 7) ^ ((lane >> 3) + 4)) << 4);  // rows 8j + 4 + lane/8
+        offs[2] = offs[0]; offs[3] = offs[1];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int row = 2 * j + (lane >> 4);                                       // rows 8m + 2j + lane/16
+            offs[j] = row * ROWB + (((lane & 15) ^ (row & 7)) << 4);
+        }
+    }
 
     for (int sp = gw; sp < total_spans; sp += nw) {
         const int s = sp / spans_per_stream;
@@ -85,24 +138,24 @@ sync_metric_warp_kernel(const float2 *__restrict__ samples, long long n, long lo
         // slot 3 stands for "the tile before the first one" in the first iteration: its products are never used,
         // but keep the arithmetic on defined data
 #pragma unroll
-        for (int q = 0; q < 8; q++) *reinterpret_cast<float4 *>(ring + (3 << 12) + (lane << 7) + (q << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        sw_fill(ring, 0, r, n, k0 - 2, full_tiles, lane, off_e, off_o);
+        for (int q = 0; q < NU; q++) *reinterpret_cast<float4 *>(ring + 3 * SLOTB + lane * ROWB + (q << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        swc_fill<C>(ring, 0, r, n, k0 - 2, full_tiles, lane, offs);
         int it = 0;
         for (int k = k0 - 2; k < k1; k++, it++) {
             const int sc = it & 3, s1 = (it + 3) & 3, s2 = (it + 2) & 3;     // current, fft_len/2 back, fft_len back
             if (k + 1 < k1) {
-                sw_fill(ring, (it + 1) & 3, r, n, k + 1, full_tiles, lane, off_e, off_o);
+                swc_fill<C>(ring, (it + 1) & 3, r, n, k + 1, full_tiles, lane, offs);
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncwarp();
-            // ---- chunk totals of this lane's 16 samples (the products themselves are not kept: most tiles are
+            // ---- chunk totals of this lane's C samples (the products themselves are not kept: most tiles are
             //      rejected as a whole below, the others recompute them in the sliding pass)
-            const unsigned char *po = ring + (sc << 12) + (lane << 7), *pd = ring + (s1 << 12) + (lane << 7);
+            const unsigned char *po = ring + sc * SLOTB + lane * ROWB, *pd = ring + s1 * SLOTB + lane * ROWB;
             float sxr = 0.f, sxi = 0.f, se = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < NU; q++) {
                 const float4 a = *reinterpret_cast<const float4 *>(po + ((q << 4) ^ sown));
                 const float4 b = *reinterpret_cast<const float4 *>(pd + ((q << 4) ^ sown));
                 // same operations, same order as the sliding pass (x[0], x[1], ... summed left to right)
@@ -138,9 +191,9 @@ sync_metric_warp_kernel(const float2 *__restrict__ samples, long long n, long lo
                     skip = (emin > 0.0f) && (pmax * pmax < 0.999f * thr4 * emin * emin);
                 }
                 if (!__all_sync(0xffffffffu, skip)) {
-                    const unsigned char *pn = ring + (s2 << 12) + (lane << 7);
+                    const unsigned char *pn = ring + s2 * SLOTB + lane * ROWB;
 #pragma unroll 2
-                    for (int q = 0; q < 8; q++) {
+                    for (int q = 0; q < NU; q++) {
                         const float4 a = *reinterpret_cast<const float4 *>(po + ((q << 4) ^ sown));   // r[n]
                         const float4 b = *reinterpret_cast<const float4 *>(pd + ((q << 4) ^ sown));   // r[n - N/2]
                         const float4 c = *reinterpret_cast<const float4 *>(pn + ((q << 4) ^ sown));   // r[n - N]
@@ -166,10 +219,10 @@ sync_metric_warp_kernel(const float2 *__restrict__ samples, long long n, long lo
                 }
                 if (A == 0.0f) { det = 0; unc = 0; }
                 if (k >= full_tiles) {
-                    const long long firsts = ((long long)k * 32 + lane) * SV_C;
-                    if (firsts + SV_C > n) {
+                    const long long firsts = ((long long)k * 32 + lane) * C;
+                    if (firsts + C > n) {
                         const int valid = (n > firsts) ? (int)(n - firsts) : 0;
-                        const unsigned m = (valid >= 16) ? 0xffffu : ((1u << valid) - 1u);
+                        const unsigned m = (valid >= C) ? FULL : ((1u << valid) - 1u);
                         det &= m; unc &= m;
                     }
                 }
@@ -182,19 +235,19 @@ sync_metric_warp_kernel(const float2 *__restrict__ samples, long long n, long lo
                     while (m) {
                         const int kk = __ffs(m) - 1;
                         m &= m - 1;
-                        const int i = (src << 4) + kk;                 // sample position relative to the tile start
+                        const int i = src * C + kk;                    // sample position relative to the tile start
                         double sr = 0.0, si = 0.0, sen = 0.0;
-                        for (int t2 = lane; t2 < 1024; t2 += 32) {
-                            const int sa = i - t2;                     // -1023 .. 511
-                            const int wa = sa & 511;
+                        for (int t2 = lane; t2 < N; t2 += 32) {
+                            const int sa = i - t2;                     // -(N-1) .. TILE-1
+                            const int wa = sa & (TILE - 1);
                             const float2 a = *reinterpret_cast<const float2 *>(
-                                ring + sw_unit((it + 4 + (sa >> 9)) & 3, wa >> 4, (wa >> 1) & 7) + ((wa & 1) << 3));
+                                ring + swc_unit<C>((it + 4 + (sa >> LT)) & 3, wa / C, (wa % C) >> 1) + ((wa & 1) << 3));
                             sen += (double)a.x * a.x + (double)a.y * a.y;
-                            if (t2 < 512) {
-                                const int sb = sa - 512;               // -1024 .. -1
-                                const int wb = sb & 511;
+                            if (t2 < N / 2) {
+                                const int sb = sa - N / 2;             // -N .. -1
+                                const int wb = sb & (TILE - 1);
                                 const float2 b = *reinterpret_cast<const float2 *>(
-                                    ring + sw_unit((it + 4 + (sb >> 9)) & 3, wb >> 4, (wb >> 1) & 7) + ((wb & 1) << 3));
+                                    ring + swc_unit<C>((it + 4 + (sb >> LT)) & 3, wb / C, (wb % C) >> 1) + ((wb & 1) << 3));
                                 sr += (double)a.x * b.x + (double)a.y * b.y;
                                 si += (double)a.y * b.x - (double)a.x * b.y;
                             }
@@ -210,13 +263,21 @@ sync_metric_warp_kernel(const float2 *__restrict__ samples, long long n, long lo
                         if (lane == src) det = dd ? (det | (1u << kk)) : (det & ~(1u << kk));
                     }
                 }
-                // ---- 16 bits per lane -> 32-bit words
-                const unsigned hi = __shfl_down_sync(0xffffffffu, det, 1);
-                if (!(lane & 1)) {
-                    const long long w = (long long)k * 16 + (lane >> 1);
+                // ---- C bits per lane -> 32-bit words
+                if (C == 16) {
+                    const unsigned hi = __shfl_down_sync(0xffffffffu, det, 1);
+                    if (!(lane & 1)) {
+                        const long long w = (long long)k * 16 + (lane >> 1);
+                        if (w < wps) {
+                            detmask[(long long)s * wps + w] = (det & 0xffffu) | (hi << 16);
+                            trigmask[(long long)s * wps + w] = 0u;         // cleared here: saves a memset pass
+                        }
+                    }
+                } else {
+                    const long long w = (long long)k * 32 + lane;
                     if (w < wps) {
-                        detmask[(long long)s * wps + w] = (det & 0xffffu) | (hi << 16);
-                        trigmask[(long long)s * wps + w] = 0u;         // cleared here: saves a memset pass
+                        detmask[(long long)s * wps + w] = det;
+                        trigmask[(long long)s * wps + w] = 0u;
                     }
                 }
             }

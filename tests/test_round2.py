@@ -507,14 +507,15 @@ def test_rolloff_on_the_warp_tx_kernel(monkeypatch, which, roll):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fft_len,n_streams,n", [(32, 1, 70001), (64, 2, 90000), (128, 1, 50000), (256, 3, 60002), (512, 1, 150000),
-                                                 (512, 2, 700), (64, 1, 511), (256, 1, 16 * 8 * 512 + 5)])
+                                                 (512, 2, 700), (64, 1, 511), (256, 1, 16 * 8 * 512 + 5), (2048, 1, 300001), (2048, 2, 70000),
+                                                 (2048, 1, 1023), (1024, 2, 50002)])
 def test_short_window_warp_sync_kernel(monkeypatch, fft_len, n_streams, n):
-    """fft_len 32 .. 512: the short-window warp-autonomous Schmidl & Cox kernel (default) vs the TMA ring kernel vs the
-    oracle: identical triggers and CFO.  Streams with frames at both ends, a 40 dB louder burst directly in front of a
+    """fft_len 32 .. 512: the short-window warp-autonomous Schmidl & Cox kernel (default), fft_len 1024 / 2048: the
+    chunk-size template of the long-window one; each vs the TMA ring kernel vs the oracle: identical triggers and CFO.  Streams with frames at both ends, a 40 dB louder burst directly in front of a
     quiet frame (every partial window sum must stay local), stretches of exact zeros, odd lengths, spans that end
     inside the last tile."""
     rng = np.random.default_rng(fft_len + n)
-    cfg = _plan(fft_len, {32: 20, 64: 48, 128: 96, 256: 200, 512: 400}[fft_len], 1)
+    cfg = _plan(fft_len, {32: 20, 64: 48, 128: 96, 256: 200, 512: 400, 1024: 600, 2048: 1200}[fft_len], 1)
     orc = cm.make_oracle(cfg)
     pk = cm.rand_packets(rng, 2, 24)
     s_ref, off_ref = orc.tx(pk)
@@ -539,10 +540,11 @@ def test_short_window_warp_sync_kernel(monkeypatch, fft_len, n_streams, n):
         monkeypatch.setenv("OFDMX_NO_WARP_SYNC", env.get("OFDMX_NO_WARP_SYNC", "0"))
         phy = cm.make_phy(cfg)
         res[name] = phy.sync(_to_dev(x if n_streams > 1 else x[0]))
-        if n >= 512:
+        if n >= fft_len:
             from test_gpu_parity import _kernels_used
             used = _kernels_used(phy, lambda: phy.sync(_to_dev(x if n_streams > 1 else x[0])))
-            assert ("sync_metric_warpn_kernel" in used) == (name == "warp"), used
+            kname = "sync_metric_warpn_kernel" if fft_len <= 512 else "sync_metric_warp_kernel"
+            assert (kname in used) == (name == "warp"), used
     ref_t, ref_s, ref_c = [], [], []
     for s in range(n_streams):
         t, c = orc.sync(x[s])

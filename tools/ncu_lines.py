@@ -1,86 +1,66 @@
-#!/usr/bin/env python3
-"""Attribute ncu per-SASS-instruction counts to CUDA source lines.
-usage: ncu_lines.py <report.ncu-rep> <kernel regex> <libofdmx.so> [top N]
-Joins `ncu --page source --csv` (per SASS address: instructions executed, stall samples) with
-`nvdisasm --print-line-info` of the cubin embedded in the library."""
-import csv
+#!/usr/bin/env python
+"""Per-source-line executed-instruction and stall-sample shares from an ncu report captured with
+--import-source on:  python tools/ncu_lines.py report.ncu-rep [min_pct]"""
 import collections
-import glob
-import os
-import re
+import csv
 import subprocess
 import sys
-import tempfile
 
-rep, kre, lib = sys.argv[1:4]
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
-                     capture_output=True, text=True).stdout
-rows = list(csv.reader(txt.splitlines()))
-kname = rows[0][1]
-hdr = rows[1]
-ia, iso, ie, ist = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
-reason_cols = {c[6:]: i for i, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c}
-data, seen = [], set()
-for r in rows[2:]:
-    if len(r) != len(hdr) or r[0] == "Address":
-        continue
-    if r[ia] in seen:
-        break
-    seen.add(r[ia])
-    data.append((int(r[ia], 16), r[iso], int(r[ie] or 0), int(r[ist] or 0),
-                 {c: int(r[i] or 0) for c, i in reason_cols.items()}))
-base = data[0][0]
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
-dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
-kbase = re.match(r"(?:void )?(\w+)", kname).group(1)
-targs = re.search(r"<([^>]*)>", kname)
-tm = ""
-if targs:
-    for a in targs.group(1).split(","):
-        m = re.match(r"\s*\((\w+)\)(\d+)", a)
-        tm += {"int": "Li%sE", "bool": "Lb%sE"}[m.group(1)] % m.group(2)
-pat = r"(_Z\d*" + re.escape(kbase) + ("I" + tm + r"E\w*" if tm else r"\w*") + ")"
-mangled = re.search(pat, dis).group(1)
-sec = dis[dis.index(".section\t.text." + mangled):]
-sec = sec[: sec.index(".section", 20)] if ".section" in sec[20:] else sec
-cur, off2line = ("?", 0), {}
-for line in sec.splitlines():
-    m = re.search(r'//## File "([^"]+)", line (\d+)', line)
-    if m:
-        cur = (os.path.basename(m.group(1)), int(m.group(2)))
-        continue
-    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+\S", line)
-    if m:
-        off2line[int(m.group(1), 16)] = cur
-by = collections.Counter()
-st = collections.Counter()
-tot = 0
-why = collections.defaultdict(collections.Counter)
-allwhy = collections.Counter()
-for a, s, n, w, rs in data:
-    k = off2line.get(a - base, ("?", 0))
-    by[k] += n
-    st[k] += w
-    tot += n
-    why[k].update(rs)
-    allwhy.update(rs)
-print("kernel", kbase, "total warp-instr", tot, "stall samples", sum(st.values()))
-srcs = {}
-for (f, l), n in by.most_common(top):
-    if f not in srcs:
-        cands = glob.glob(os.path.join(os.path.dirname(os.path.abspath(lib)), "..", "csrc", f))
-        srcs[f] = open(cands[0]).read().splitlines() if cands else []
-    text = srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
-    top3 = " ".join("%s:%d" % kv for kv in why[(f, l)].most_common(3) if kv[1])
-    print("%-22s L%-4d %9d %5.1f%%  stall %5.1f%%  [%s]  %s" % (f, l, n, 100.0 * n / tot, 100.0 * st[(f, l)] / max(1, sum(st.values())), top3, text[:70]))
-print("stall reasons overall:", " ".join("%s:%.1f%%" % (k, 100.0 * v / max(1, sum(allwhy.values()))) for k, v in allwhy.most_common(8)))
-# per-file totals
-pf, ps = collections.Counter(), collections.Counter()
-for (f, l), n in by.items():
-    pf[f] += n
-    ps[f] += st[(f, l)]
-for f, n in pf.most_common():
-    print("file %-24s instr %5.1f%%  stall %5.1f%%" % (f, 100.0 * n / tot, 100.0 * ps[f] / max(1, sum(st.values()))))
+
+def main():
+    rep = sys.argv[1]
+    thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, v = rows[0], rows[-1]
+    for key in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
+                "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+                "launch__registers_per_thread", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size",
+                "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"):
+        for i, n in enumerate(h):
+            if n == key:
+                print("%-70s %s %s" % (n, v[i], rows[1][i] if len(rows) > 2 else ""))
+    stall = {}
+    for i, n in enumerate(h):
+        if n.startswith("smsp__average_warp_latency_issue_stalled_") or n.startswith("smsp__average_warps_issue_stalled_"):
+            if n.endswith(".ratio") or n.endswith("_per_issue_active.ratio"):
+                try:
+                    stall[n.split("stalled_")[1].split(".")[0]] = float(v[i])
+                except ValueError:
+                    pass
+    tot = sum(x for k, x in stall.items() if "not_issued" not in k) or 1.0
+    print("stalls:", ", ".join("%s %.1f%%" % (k.replace("_per_warp_active", ""), 100 * x / tot)
+                               for k, x in sorted(stall.items(), key=lambda kv: -kv[1])[:9] if "not_issued" not in k))
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    cur, agg = None, collections.defaultdict(lambda: [0, 0, ""])
+    for r in csv.reader(src.splitlines()):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+            continue
+        if r[0] in ("Line No", "Function Name"):
+            continue
+        if len(r) > 8 and r[2] == "-" and r[0].isdigit():
+            a = agg[(cur, int(r[0]))]
+            a[0] += int(r[7]) if r[7].isdigit() else 0
+            a[1] += int(r[6]) if r[6].isdigit() else 0
+            a[2] = r[1]
+    ti = sum(a[0] for a in agg.values()) or 1
+    ts = sum(a[1] for a in agg.values()) or 1
+    byf = collections.defaultdict(lambda: [0, 0])
+    for (f, l), a in agg.items():
+        byf[f][0] += a[0]
+        byf[f][1] += a[1]
+    for f, a in sorted(byf.items(), key=lambda kv: -kv[1][0]):
+        print("%-28s %5.1f%% instr %5.1f%% samples" % (f, 100.0 * a[0] / ti, 100.0 * a[1] / ts))
+    for (f, l), a in sorted(agg.items()):
+        if 100.0 * a[0] / ti >= thr or 100.0 * a[1] / ts >= thr:
+            print("%-24s %4d %5.2f%%i %5.2f%%s  %s" % (f[:24], l, 100.0 * a[0] / ti, 100.0 * a[1] / ts, a[2].strip()[:96]))
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,10 @@ __device__ long long next_bit(const uint32_t *m, long long i, long long limit, i
     return limit;
 }
 
+// Measured and not kept (round 2, headline workload, 70 us): staging the CTA's words in shared memory (101 us), a
+// persistent grid with the next trip prefetched (83 us), a per-thread 16-word window around each flank (136 us) --
+// the kernel is bound by the instructions of the divergent cluster walks (ncu: 70 % issue utilisation, 1-2 lanes
+// active per warp), not by the latency of their loads.
 #define PL_WPT 8   // detect words per thread
 __global__ void __launch_bounds__(OFDMX_THREADS)
 plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trigmask, long long n,
@@ -71,12 +75,25 @@ plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trig
 {
     const long long total = wps * n_streams;
     const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PL_WPT;
-    for (int qq = 0; qq < PL_WPT; qq++) {
-        const long long g = g0 + qq;
-        if (g >= total) return;
-        const uint32_t word = detmask[g];
+    if (g0 >= total) return;
+    // the thread's eight words as two 16-byte loads (a warp reads 1 KB contiguous); almost all of them are zero
+    uint32_t wv[PL_WPT];
+    if (g0 + PL_WPT <= total && (reinterpret_cast<uintptr_t>(detmask + g0) & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(detmask + g0)), b = __ldg(reinterpret_cast<const uint4 *>(detmask + g0) + 1);
+        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
+    } else {
+#pragma unroll
+        for (int qq = 0; qq < PL_WPT; qq++) wv[qq] = (g0 + qq < total) ? detmask[g0 + qq] : 0u;
+    }
+    if (!(wv[0] | wv[1] | wv[2] | wv[3] | wv[4] | wv[5] | wv[6] | wv[7])) return;
+    // stream and word-in-stream of the thread's first word: one 64-bit division per thread, the following words
+    // step from it (a thread's eight words may cross into the next streams)
+    long long s = g0 / wps, w = g0 - s * wps;
+#pragma unroll
+    for (int qq = 0; qq < PL_WPT; qq++, w++) {
+        while (w >= wps) { w -= wps; s++; }
+        const uint32_t word = wv[qq];
         if (!word) continue;
-        const long long s = g / wps, w = g - s * wps;
         const uint32_t *m = detmask + s * wps;
         uint32_t *tm = trigmask + s * wps;
         const uint32_t prev = (w > 0) ? (m[w - 1] >> 31) : 0u;
@@ -151,16 +168,22 @@ trig_scatter_kernel(const uint32_t *__restrict__ trigmask, long long n_words, lo
     const long long base = ((long long)blockIdx.x * OFDMX_THREADS + threadIdx.x) * TRIG_WPT;
     uint32_t wv[TRIG_WPT];
     int c = 0;
-    for (int q = 0; q < TRIG_WPT; q++) {
-        wv[q] = (base + q < n_words) ? trigmask[base + q] : 0u;
-        c += __popc(wv[q]);
+    if (base + TRIG_WPT <= n_words && (reinterpret_cast<uintptr_t>(trigmask + base) & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(trigmask + base));     // one 16-byte load per thread
+        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < TRIG_WPT; q++) wv[q] = (base + q < n_words) ? trigmask[base + q] : 0u;
     }
+#pragma unroll
+    for (int q = 0; q < TRIG_WPT; q++) c += __popc(wv[q]);
     int total;
     int o = blocksum[blockIdx.x] + block_excl_scan(c, wt, total);
-    for (int q = 0; q < TRIG_WPT; q++) {
+    long long s = base / wps, w = base - s * wps;            // one division per thread; the words step from it
+    for (int q = 0; q < TRIG_WPT; q++, w++) {
         const long long g = base + q;
         if (g >= n_words) break;
-        const long long s = g / wps, w = g - s * wps;
+        while (w >= wps) { w -= wps; s++; }
         if (w == 0) stream_start[s] = o < max_trig ? o : max_trig;
         uint32_t x = wv[q];
         while (x) {
@@ -189,21 +212,34 @@ cfo_kernel(const float2 *__restrict__ samples, long long n, long long stride, in
         const float2 *r = samples + (long long)trig_stream[j] * stride;
         double sr = 0, si = 0;
         if (t - 2 * h + 1 >= 0) {
-            // interior trigger: batches of 8 independent load pairs per lane (the rolled loop exposed one L2/HBM
-            // latency per 32 products)
+            // interior trigger: batches of independent load pairs per lane (the rolled loop exposed one L2/HBM
+            // latency per 32 products): 16 pairs when the half window has that many per lane, else 8
             const float2 *px = r + t - lane, *py = px - h;
-            for (int k0 = 0; k0 < h; k0 += 256) {
-                float2 x[8], y[8];
+            if (h >= 512) {
+                for (int k0 = 0; k0 < h; k0 += 512) {
+                    float2 x[16], y[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int k = k0 + 32 * u;
-                    if (k + lane < h) { x[u] = __ldg(px - k); y[u] = __ldg(py - k); }
-                    else { x[u] = make_float2(0.f, 0.f); y[u] = x[u]; }
+                    for (int u = 0; u < 16; u++) { x[u] = __ldg(px - (k0 + 32 * u)); y[u] = __ldg(py - (k0 + 32 * u)); }
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        sr += (double)x[u].x * y[u].x + (double)x[u].y * y[u].y;
+                        si += (double)x[u].y * y[u].x - (double)x[u].x * y[u].y;
+                    }
                 }
+            } else {
+                for (int k0 = 0; k0 < h; k0 += 256) {
+                    float2 x[8], y[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    sr += (double)x[u].x * y[u].x + (double)x[u].y * y[u].y;
-                    si += (double)x[u].y * y[u].x - (double)x[u].x * y[u].y;
+                    for (int u = 0; u < 8; u++) {
+                        const int k = k0 + 32 * u;
+                        if (k + lane < h) { x[u] = __ldg(px - k); y[u] = __ldg(py - k); }
+                        else { x[u] = make_float2(0.f, 0.f); y[u] = x[u]; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        sr += (double)x[u].x * y[u].x + (double)x[u].y * y[u].y;
+                        si += (double)x[u].y * y[u].x - (double)x[u].x * y[u].y;
+                    }
                 }
             }
         } else

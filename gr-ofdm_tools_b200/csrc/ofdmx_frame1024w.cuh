@@ -254,6 +254,14 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
         // FFT code, so that all warps of the SM share one copy in the instruction cache.
         int off = 0, psyms = 0;
         bool dead = false;
+        float2 phs = make_float2(1.f, 0.f), sD = make_float2(1.f, 0.f);   // fft_len < 1024: carried NCO phasor and its per-symbol step
+        if constexpr (NFFT < 1024) {
+            double td = fs->kappa * (double)D;
+            td -= rint(td);
+            float sn, cs;
+            sincospif(2.0f * (float)td, &sn, &cs);
+            sD = make_float2(cs, sn);
+        }
         for (int sidx = 0; sidx < fs->nsym; sidx++) {
             const long long i0 = t + (long long)sidx * D + p.cp;
             if constexpr (NFFT == 2048) {
@@ -268,7 +276,7 @@ rx_framew_kernel(const KP p, const float2 *__restrict__ samples, long long n, lo
                 }
             } else {
                 fsmall_symbol<NFFT>(p, r, n, i0, t, fs->kappa, make_float2(fs->stx, fs->sty), fs->tnext <= i0 + NFFT - 1, j, jend,
-                                    trig, cfo, Y, tws, lane, ltw);
+                                    trig, cfo, Y, tws, lane, ltw, phs, sD, (sidx & 15) == 0);
             }
             __syncwarp();
             if (sidx == 0) {

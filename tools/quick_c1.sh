@@ -1,6 +1,6 @@
 #!/bin/bash
-# short-window sync kernel: parity tests, then configs[1] and configs[0] kernel times
-python -m pytest tests/test_round2.py tests/test_gpu_parity.py -m gpu -x -q -k "short_window or small_fft or fft256 or fft_len_32" 2>&1 | tail -5
+# small-fft kernels: parity tests (RX and TX), then configs[1] and configs[0] kernel times
+python -m pytest tests -m gpu -x -q -k "short_window or small_fft or fft256 or fft_len_32 or radio or c1 or hier or rolloff or single_sync or several_carrier" 2>&1 | tail -5
 for c in 1 0; do
 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-agc > gpurun_out/qc$c.json 2> gpurun_out/qc$c.err || tail -5 gpurun_out/qc$c.err
 python -c "

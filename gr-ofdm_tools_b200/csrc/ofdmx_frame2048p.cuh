@@ -56,7 +56,17 @@ __device__ __forceinline__ void f2kp_symbol(const KP &p, const float2 *__restric
     float2 v[32];
     const long long sbase = i0 - p.D + lane;          // stream index of this lane's first sample
     const float sgn = half ? -1.0f : 1.0f;
-    if (!slow) {
+    // `slow`: another raw trigger falls inside (or before) this symbol, where the sample-and-hold value of the NCO
+    // changes.  On back-to-back frames that is the NEXT FRAME's trigger arriving a few samples early (its jitter), i.e.
+    // nearly every other frame's last symbol, with only the last few samples of the upper half affected: those are
+    // patched after the uniform-frequency path (c = first affected sample of the upper half); anything else takes
+    // the per-sample path below.
+    int c = 1024;
+    if (slow) {
+        const long long tnx = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
+        c = (tnx - i0 - 1024 >= 800) ? (int)min(tnx - i0 - 1024, 1024LL) : -1;
+    }
+    if (c >= 0) {
         const float2 qs = make_float2(sgn * q1024.x, sgn * q1024.y);
         if (sbase - lane >= 0 && sbase - lane + 2048 <= n) {
 #pragma unroll
@@ -92,10 +102,38 @@ __device__ __forceinline__ void f2kp_symbol(const KP &p, const float2 *__restric
             v[a] = cmul(v[a], ph);
             ph = cmul(ph, st);
         }
+        if (c < 1024) {
+            // upper-half samples m >= c (c >= 800: rows 24 .. 31 at most): add x (P_exact - P_uniform) [W_2048^m]
+            const int a0 = (c - 31) >> 5;
+#pragma unroll 1
+            for (int a = a0; a < 32; a++) {
+                const int m = lane + 32 * a;
+                float2 d = make_float2(0.f, 0.f);
+                if (m >= c) {
+                    const long long i = i0 + m + 1024, sidx = i - p.D;
+                    const float2 x = (sidx >= 0 && sidx < n) ? __ldg(&r[sidx]) : make_float2(0.f, 0.f);
+                    const float2 pe = f2kp_exact_phasor(i, j, jend, trig, cfo);
+                    double tb2 = kappa * (double)(i - t + 1);
+                    tb2 -= rint(tb2);
+                    float s2, c2;
+                    sincospif(2.0f * (float)tb2, &s2, &c2);
+                    d = cmul(x, make_float2(sgn * (pe.x - c2), sgn * (pe.y - s2)));
+                    if (half) {
+                        sincospif(-(float)m * (1.0f / 1024.0f), &s2, &c2);     // W_2048^m
+                        d = cmul(d, make_float2(c2, s2));
+                    }
+                }
+                Tw[a * F1K_ROW + lane] = d;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int a = 24; a < 32; a++)
+                if (a >= a0) v[a] = cadd(v[a], Tw[a * F1K_ROW + lane]);
+            __syncwarp();
+        }
     } else {
-        // another raw trigger falls inside (or before) this symbol: the sample-and-hold value of the NCO changes
-        // there, so the two halves no longer differ by a constant phasor.  Every sample gets its own phase (exact
-        // piecewise accumulation behind the trigger, closed form in front of it).
+        // the general case: the two halves no longer differ by a constant phasor.  Every sample gets its own phase
+        // (exact piecewise accumulation behind the trigger, closed form in front of it).
         const long long tnx = (j + 1 < jend) ? trig[j + 1] : 0x7fffffffffffffffLL;
 #pragma unroll 1
         for (int a = 0; a < 32; a++) {

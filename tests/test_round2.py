@@ -555,3 +555,34 @@ def test_short_window_warp_sync_kernel(monkeypatch, fft_len, n_streams, n):
         assert np.array_equal(trig, np.array(ref_t, np.int64)), name
         assert np.array_equal(st, np.array(ref_s)), name
         np.testing.assert_allclose(cfo, np.array(ref_c, np.float32), atol=2e-6, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bps,snr,cfo", [(6, 28.0, 0.2), (4, 22.0, -0.35), (2, 15.0, 0.45)])
+def test_pair_kernel_next_trigger_inside_the_last_symbol(bps, snr, cfo):
+    """fft_len 2048, back-to-back frames: the next frame's trigger often arrives a few samples early and so falls inside
+    this frame's last symbol, where the sample-and-hold NCO frequency changes.  The pair-of-warps kernel patches the
+    few affected samples after its uniform-frequency path (and takes the per-sample path when the trigger lies
+    deeper in the symbol): records, bytes and equalised symbols against the oracle, and the case must occur."""
+    cfg = cm.cfg_c4(bps_payload=bps)
+    rng = np.random.default_rng(77 + bps)
+    sym_bytes = 1200 * bps // 8
+    pk = [rng.integers(0, 256, 2 * sym_bytes - 4, dtype=np.uint8).tobytes() for _ in range(40)]   # whole symbols
+    s, off = cm.make_oracle(cfg).tx(pk)
+    fr = cm.split_frames(s, off)
+    # a shortened frame now and then puts the next trigger deep inside the symbol (the per-sample path)
+    fr = [f if i % 9 != 4 else f[:len(f) - 300] for i, f in enumerate(fr)]
+    stream = cm.channel(fr, rng, gaps=(0, 0), lead=700, tail=6000, snr_db=snr, cfo=cfo, fft_len=2048)
+    res, ref = _compare_rx(cfg, stream)
+    t = ref["triggers"]
+    D = 2048 + cfg["cp_len"]
+    early = 0
+    for i, f in enumerate(ref["frames"]):
+        nx = t[np.searchsorted(t, f["trigger"], side="right"):][:1]
+        last_end = int(f["trigger"]) + (3 + int(f["frame_syms"]) - 1) * D + cfg["cp_len"] + 2047
+        early += int(len(nx) and nx[0] <= last_end)
+    assert early >= 5, early
+    from test_gpu_parity import _kernels_used
+    phy = cm.make_phy(cfg)
+    assert "rx_framep_kernel" in _kernels_used(phy, lambda: phy.rx(_to_dev(stream)))
+    assert len(res.frames) >= 30

@@ -75,7 +75,7 @@ __device__ __forceinline__ void fsmall_symbol(const KP &p, const float2 *__restr
     if (s0 >= 0 && s0 + NFFT <= n) {                  // whole symbol inside the stream (warp-uniform)
         const float2 *src = r + s0 + lane;
 #pragma unroll
-        for (int a = 0; a < R; a++) v[a] = __ldg(src + 32 * a);
+        for (int a = 0; a < R; a++) v[a] = f1k_ld_stream(src + 32 * a);   // no L1 allocation: the small tables stay resident
     } else {
 #pragma unroll
         for (int a = 0; a < R; a++) {

@@ -504,6 +504,8 @@ def run_rx_config(cid, C, args, dev, world, rank, dist, clock_sampler=None, with
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if cid == 2:
             traffic = tr[dom]["dram_bytes_per_algorithmic_byte"] * algo
+        elif dom in tr.get("configs", {}).get(str(cid), {}):
+            traffic = tr["configs"][str(cid)][dom]["dram_bytes_per_algorithmic_byte"] * algo
     except Exception:
         pass
     out = {

@@ -15,7 +15,10 @@ KERNELS = [
     ("framew_1024.o", "_Z16rx_framew_kernelILi1024ELi4ELb0EEv2KPPK6float2xxPKxPKiPKfS7_S7_P11ofdmx_framePhxPS1_xjii", "rx_framew_kernel<1024,4,false>"),
     ("framew_2048.o", "_Z16rx_framew_kernelILi2048ELi6ELb0EEv2KPPK6float2xxPKxPKiPKfS7_S7_P11ofdmx_framePhxPS1_xjii", "rx_framew_kernel<2048,6,false>"),
     ("framew_64.o", "_Z16rx_framew_kernelILi64ELi2ELb0EEv2KPPK6float2xxPKxPKiPKfS7_S7_P11ofdmx_framePhxPS1_xjii", "rx_framew_kernel<64,2,false>"),
-    ("api.o", "_Z23sync_metric_warp_kernelPK6float2xxfdPjS2_xiiii", "sync_metric_warp_kernel"),
+    ("framep.o", "_Z16rx_framep_kernelILi6ELb0EEv2KPPK6float2xxPKxPKiPKfS7_S7_P11ofdmx_framePhxPS1_xjPKti", "rx_framep_kernel<6,false>"),
+    ("api.o", "_Z23sync_metric_warp_kernelILi16EEvPK6float2xxfdPjS3_xiiii", "sync_metric_warp_kernel<16>"),
+    ("api.o", "_Z23sync_metric_warp_kernelILi32EEvPK6float2xxfdPjS3_xiiii", "sync_metric_warp_kernel<32>"),
+    ("api.o", "_Z24sync_metric_warpn_kernelILi64EEvPK6float2xxfdPjS3_xiiii", "sync_metric_warpn_kernel<64>"),
     ("api.o", "_Z22sync_metric_tma_kernel14CUtensorMap_stPK6float2xxifdPjS3_xxxx", "sync_metric_tma_kernel"),
     ("api.o", "_Z16agc2_span_kernelPK6float2PS_xxiixiffffPKffPfS5_Piii", "agc2_span_kernel"),
     ("txw_1024.o", None, "tx_framew_kernel<1024,4>"),

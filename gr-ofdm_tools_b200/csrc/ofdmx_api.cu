@@ -435,6 +435,18 @@ bool make_sample_map(CUtensorMap *tmap, const float2 *samples, int64_t n_streams
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Spans of the warp-autonomous sync kernels: the warps take spans round-robin (static), so the spans of a stream are
+// sized to come out even -- as many per stream as fit four rounds of all resident warps, all of (almost) the same
+// length -- instead of a fixed length that leaves a short last span per stream and a ragged last round.
+static void plan_spans(long long tiles, long long n_streams, long long warps, long long min_span, long long &span, long long &spans)
+{
+    const long long per = std::max<long long>(1, (4 * warps) / std::max<long long>(1, n_streams));
+    span = (tiles + per - 1) / per;
+    span = std::max<long long>(min_span, std::min<long long>(span, 4096));
+    spans = (tiles + span - 1) / span;
+    span = (tiles + spans - 1) / spans;                     // equalise: the same number of spans, none much shorter
+}
+
 // sync front end shared by ofdmx_rx and ofdmx_sync: detect bits -> triggers -> cfo
 int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_streams, int64_t n_samples,
              int64_t stride, int64_t max_trig, ofdmx_counts *counts_dev, cudaStream_t st)
@@ -450,9 +462,8 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         const long long tile = 32LL * C;
         const long long tiles = (n_samples + tile - 1) / tile;
         const long long warps = (long long)ctx->sm_count * wpc;
-        long long span = (tiles * n_streams + 4 * warps - 1) / (4 * warps);
-        span = std::max<long long>(16, std::min<long long>(span, 1024));
-        const long long spans = (tiles + span - 1) / span;
+        long long span, spans;
+        plan_spans(tiles, n_streams, warps, 16, span, spans);
         const long long total = spans * n_streams;
         const unsigned grid = (unsigned)std::min<long long>((total + wpc - 1) / wpc, (long long)ctx->sm_count);
         KT(K_SYNC_WARP);
@@ -467,9 +478,8 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         // fft_len 32 .. 512: the short-window warp-autonomous kernel (one warm-up tile per span)
         const long long tiles = (n_samples + SW_TILE - 1) / SW_TILE;
         const long long warps = (long long)ctx->sm_count * SW_WARPS;
-        long long span = (tiles * n_streams + 4 * warps - 1) / (4 * warps);
-        span = std::max<long long>(8, std::min<long long>(span, 1024));
-        const long long spans = (tiles + span - 1) / span;
+        long long span, spans;
+        plan_spans(tiles, n_streams, warps, 8, span, spans);
         const long long total = spans * n_streams;
         const unsigned grid = (unsigned)std::min<long long>((total + SW_WARPS - 1) / SW_WARPS, (long long)ctx->sm_count);
         KT(K_SYNC_WARPN);

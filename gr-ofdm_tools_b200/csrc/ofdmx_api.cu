@@ -1425,23 +1425,27 @@ int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_stre
     // gain equals the predecessor's exit gain bit for bit (ofdmx_cond.cuh).  Needs separate in / out buffers (a
     // re-run reads the input again) and spans several warm-up lengths long.
     {
-        // spans of >= 16 K samples (the usual warm-up is 10-15 K for a tracked signal); the warm-up of a row is chosen
-        // on the device from the level in front of it and capped at 4 spans
-        long long min_span = 16384;
+        // spans of >= 8 K samples, one per resident lane at most (the kernel is bound by the serial walk of a warp, so
+        // one wave of short spans beats fewer long ones although the warm-up -- 10-15 K samples for a tracked signal --
+        // is then longer than the span); the warm-up of a warp's rows is chosen on the device from the level in front of
+        // them and capped at 4 spans
+        long long min_span = 8192;
         if (const char *e = getenv("OFDMX_AGC_SPAN")) min_span = std::max(1024LL, atoll(e));
         const long long lanes = (long long)c->sm_count * 16 * 32;
         const bool disjoint = (out_dev + 2 * ((n_streams - 1) * stride + n) <= in_dev) || (in_dev + 2 * ((n_streams - 1) * stride + n) <= out_dev);
         long long spans = std::min<long long>(lanes / n_streams, n / min_span);
-        if (disjoint && spans >= 8 && !c->no_agc_spans) {
+        if (disjoint && spans >= 8 && !c->no_agc_spans && 5 * ((n + spans - 1) / spans + 32) < 0x7fffffffLL) {   // span + warm-up as int
             const long long span = ((n + spans - 1) / spans + 31) / 32 * 32;
-            const long long warm = 4 * span;
+            long long warm = 4 * span;
+            if (const char *e = getenv("OFDMX_AGC_WARM")) warm = std::max(32LL, std::min(warm, atoll(e)));   // experiment: cap of the warm-up
             spans = (n + span - 1) / span;
             const long long rows = n_streams * spans;
             const int rounds = 6;
             if (int rc = grow(c, c->ws_agc, (size_t)rows * 12 + 256)) return rc;
             float *entry = (float *)c->ws_agc.p, *exitg = entry + rows;
             int *need = (int *)(exitg + rows), *n_open = need + rows;
-            const unsigned grid = (unsigned)((rows + 32 * AGC_WARPS - 1) / (32 * AGC_WARPS));
+            // a warp takes 32 consecutive spans of one stream
+            const unsigned grid = (unsigned)((n_streams * ((spans + 31) / 32) + AGC_WARPS - 1) / AGC_WARPS);
             const unsigned vgrid = (unsigned)std::min<long long>((rows + 255) / 256, (long long)c->sm_count * 4);
             CUDA_TRY(c, cudaMemsetAsync(n_open, 0, sizeof(int) * 16, st));
             { KT(K_AGC2); agc2_span_kernel<<<grid, AGC_WARPS * 32, 0, st>>>((const float2 *)in_dev, (float2 *)out_dev, n, stride, (int)n_streams,

@@ -93,6 +93,13 @@ __device__ __forceinline__ float agc2_step(float2 &x, float g, float attack, flo
     return g;
 }
 
+// A warp takes 32 CONSECUTIVE spans of ONE stream (warps per stream = ceil(spans / 32)) and gives them all the same
+// warm-up W (the largest any of its rows asks for, a multiple of 32): row rr of a tile is then the fixed distance
+// rr * span from row 0, so loads and stores are plain pointer arithmetic, every lane walks the same iteration range
+// [0, W + span), the entry gain is captured and the output starts at iteration W for everybody.  Lanes whose warm-up
+// would begin before the stream (k * span < W; the first span in particular) simply start walking later, at sample
+// 0 with the gain the call was entered with -- which is exact, not a guess.  The walk itself is the warp's serial
+// time (few streams = few warps per SM), so the next tile's loads are in flight while the current tile is walked.
 __global__ void __launch_bounds__(AGC_WARPS * 32)
 agc2_span_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long long n, long long stride, int n_streams,
                  int spans, long long span, int warm, float attack, float decay, float reference, float max_gain,
@@ -101,76 +108,102 @@ agc2_span_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, long l
 {
     __shared__ float2 tile[AGC_WARPS][32][33];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long rows = (long long)n_streams * spans;
-    const long long r0 = ((long long)blockIdx.x * AGC_WARPS + w) * 32;
-    if (r0 >= rows) return;
-    const long long row = r0 + lane;
-    const bool live = row < rows;
-    const int s = live ? (int)(row / spans) : 0, k = live ? (int)(row - (long long)s * spans) : 0;
+    const int wps = (spans + 31) >> 5;                              // warps per stream
+    const long long gwarp = (long long)blockIdx.x * AGC_WARPS + w;
+    if (gwarp >= (long long)n_streams * wps) return;
+    const int s = (int)(gwarp / wps), kbase = (int)(gwarp - (long long)s * wps) * 32;
+    const int k = kbase + lane;
+    const bool live = k < spans;
+    const long long row = (long long)s * spans + k;
     bool run = live;
     if (repair) run = live && k > 0 && need[row] != 0;
-    if (!__any_sync(0xffffffffu, run)) return;
-    const long long a = (long long)k * span;                       // first sample of the span
-    // warm-up length of this row: the loop forgets its state at 1 - decay |x| per sample, so ~24 time constants
-    // 1 / (decay E|x|) take a gain error of order one below float resolution (plus a margin for the last bits to
-    // coincide); E|x| is sampled from the 256 samples in front of the span.  Capped at `warm`: a row whose loop
-    // barely contracts (weak signal, zero gap) will fail the acceptance test and be repaired instead.
-    int skip = 0;
-    if (!repair && k > 0 && run) {
-        const float2 *q = in + (long long)s * stride + a;
-        float m = 0.f;
-        const int cnt = (int)min(64LL, a / 4);
-        for (int i = 1; i <= cnt; i++) { const float2 v = q[-4 * i]; m += fabsf(v.x) + fabsf(v.y); }
-        m = (cnt > 0) ? m * 0.75f / (float)cnt : 0.f;              // |re| + |im| ~ 1.3 |x|
-        const float tau = 1.0f / fmaxf(decay * m, 1e-9f);
-        const float want = fminf(24.0f * tau + 1536.0f, (float)warm);
-        skip = (int)min((long long)want, a);
-        skip = (skip + 31) & ~31;                                  // keep 256-byte alignment of the row start
-        if (skip > a) skip = (int)a;
-    }
-    const long long first = a - skip, len = min(span, n - a) + skip;
-    float g = 1.0f;
-    if (run) g = (k == 0 || !repair) ? gain_io[s] : exitg[row - 1];      // warm-up guess: the gain the call was entered with
-    if (run && repair) entry[row] = g;
-    const float2 *src = in + (long long)s * stride + first;
-    float2 *dst = out + (long long)s * stride + first;
-    // per-lane geometry differs (the first span has no warm-up): lanes exchange it by shuffles inside the tile loops
-    long long maxlen = run ? len : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    for (long long i0 = 0; i0 < maxlen; i0 += 32) {
-        // load: row rr of the tile = 32 consecutive samples of lane rr's range
-#pragma unroll 4
-        for (int rr = 0; rr < 32; rr++) {
-            const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)src, rr);
-            const long long ln = __shfl_sync(0xffffffffu, run ? len : 0, rr);
-            float2 v = make_float2(0.f, 0.f);
-            if (i0 + lane < ln) v = __ldcs(reinterpret_cast<const float2 *>(sp) + i0 + lane);
-            tile[w][rr][lane] = v;
+    const unsigned runmask = __ballot_sync(0xffffffffu, run);
+    if (!runmask) return;
+    const float2 *ins = in + (long long)s * stride;
+    float2 *outs = out + (long long)s * stride;
+    const long long a = (long long)k * span;                        // first sample of this lane's span
+    // warm-up: the loop forgets its state at 1 - decay |x| per sample, so ~24 time constants 1 / (decay E|x|) take a
+    // gain error of order one below float resolution (plus a margin for the last bits to coincide); E|x| is sampled
+    // in front of the span.  Capped at `warm`: a row whose loop barely contracts (weak signal,
+    // zero gap) will fail the acceptance test and be repaired instead.
+    int W = 0;
+    if (!repair) {
+        float want = 0.f;
+        if (run && k > 0) {
+            // 64 samples spread over the (up to) 8192 samples in front of the span: what contracts the warm-up is the
+            // mean level over its whole length, and a short window that happens to sit on a quiet stretch of a frame made
+            // one row in most warps ask for three times the warm-up of the others (the warp walks the maximum)
+            const float2 *q = ins + a;
+            float m = 0.f;
+            const int st = (int)max(4LL, min(a, 8192LL) / 64);
+            const int cnt = (int)min(64LL, a / st);
+            for (int i = 1; i <= cnt; i++) { const float2 v = q[-(long long)st * i]; m += fabsf(v.x) + fabsf(v.y); }
+            m = (cnt > 0) ? m * 0.75f / (float)cnt : 0.f;           // |re| + |im| ~ 1.3 |x|
+            const float tau = 1.0f / fmaxf(decay * m, 1e-9f);
+            want = fminf(24.0f * tau + 1536.0f, (float)warm);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) want = fmaxf(want, __shfl_xor_sync(0xffffffffu, want, o));
+        W = ((int)want + 31) & ~31;
+    }
+    // this lane walks iterations [start, stop): iteration it is sample a - W + it of the stream
+    const int start = (int)max(0LL, (long long)W - a);
+    const int stop = run ? W + (int)min(span, n - a) : 0;
+    const int total = W + (int)span;                                // warp-uniform iteration count (multiple-of-32 tiles)
+    float g = 1.0f;
+    if (run) g = repair ? exitg[row - 1] : gain_io[s];
+    if (run && repair) entry[row] = g;
+    (void)guess;
+    const long long base0 = (long long)kbase * span - W;            // stream index of row 0, iteration 0
+    float2 v[32];
+    auto load_tile = [&](int it0) {
+        const long long g0 = base0 + it0 + lane;
+#pragma unroll
+        for (int rr = 0; rr < 32; rr++) {
+            const long long gi = g0 + (long long)rr * span;
+            v[rr] = make_float2(0.f, 0.f);
+            if (((runmask >> rr) & 1u) && gi >= 0 && gi < n) v[rr] = __ldcs(ins + gi);
+        }
+    };
+    load_tile(0);
+    for (int it0 = 0; it0 < total; it0 += 32) {
+#pragma unroll
+        for (int rr = 0; rr < 32; rr++) tile[w][rr][lane] = v[rr];
         __syncwarp();
-        if (run) {
-            const int nc = (int)min((long long)32, len - i0);
+        if (it0 + 32 < total) load_tile(it0 + 32);
+        if (it0 + 32 > start && it0 < stop) {
+            const int q0 = max(0, start - it0), q1 = min(32, stop - it0);
+            if (!repair && it0 <= W && W < it0 + 32 && W >= start && W < stop) {
+                // the tile in which the span proper begins: capture the entry gain in front of sample W
+                for (int q = q0; q < q1; q++) {
+                    if (it0 + q == W) entry[row] = g;
+                    float2 x = tile[w][lane][q];
+                    g = agc2_step(x, g, attack, decay, reference, max_gain, abs_rate);
+                    tile[w][lane][q] = x;
+                }
+            } else {
 #pragma unroll 4
-            for (int q = 0; q < nc; q++) {
-                if (!repair && i0 + q == skip) entry[row] = g;     // gain on entering the span proper
-                float2 x = tile[w][lane][q];
-                g = agc2_step(x, g, attack, decay, reference, max_gain, abs_rate);
-                tile[w][lane][q] = x;
+                for (int q = q0; q < q1; q++) {
+                    float2 x = tile[w][lane][q];
+                    g = agc2_step(x, g, attack, decay, reference, max_gain, abs_rate);
+                    tile[w][lane][q] = x;
+                }
             }
         }
         __syncwarp();
+        if (it0 + 32 > W) {                                          // output starts at iteration W
+            const long long g0 = base0 + it0 + lane;
+            const bool col = it0 + lane >= W;
 #pragma unroll 4
-        for (int rr = 0; rr < 32; rr++) {
-            const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)dst, rr);
-            const long long ln = __shfl_sync(0xffffffffu, run ? len : 0, rr);
-            const int sk = __shfl_sync(0xffffffffu, skip, rr);
-            if (i0 + lane < ln && i0 + lane >= sk) __stcs(reinterpret_cast<float2 *>(dp) + i0 + lane, tile[w][rr][lane]);
+            for (int rr = 0; rr < 32; rr++) {
+                const long long gi = g0 + (long long)rr * span;
+                if (col && ((runmask >> rr) & 1u) && gi < n && kbase + rr < spans) __stcs(outs + gi, tile[w][rr][lane]);
+            }
         }
         __syncwarp();
     }
     if (run) {
-        if (!repair && len <= skip) entry[row] = g;
+        if (!repair && W >= stop) entry[row] = g;                   // empty span (cannot happen for k < spans; kept for safety)
         exitg[row] = g;
     }
 }

@@ -1436,8 +1436,7 @@ int ofdmx_agc2(ofdmx_ctx *c, const float *in_dev, float *out_dev, int64_t n_stre
         long long spans = std::min<long long>(lanes / n_streams, n / min_span);
         if (disjoint && spans >= 8 && !c->no_agc_spans && 5 * ((n + spans - 1) / spans + 32) < 0x7fffffffLL) {   // span + warm-up as int
             const long long span = ((n + spans - 1) / spans + 31) / 32 * 32;
-            long long warm = 4 * span;
-            if (const char *e = getenv("OFDMX_AGC_WARM")) warm = std::max(32LL, std::min(warm, atoll(e)));   // experiment: cap of the warm-up
+            const long long warm = 4 * span;
             spans = (n + span - 1) / span;
             const long long rows = n_streams * spans;
             const int rounds = 6;

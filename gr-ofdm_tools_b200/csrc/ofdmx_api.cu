@@ -840,7 +840,7 @@ static int build_plan(const ofdmx_params *prm, PlanFields *c, Stage &stg)
     }
     // ---- fft_len 1024 warp-per-packet TX kernel: per-bin allocation map and the constant sync symbols
     if (nsw == 2 && (N == 1024 || N == 512 || N == 256 || N == 128 || N == 64) && prm->n_occ_sets == 1 && prm->n_pilot_sets <= 1 && !kp.pil_in_occ
-        && kp.bps_h == 1 && c->hl >= 32) {
+        && kp.bps_h == 1 && c->hl >= 32 && kp.roll <= 512) {   // (the flank samples are parked in half of the transpose buffer)
         std::vector<uint16_t> tx_map((size_t)N, (uint16_t)TXW_EMPTY);
         for (int q = 0; q < occ_size[0]; q++) tx_map[occ_bins[occ_base[0] + q] ^ (N / 2)] = (uint16_t)q;   // later entries win, as in the scatter
         for (int q = 0; q < (int)pil_bins.size(); q++) tx_map[pil_bins[q] ^ (N / 2)] = (uint16_t)(TXW_PILOT | q);

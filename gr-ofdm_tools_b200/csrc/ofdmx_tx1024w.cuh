@@ -69,25 +69,35 @@ __device__ __forceinline__ void tx_ifft_store(float2 (&v)[NFFT / 32], float2 *__
                 if (t >= NFFT - cp) dst[t - (NFFT - cp)] = w;
             }
         } else {
+            // The flank arithmetic stays out of the unrolled store loop (32 copies of it made the hot code larger still:
+            // 228 -> 258 Gsamples/s; running ONE copy of the 32-point transform twice on top of that measured slower, 251): the loop only parks the raw samples the
+            // flanks need in the (now free) transpose buffer -- Tw[m] = x[fft_len - cp + m] for the up flank,
+            // Tw[512 + t] = x[t] for the delay line, m, t < nfl -- and two short rolled loops do the arithmetic.
+            __syncwarp();             // every lane has read its row of Tw
 #pragma unroll
             for (int q = 0; q < 32; q++) {
                 const int t = lane + 32 * brev5(q);
                 const float2 w = finish(v[q]);
                 dst[cp + t] = w;
-                if (t >= NFFT - cp) {
-                    const int m = t - (NFFT - cp);
-                    if (m < nfl) {        // up flank + the delay line of the previous symbol
-                        const float up = flank[m];
-                        const float2 tl = tail[m];
-                        dst[m] = finish(make_float2(__fadd_rn(__fmul_rn(v[q].x, up), tl.x), __fadd_rn(__fmul_rn(v[q].y, up), tl.y)));
-                    } else dst[m] = w;
+                const int m = t - (NFFT - cp);
+                if (m >= 0) {
+                    if (m < nfl) Tw[m] = v[q];
+                    else dst[m] = w;
                 }
+                if (t < nfl) Tw[512 + t] = v[q];
+            }
+            __syncwarp();
+            for (int m = lane; m < nfl; m += 32) {            // up flank + the delay line of the previous symbol
+                const float2 x = Tw[m];
+                const float up = flank[m];
+                const float2 tl = tail[m];
+                dst[m] = finish(make_float2(__fadd_rn(__fmul_rn(x.x, up), tl.x), __fadd_rn(__fmul_rn(x.y, up), tl.y)));
             }
             __syncwarp();             // every old tail value has been consumed
-#pragma unroll
-            for (int q = 0; q < 32; q++) {
-                const int t = lane + 32 * brev5(q);
-                if (t < nfl) { const float dn = flank[nfl + t]; tail[t] = make_float2(__fmul_rn(v[q].x, dn), __fmul_rn(v[q].y, dn)); }
+            for (int t = lane; t < nfl; t += 32) {
+                const float2 x = Tw[512 + t];
+                const float dn = flank[nfl + t];
+                tail[t] = make_float2(__fmul_rn(x.x, dn), __fmul_rn(x.y, dn));
             }
             __syncwarp();
         }

@@ -37,12 +37,12 @@ struct DevBuf {
 
 enum KSlot { K_SYNC = 0, K_PLATEAU, K_TRIG_COUNT, K_TRIG_SCAN, K_TRIG_SCATTER, K_CFO, K_FRAME, K_CHAIN_NEXT, K_CHAIN_ENTRY,
              K_CHAIN_MARK, K_CHAIN_SCAN, K_CHAIN_EMIT, K_TX_OFF, K_TX, K_FFT, K_CRC, K_FRAME1K, K_FRAME1KW, K_SYNC_FAST,
-             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_FRAMEP, K_SYNC_WARPN, K_NSLOTS };
+             K_SYNC_TMA, K_AGC2, K_SYNC_WARP, K_TX1KW, K_IIR, K_PAPR, K_AGC2_AUX, K_FRAMEP, K_SYNC_WARPN, K_CHAIN_SMALL, K_NSLOTS };
 static const char *const kSlotNames[K_NSLOTS] = {
     "(unused)", "plateau_kernel", "(unused)", "trig_scan_kernel", "trig_scatter_kernel",
     "cfo_kernel", "rx_frame_kernel", "chain_next_kernel", "chain_entry_kernel", "chain_mark_kernel",
     "chain_scan_kernel", "chain_emit_kernel", "tx_offsets_kernel", "tx_frame_kernel", "fft_vcc_kernel", "crc32_kernel",
-    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel", "rx_framep_kernel", "sync_metric_warpn_kernel" };
+    "rx_frame1024_kernel", "rx_framew_kernel", "sync_metric_fast_kernel", "sync_metric_tma_kernel", "agc2_kernel", "sync_metric_warp_kernel", "tx_framew_kernel", "iir_ccd_kernel", "papr_kernel", "agc2_verify/mopup/final_kernel", "rx_framep_kernel", "sync_metric_warpn_kernel", "chain_small_kernel" };
 
 struct ProfRec { int slot; cudaEvent_t a, b; };
 
@@ -1300,6 +1300,13 @@ static int rx_core(ofdmx_ctx *c, DevBuf &wsbuf, const float *samples_dev, int64_
         rx_frame_kernel<<<c->sm_count * 2, OFDMX_THREADS, c->frame_smem, st>>>(
             kp_call, smp, n_samples, stride, w.trig, w.trig_stream, w.cfo, w.stream_start, w.n_trig, w.spec, bytes_out,
             byte_stride, (float2 *)z_out, z_stride);
+    }
+    if (w.nblk == 1) {      // trigger capacity of the call fits one block: one launch instead of five
+        KT(K_CHAIN_SMALL);
+        chain_small_kernel<<<1, CH_T, 0, st>>>(c->kp, w.trig, w.trig_stream, w.spec, w.stream_start, w.n_trig, c->emit_all ? 1 : 0,
+                                               counts_dev, frames_out);
+        CUDA_TRY(c, cudaGetLastError());
+        return OFDMX_OK;
     }
     { KT(K_CHAIN_NEXT); chain_next_kernel<<<w.nblk, CH_T, 0, st>>>(c->kp, w.trig, w.trig_stream, w.spec, w.stream_start, w.n_trig,
                                                                  w.jumpA, w.jumpB); }

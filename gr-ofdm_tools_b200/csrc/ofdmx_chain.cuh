@@ -177,3 +177,84 @@ chain_emit_kernel(const ofdmx_frame *__restrict__ spec, const int *__restrict__ 
         __syncthreads();
     }
 }
+
+// All five steps in ONE single-CTA kernel for calls whose trigger capacity fits one block (<= CH_B triggers: small
+// receive calls, streaming chunks): next[] -> examined marks by pointer doubling from trigger 0 -> ordered emit.  The
+// five launches above cost ~50 us on such a call -- a quarter of a configs[0] step -- for microseconds of work.
+__global__ void __launch_bounds__(CH_T)
+chain_small_kernel(const KP p, const long long *__restrict__ trig, const int *__restrict__ trig_stream,
+                   const ofdmx_frame *__restrict__ spec, const int *__restrict__ stream_start,
+                   const int *__restrict__ n_trig_dev, int emit_all, ofdmx_counts *__restrict__ counts,
+                   ofdmx_frame *__restrict__ frames_out)
+{
+    __shared__ int jA[CH_B], jB[CH_B];
+    __shared__ uint8_t mA[CH_B], mB[CH_B];
+    __shared__ int wt[33];
+    const int nt = min(*n_trig_dev, CH_B), cnt = nt;
+    if (cnt <= 0) {
+        if (threadIdx.x == 0) counts->n_frames = 0;
+        return;
+    }
+    for (int i = threadIdx.x; i < cnt; i += CH_T) {
+        const ofdmx_frame f = spec[i];
+        const int b = stream_start[trig_stream[i] + 1];          // first trigger of the next stream
+        long long resume = 0;
+        int nx = -1;
+        if (!(f.flags & OFDMX_F_HDR_SEEN)) nx = b;                // demux stalls waiting for the header
+        else if (!(f.flags & OFDMX_F_HDR_OK)) resume = f.trigger + 1;   // header CRC failed
+        else if (!(f.flags & OFDMX_F_COMPLETE)) nx = b;           // demux stalls waiting for the payload
+        else
+            resume = (f.frame_syms > 0) ? f.trigger + (long long)(p.nsw + 1 + f.frame_syms) * p.D - p.holdoff
+                                        : f.trigger + (long long)(p.nsw + 1) * p.D;
+        if (nx < 0) {
+            int lo = i + 1, hi = b;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (trig[mid] < resume) lo = mid + 1; else hi = mid;
+            }
+            nx = lo;
+        }
+        jA[i] = (nx < cnt) ? nx : CH_B;
+        mA[i] = (i == 0) ? 1 : 0;                                 // the orbit starts at trigger 0
+    }
+    __syncthreads();
+    int *jc = jA, *jn = jB;
+    uint8_t *mc = mA, *mn = mB;
+    for (int span = 1; span < cnt; span <<= 1) {
+        for (int li = threadIdx.x; li < cnt; li += CH_T) mn[li] = mc[li];
+        __syncthreads();
+        for (int li = threadIdx.x; li < cnt; li += CH_T) {
+            const int jx = jc[li];
+            if (jx < cnt) {
+                if (mc[li]) mn[jx] = 1;
+                jn[li] = jc[jx];
+            } else {
+                jn[li] = CH_B;
+            }
+        }
+        __syncthreads();
+        int *tj = jc; jc = jn; jn = tj;
+        uint8_t *tm = mc; mc = mn; mn = tm;
+    }
+    int carry = 0;
+    for (int i0 = 0; i0 < cnt; i0 += CH_T) {
+        const int i = i0 + threadIdx.x;
+        ofdmx_frame f;
+        int em = 0;
+        bool examined = false;
+        if (i < cnt) {
+            f = spec[i];
+            examined = mc[i] != 0;
+            em = (emit_all || (examined && (f.flags & OFDMX_F_HDR_OK) && (f.flags & OFDMX_F_COMPLETE))) ? 1 : 0;
+        }
+        int total;
+        const int ex = block_excl_scan(em, wt, total);
+        if (em) {
+            if (examined) f.flags |= OFDMX_F_ACCEPTED;
+            frames_out[carry + ex] = f;
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts->n_frames = carry;
+}

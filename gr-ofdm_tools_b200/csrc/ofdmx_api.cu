@@ -479,7 +479,7 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
         const long long tiles = (n_samples + SW_TILE - 1) / SW_TILE;
         const long long warps = (long long)ctx->sm_count * SW_WARPS;
         long long span, spans;
-        plan_spans(tiles, n_streams, warps, 8, span, spans);
+        plan_spans(tiles, n_streams, warps, 4, span, spans);     // short spans only when the input is small: latency of small calls
         const long long total = spans * n_streams;
         const unsigned grid = (unsigned)std::min<long long>((total + SW_WARPS - 1) / SW_WARPS, (long long)ctx->sm_count);
         KT(K_SYNC_WARPN);

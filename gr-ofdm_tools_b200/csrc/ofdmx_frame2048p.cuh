@@ -70,7 +70,7 @@ __device__ __forceinline__ void f2kp_symbol(const KP &p, const float2 *__restric
         const float2 qs = make_float2(sgn * q1024.x, sgn * q1024.y);
         if (sbase - lane >= 0 && sbase - lane + 2048 <= n) {
 #pragma unroll
-            for (int a = 0; a < 32; a++) v[a] = f1k_ld_stream(&r[sbase + 32 * a]);   // no L1 allocation: the small tables stay resident
+            for (int a = 0; a < 32; a++) v[a] = half ? __ldg(&r[sbase + 32 * a]) : f1k_ld_stream(&r[sbase + 32 * a]);   // one warp of the pair allocates in L1 (the other's read of the same line merges with it), the other streams
             // (the upper half in four groups of eight: 64 more registers for it do not exist; measured alternatives --
             // cp.async of the upper half into the transpose buffer, one rolled copy of the 32-point transform -- cost
             // more in spills than they gained)
@@ -78,7 +78,7 @@ __device__ __forceinline__ void f2kp_symbol(const KP &p, const float2 *__restric
             for (int g = 0; g < 4; g++) {
                 float2 hi[8];
 #pragma unroll
-                for (int a = 0; a < 8; a++) hi[a] = f1k_ld_stream(&r[sbase + 1024 + 32 * (8 * g + a)]);
+                for (int a = 0; a < 8; a++) hi[a] = half ? __ldg(&r[sbase + 1024 + 32 * (8 * g + a)]) : f1k_ld_stream(&r[sbase + 1024 + 32 * (8 * g + a)]);
 #pragma unroll
                 for (int a = 0; a < 8; a++) v[8 * g + a] = cadd(v[8 * g + a], cmul(hi[a], qs));
             }

@@ -522,8 +522,16 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
     { KT(K_TRIG_SCAN); trig_scan_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nb, (int)max_trig, counts_dev, w.n_trig, w.stream_start, n_streams); }
     { KT(K_TRIG_SCATTER); trig_scatter_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.wps, w.blocksum, (int)max_trig,
                                                                              w.trig, w.trig_stream, w.stream_start); }
-    { KT(K_CFO); cfo_kernel<<<ctx->sm_count * 8, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream,
-                                                                          w.n_trig, w.cfo); }
+    {
+        KT(K_CFO);
+        const unsigned cg = ctx->sm_count * 8;
+        if (kp.N <= 64)
+            cfo_small_kernel<8><<<cg, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream, w.n_trig, w.cfo);
+        else if (kp.N == 128)
+            cfo_small_kernel<16><<<cg, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream, w.n_trig, w.cfo);
+        else
+            cfo_kernel<<<cg, OFDMX_THREADS, 0, st>>>(samples, n_samples, stride, kp.N, w.trig, w.trig_stream, w.n_trig, w.cfo);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }

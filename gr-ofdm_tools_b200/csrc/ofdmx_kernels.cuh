@@ -259,6 +259,44 @@ cfo_kernel(const float2 *__restrict__ samples, long long n, long long stride, in
     (void)n;
 }
 
+// Short windows (fft_len <= 256): a whole warp per trigger leaves most lanes with one product and pays a five-step
+// float64 reduction for it, so G = fft_len/8 lanes (8 .. 32) share a trigger and a warp takes 32/G of them.
+template <int G>
+__global__ void __launch_bounds__(OFDMX_THREADS)
+cfo_small_kernel(const float2 *__restrict__ samples, long long n, long long stride, int N,
+                 const long long *__restrict__ trig, const int *__restrict__ trig_stream,
+                 const int *__restrict__ n_trig_dev, float *__restrict__ cfo)
+{
+    constexpr int TPW = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
+    const int nt = *n_trig_dev;
+    const int h = N >> 1;
+    const int warps = gridDim.x * (OFDMX_THREADS / 32);
+    for (int j0 = (blockIdx.x * (OFDMX_THREADS / 32) + (threadIdx.x >> 5)) * TPW; j0 < nt; j0 += warps * TPW) {
+        const int j = j0 + grp;
+        double sr = 0, si = 0;
+        if (j < nt) {
+            const long long t = trig[j];
+            const float2 *r = samples + (long long)trig_stream[j] * stride;
+#pragma unroll 4
+            for (int k = gl; k < h; k += G) {
+                const long long a = t - k, b = a - h;
+                if (b < 0) continue;
+                const float2 x = __ldg(&r[a]), y = __ldg(&r[b]);
+                sr += (double)x.x * y.x + (double)x.y * y.y;
+                si += (double)x.y * y.x - (double)x.x * y.y;
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        if (gl == 0 && j < nt) cfo[j] = (float)atan2(-si, -sr);
+    }
+    (void)n;
+}
+
 #endif  // OFDMX_GENERIC_KERNELS
 // =============================================================================================
 // RX frame kernel: everything downstream of the trigger for one frame, in one CTA.

@@ -517,8 +517,13 @@ int run_sync(ofdmx_ctx *ctx, const RxWs &w, const float2 *samples, int64_t n_str
 #undef SVF
     }
     const long long pb = (w.n_words + OFDMX_THREADS * PL_WPT - 1) / (OFDMX_THREADS * PL_WPT);
-    { KT(K_PLATEAU); plateau_kernel<<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp,
-                                                                            w.blocksum); }
+    {
+        KT(K_PLATEAU);
+        if (n_samples + 2LL * kp.cp + 64 < 0x7fffffffLL)      // per-stream sample indices fit an int
+            plateau_kernel<int><<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp, w.blocksum);
+        else
+            plateau_kernel<long long><<<(unsigned)pb, OFDMX_THREADS, 0, st>>>(w.detmask, w.trigmask, n_samples, w.wps, n_streams, kp.cp, w.blocksum);
+    }
     { KT(K_TRIG_SCAN); trig_scan_kernel<<<1, 1024, 0, st>>>(w.blocksum, w.nb, (int)max_trig, counts_dev, w.n_trig, w.stream_start, n_streams); }
     { KT(K_TRIG_SCATTER); trig_scatter_kernel<<<w.nb, OFDMX_THREADS, 0, st>>>(w.trigmask, w.n_words, w.wps, w.blocksum, (int)max_trig,
                                                                              w.trig, w.trig_stream, w.stream_start); }

@@ -25,23 +25,28 @@
 // clusters: a run start preceded by >= cp+1 clear bits is reached by the sequential scan in its
 // fresh state, so each such start can be walked by its own thread.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mword(const uint32_t *m, long long w, long long wps)
+// Index type I of the walks: int when the stream length fits (the cluster walks are instruction bound and 64-bit
+// index arithmetic is two instructions per operation), long long otherwise.
+template <typename I>
+__device__ __forceinline__ uint32_t mword(const uint32_t *m, I w, I wps)
 {
     return (w < 0 || w >= wps) ? 0u : m[w];
 }
-__device__ __forceinline__ int mbit(const uint32_t *m, long long i, long long n, long long wps)
+template <typename I>
+__device__ __forceinline__ int mbit(const uint32_t *m, I i, I n, I wps)
 {
     if (i < 0 || i >= n) return 0;
-    return (mword(m, i >> 5, wps) >> (i & 31)) & 1u;
+    return (mword<I>(m, i >> 5, wps) >> (i & 31)) & 1u;
 }
 // are all bits in [lo, hi) clear?  (indices < 0 count as clear)
-__device__ bool bits_clear(const uint32_t *m, long long lo, long long hi, long long wps)
+template <typename I>
+__device__ bool bits_clear(const uint32_t *m, I lo, I hi, I wps)
 {
     if (lo < 0) lo = 0;
     if (hi <= lo) return true;
-    long long w0 = lo >> 5, w1 = (hi - 1) >> 5;
-    for (long long w = w0; w <= w1; w++) {
-        uint32_t x = mword(m, w, wps);
+    I w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    for (I w = w0; w <= w1; w++) {
+        uint32_t x = mword<I>(m, w, wps);
         if (w == w0) x &= 0xffffffffu << (lo & 31);
         if (w == w1 && ((hi & 31) != 0)) x &= 0xffffffffu >> (32 - (hi & 31));
         if (x) return false;
@@ -49,14 +54,15 @@ __device__ bool bits_clear(const uint32_t *m, long long lo, long long hi, long l
     return true;
 }
 // first index >= i whose bit equals `val`, searching no further than limit (exclusive); returns limit if none
-__device__ long long next_bit(const uint32_t *m, long long i, long long limit, int val, long long wps)
+template <typename I>
+__device__ I next_bit(const uint32_t *m, I i, I limit, int val, I wps)
 {
     while (i < limit) {
-        uint32_t x = mword(m, i >> 5, wps);
+        uint32_t x = mword<I>(m, i >> 5, wps);
         if (!val) x = ~x;
         x &= 0xffffffffu << (i & 31);
         if (x) {
-            long long j = ((i >> 5) << 5) + (__ffs(x) - 1);
+            I j = ((i >> 5) << 5) + (__ffs(x) - 1);
             return j < limit ? j : limit;
         }
         i = ((i >> 5) + 1) << 5;
@@ -69,10 +75,13 @@ __device__ long long next_bit(const uint32_t *m, long long i, long long limit, i
 // the kernel is bound by the instructions of the divergent cluster walks (ncu: 70 % issue utilisation, 1-2 lanes
 // active per warp), not by the latency of their loads.
 #define PL_WPT 8   // detect words per thread
+template <typename I>
 __global__ void __launch_bounds__(OFDMX_THREADS)
-plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trigmask, long long n,
-               long long wps, long long n_streams, int cp, int *__restrict__ blocksum)
+plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trigmask, long long n_ll,
+               long long wps_ll, long long n_streams, int cp, int *__restrict__ blocksum)
 {
+    const long long wps = wps_ll;
+    const I n = (I)n_ll, wpsI = (I)wps_ll;
     const long long total = wps * n_streams;
     const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PL_WPT;
     if (g0 >= total) return;
@@ -96,33 +105,34 @@ plateau_kernel(const uint32_t *__restrict__ detmask, uint32_t *__restrict__ trig
         if (!word) continue;
         const uint32_t *m = detmask + s * wps;
         uint32_t *tm = trigmask + s * wps;
+        const I wI = (I)w;
         const uint32_t prev = (w > 0) ? (m[w - 1] >> 31) : 0u;
         uint32_t rising = word & ~((word << 1) | prev);
         while (rising) {
             const int b = __ffs(rising) - 1;
             rising &= rising - 1;
-            long long i = (w << 5) + b;
-            if (!bits_clear(m, i - (cp + 1), i, wps)) continue;   // reached in non-fresh state: owned by an earlier cluster
+            I i = (wI << 5) + b;
+            if (!bits_clear<I>(m, i - (cp + 1), i, wpsI)) continue;   // reached in non-fresh state: owned by an earlier cluster
             // sequential walk of this cluster
             for (;;) {
-                if (n - i < 2LL * cp) break;                       // "come back later": never at stream end
-                const long long start = i;
-                i = next_bit(m, i, n, 0, wps);                     // end of run (exclusive)
+                if (n - i < 2 * (I)cp) break;                       // "come back later": never at stream end
+                const I start = i;
+                i = next_bit<I>(m, i, n, 0, wpsI);                     // end of run (exclusive)
                 if (i - start > 1) {
-                    const long long tp = start + (i - start) / 2;
+                    const I tp = start + (i - start) / 2;
                     atomicOr(&tm[tp >> 5], 1u << (tp & 31));
                     // per-block trigger count for the ordered compaction (same partition as trig_scatter_kernel)
-                    atomicAdd(&blocksum[(s * wps + (tp >> 5)) / (OFDMX_THREADS * TRIG_WPT)], 1);
+                    atomicAdd(&blocksum[(s * wps + (long long)(tp >> 5)) / (OFDMX_THREADS * TRIG_WPT)], 1);
                     i = (i + cp < n - 1) ? i + cp : n - 1;
                 }
                 i++;                                               // the for-loop increment
                 if (i >= n) break;
                 // next flank the sequential scan would see
-                const long long lim = (i + cp + 2 < n) ? i + cp + 2 : n;
-                const long long j = next_bit(m, i, lim, 1, wps);
+                const I lim = (i + cp + 2 < n) ? i + cp + 2 : n;
+                const I j = next_bit<I>(m, i, lim, 1, wpsI);
                 if (j >= lim) break;                               // >= cp+1 clear bits follow: next start is independent
-                const bool rising_j = !mbit(m, j - 1, n, wps);
-                if (rising_j && bits_clear(m, j - (cp + 1), j, wps)) break;   // independent start: its own thread walks it
+                const bool rising_j = !mbit<I>(m, j - 1, n, wpsI);
+                if (rising_j && bits_clear<I>(m, j - (cp + 1), j, wpsI)) break;   // independent start: its own thread walks it
                 i = j;
             }
         }

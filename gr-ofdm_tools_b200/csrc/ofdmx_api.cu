@@ -55,7 +55,6 @@ struct PlanFields {
     KP kp{};
     std::vector<int> occ_sizes;
     int hl = 0;
-    int nsw = 2;                    // sync words in front of the header symbol (1: sync_word2=())
     size_t frame_smem = 0, tx_smem = 0, sync_fast_smem = 0, frame1k_smem = 0, sync_tma_smem = 0;
     int sync_tma_occ = 3;           // resident CTAs per SM of the TMA sync kernel (persistent grid size)
     bool sync_warp_ok = false;
